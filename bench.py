@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the fem-shell hot path on B200 (contract: see DESIGN.md section 6).
+
+    python bench.py --gpus 1 --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference (oracle)
+    torchrun ... bench.py --gpus N ...                       # one rank per GPU, weak scaling
+
+Workload at N=1 = BASELINE.json configs[1]: meshGen square plate, 1000 x 1000 nodes of DKQ+PLANE
+Quad-4 (998 001 elements, 6 000 000 DOF), clamped edges, uniform pressure, E=1e7 nu=0.3 t=0.5.
+At N>1 every rank owns one such 1000 x 1000-node strip of a 1000 x (1000 N) plate (weak scaling).
+
+A step = one pass of the solve hot path over one load case: rhs for a new pressure amplitude
+(1+sin(tau/25.01), fluid_solver.cpp:192) followed by exactly --iters Jacobi-PCG iterations on the
+device-resident stiffness matrix (2.6 GB, far larger than the 126 MB L2, so nothing is cache
+resident between steps).  value = DOF x iterations / second over all ranks.  The same JSON line
+also carries elements assembled/s (values pass timed over K repetitions), the SpMV roofline, the
+end-to-end number through the host-buffer plugin call, a CPU baseline and time-to-solution.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NU, EM, THICK, QLOAD, PLATE = 0.3, 1.0e7, 0.5, 300.0, 10.0
+METRIC = "CG DOF-iterations/s"
+UNIT = "DOF-iterations/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(fsb, nodes_x, nodes_y):
+    """meshGen: q nx ny 0 0 Lx Ly 1,1,1,1 q0 2 1 z  (clamped = boundary id 1, uniform load)"""
+    return fsb.meshgen("q", nodes_x - 1, nodes_y - 1, 0.0, 0.0, PLATE, PLATE * (nodes_y - 1) / (nodes_x - 1),
+                       (1, 1, 1, 1), QLOAD, 2, 1)
+
+
+def spmv_bytes(n_dof, n_blocks):
+    nnz = 36 * n_blocks
+    actual = 8 * nnz + 4 * n_blocks + 4 * (n_dof // 6 + 1) + 8 * n_dof + 8 * n_dof   # vals + block cols + row ptr + x + y
+    csr_equiv = 12 * nnz + 20 * n_dof                                                 # SURVEY.md section 8d figure
+    return actual, csr_equiv
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """the reference's CPU implementation of the path, restated (oracle/fs_oracle.c; the reference itself
+    needs libMesh+PETSc+MPI, which do not exist in this image) on the box's host cores"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import fso
+    import fem_shell_b200 as fsb   # only for the host-side mesh generator (no GPU work on this arm)
+    threads = fso.max_threads()
+    nodes = args.ref_nodes
+    m = make_workload(fsb, nodes, nodes)
+    om = fso.Mesh(m["xyz"], m["etype"], m["eptr"], m["enodes"], m["bc"])
+    t0 = time.perf_counter()
+    sysm = fso.assemble(om, m["forces"], NU, EM, THICK, threads=threads)
+    t_asm = time.perf_counter() - t0
+    n_dof = 6 * sysm.n_dofnodes
+    iters = args.ref_iters
+    x = None
+    for _ in range(args.warmup):
+        x, _, _ = fso.pcg(sysm, rtol=1e-30, max_its=iters, threads=threads)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        x, its, _ = fso.pcg(sysm, b=sysm.rhs * (1.0 + np.sin(k / 25.01)), rtol=1e-30, max_its=iters, threads=threads)
+    dt = time.perf_counter() - t0
+    value = n_dof * iters * args.steps / dt
+    sample = "%dx%d-node Quad-4 plate (%d DOF), %d Jacobi-PCG iterations per step, OpenMP CSR" % (nodes, nodes, n_dof, iters)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "meshGen %dx%d nodes DKQ+PLANE Quad-4, clamped, uniform pressure" % (nodes, nodes),
+                   "iters_per_step": iters, "pc": "jacobi"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "elements_per_s": om.n_elem / t_asm},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import fem_shell_b200 as fsb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        ids = [fsb.FemShell.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        nccl_id = ids[0]
+
+    nx = args.nodes
+    ny = args.nodes * world                      # weak scaling: one 1000 x 1000-node strip per GPU
+    m = make_workload(fsb, nx, ny)
+    n_nodes, n_elem = m["xyz"].shape[0], m["etype"].size
+    s = fsb.FemShell(device=local_rank, rank=rank, world=world, nccl_id=nccl_id)
+    s.set_material(NU, EM, THICK)
+    t0 = time.perf_counter()
+    s.set_mesh(m["xyz"], m["etype"], m["eptr"], m["enodes"], m["bc"])
+    t_setup = time.perf_counter() - t0
+    s.set_nodal_loads(m["forces"])
+    sz = s.sizes()
+    n_dof = 6 * sz["n_dofnodes"]
+    n_own = sz["own_end"] - sz["own_begin"]
+    stream = torch.cuda.ExternalStream(s.stream, device=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, reps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for k in range(reps):
+            fn(k)
+        e1.record(stream)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- assembly: values pass over all elements (pattern + colouring were built once in set_mesh) ----
+    for _ in range(max(args.warmup, 3)):
+        s.assemble()
+    asm_ms = timed(lambda k: s.assemble(), args.steps) / args.steps
+
+    # ---- the timed region: K steps of (rhs + ITERS PCG iterations) ----
+    iters = args.iters
+
+    def step(k):
+        s.build_rhs(1.0 + np.sin(k / 25.01))
+        s.solve(rtol=1e-30, max_its=iters, pc=fsb.PC_JACOBI, warm_start=False, check_every=iters, allow_not_converged=True)
+
+    for k in range(args.warmup):
+        step(k)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms = timed(step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = n_dof * iters / (ms_per_step * 1e-3)
+
+    # ---- dominant kernel: SpMV, timed alone on the same stream right after the timed region ----
+    spmv_ms = max_over_ranks(s.bench_spmv(50))
+    actual_b, csr_b = spmv_bytes(6 * n_own, sz["n_blocks"])
+    peak, peak_src = peaks()
+    achieved = actual_b / (spmv_ms * 1e-3) / 1e9
+
+    # ---- end to end through the host-buffer plugin call (loads in, displacements out) ----
+    F_host = torch.empty((n_nodes, 6), dtype=torch.float64).pin_memory()
+    F_host.copy_(torch.from_numpy(m["forces"]))
+    sols_host = torch.empty((n_nodes, 6), dtype=torch.float64).pin_memory()
+    Fh, Sh = F_host.numpy(), sols_host.numpy()
+
+    def e2e_step(k):
+        s.solve_host(Fh, Sh, reassemble=True, rtol=1e-30, max_its=iters, pc=fsb.PC_JACOBI, warm_start=False,
+                     check_every=iters, allow_not_converged=True)
+
+    for k in range(min(args.warmup, 3)):
+        e2e_step(k)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        e2e_step(k)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = n_dof * iters * args.steps / e2e_s
+
+    # ---- time to solution (assemble + PCG to rtol 1e-8), bounded ----
+    tts = None
+    if args.tts != "off":
+        per_iter_ms = ms_per_step / iters
+        cap = int(max(1000, min(args.tts_max_s * 1e3 / per_iter_ms, 5e6)))
+        s.build_rhs(1.0)
+        barrier()
+        t0 = time.perf_counter()
+        a_ms = s.assemble()
+        info = s.solve(rtol=1e-8, max_its=cap, pc=fsb.PC_JACOBI, warm_start=False, check_every=256, allow_not_converged=True)
+        barrier()
+        tts = {"seconds": time.perf_counter() - t0, "assemble_ms": a_ms, "solve_ms": info.solve_ms, "iterations": info.iterations,
+               "rel_residual": info.rel_residual, "converged": info.status == 0, "rtol": 1e-8, "iteration_cap": cap}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline on the host cores (rank 0, N=1 only): the oracle on a bounded sample ----
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from oracle import fso
+        threads = fso.max_threads()
+        om = fso.Mesh(m["xyz"], m["etype"], m["eptr"], m["enodes"], m["bc"])
+        t0 = time.perf_counter()
+        sysm = fso.assemble(om, m["forces"], NU, EM, THICK, threads=threads)
+        t_asm = time.perf_counter() - t0
+        c_it = args.cpu_iters
+        fso.pcg(sysm, rtol=1e-30, max_its=2, threads=threads)
+        t0 = time.perf_counter()
+        fso.pcg(sysm, rtol=1e-30, max_its=c_it, threads=threads)
+        t_cg = time.perf_counter() - t0
+        cpu = {"value": n_dof * c_it / t_cg, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "same %dx%d-node system: full values pass + %d Jacobi-PCG iterations (OpenMP over rows)" % (nx, ny, c_it),
+               "elements_per_s": n_elem / t_asm}
+
+    launches_per_step = 3 + 3 * iters           # rhs, spmv(x0), init, then (spmv+dot, update, direction) per iteration
+    if world > 1:
+        launches_per_step += 2 + 3 * iters      # pack + finalise kernels around the NCCL calls
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: meshGen %dx%d nodes DKQ+PLANE Quad-4 (%d elements, %d DOF), clamped, uniform pressure%s"
+                   % (nx, ny, n_elem, n_dof, "" if world == 1 else " = one 1000x1000-node strip per GPU"),
+                   "iters_per_step": iters, "pc": "jacobi", "dof_order": "first_encounter",
+                   "l2_policy": "inputs larger than L2 (matrix %.2f GB per GPU streamed every iteration)" % (8e-9 * 36 * sz["n_blocks"]),
+                   "parallelism": "node-block strips x%d" % world},
+        "metrics": {"cg_dof_iterations_per_s": value, "elements_assembled_per_s": n_elem / (asm_ms * 1e-3),
+                    "assemble_ms": asm_ms, "time_to_solution": tts, "setup_s_pattern_colouring_upload": t_setup,
+                    "colors": sz["n_colors"]},
+        "roofline": {"bound": "hbm", "kernel": "k_spmv", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "bytes_per_launch": actual_b, "csr_equiv_bytes_per_launch": csr_b,
+                     "csr_equiv_gbs": csr_b / (spmv_ms * 1e-3) / 1e9, "ms_per_launch": spmv_ms,
+                     "share_of_step": spmv_ms * (iters + 1) / ms_per_step, "traffic": args.traffic},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(Fh.nbytes if world == 1 else 48 * n_own),
+                "d2h_bytes_per_step": int(Sh.nbytes), "includes": "loads H2D, values re-assembly, %d PCG iterations, displacements D2H" % iters},
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nodes", type=int, default=1000, help="nodes per side of one GPU's strip")
+    ap.add_argument("--iters", type=int, default=200, help="PCG iterations per step")
+    ap.add_argument("--tts", default="auto", choices=["auto", "on", "off"])
+    ap.add_argument("--tts-max-s", type=float, default=90.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-iters", type=int, default=30)
+    ap.add_argument("--ref-nodes", type=int, default=1000)
+    ap.add_argument("--ref-iters", type=int, default=10)
+    ap.add_argument("--traffic", type=float, default=None, help="dram bytes/launch of k_spmv from an ncu --set full capture")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

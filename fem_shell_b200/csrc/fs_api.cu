@@ -1,0 +1,622 @@
+// fs_api.cu -- the C ABI of include/femshell_b200.h: context life cycle, mesh ingestion (DOF map,
+// Dirichlet sets, node-block partition, halo lists), loads, solution gather, exports.
+// Reference anchors are given per function in the header; host-side restatements here follow
+//   DOF numbering      libMesh DofMap as used at fs.cpp:125,1205
+//   Dirichlet sets     fs.cpp:90-120
+//   interface nodes    fsp.cpp:55-71
+//   solution layout    fs.cpp:140-141,163-169
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "fs_context.hpp"
+
+using namespace fs;
+
+#define FS_TRY(expr)               \
+    do {                           \
+        int rc__ = (expr);         \
+        if (rc__ != FS_OK) return rc__; \
+    } while (0)
+
+#define FS_CHECK_CTX(c) \
+    if (!(c)) return FS_ERR_ARG
+
+static inline unsigned int nblk(int64_t n, int bs) { return (unsigned int)((n + bs - 1) / bs); }
+
+extern "C" {
+
+int fs_create(fs_context **out, int device)
+{
+    if (!out) return FS_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return FS_ERR_CUDA;  // no CPU fallback
+    fs_context *c = new (std::nothrow) fs_context();
+    if (!c) return FS_ERR_ARG;
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+        cudaMallocHost((void **)&c->h_state, sizeof(CgState)) != cudaSuccess) {
+        delete c;
+        return FS_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    if (c->d_state.alloc(1) != cudaSuccess || c->d_counter.alloc(1) != cudaSuccess) {
+        delete c;
+        return FS_ERR_CUDA;
+    }
+    solver_query_occupancy(c);
+    *out = c;
+    return FS_OK;
+}
+
+int fs_destroy(fs_context *c)
+{
+    FS_CHECK_CTX(c);
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm) ncclCommDestroy((ncclComm_t)c->comm);
+    if (c->h_state) cudaFreeHost(c->h_state);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    cudaStream_t st = c->stream;
+    delete c;  // frees the device buffers
+    if (st) cudaStreamDestroy(st);
+    return FS_OK;
+}
+
+const char *fs_last_error(const fs_context *c) { return c ? c->err.c_str() : "null context"; }
+
+void *fs_get_stream(fs_context *c) { return c ? (void *)c->stream : nullptr; }
+
+int fs_dist_unique_id(uint8_t id_out[128])
+{
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) return FS_ERR_COMM;
+    memcpy(id_out, &id, 128);
+    return FS_OK;
+}
+
+int fs_dist_init(fs_context *c, int rank, int world, const uint8_t id_bytes[128])
+{
+    FS_CHECK_CTX(c);
+    if (world < 1 || rank < 0 || rank >= world) return fail(c, FS_ERR_ARG, "bad rank/world");
+    if (c->n_nodes) return fail(c, FS_ERR_STATE, "fs_dist_init must precede fs_set_mesh");
+    c->rank = rank;
+    c->world = world;
+    if (world > 1) {
+        FS_CUDA(c, cudaSetDevice(c->device));
+        ncclUniqueId id;
+        memcpy(&id, id_bytes, 128);
+        ncclComm_t comm;
+        ncclResult_t r = ncclCommInitRank(&comm, world, id, rank);
+        if (r != ncclSuccess) return fail(c, FS_ERR_COMM, std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
+        c->comm = (ncclComm *)comm;
+    }
+    return FS_OK;
+}
+
+int fs_set_material(fs_context *c, double nu, double E, double t)
+{
+    FS_CHECK_CTX(c);
+    if (!(E > 0.0) || !(t > 0.0) || !(nu > -1.0 && nu < 1.0)) return fail(c, FS_ERR_ARG, "material out of range");
+    c->nu = nu; c->E = E; c->thickness = t;
+    c->material_set = true;
+    c->assembled = false;
+    return FS_OK;
+}
+
+int fs_set_quirks(fs_context *c, int q)
+{
+    FS_CHECK_CTX(c);
+    c->quirks = q & FS_QUIRKS_REFERENCE;
+    c->assembled = false;
+    return FS_OK;
+}
+
+int fs_set_dof_order(fs_context *c, int mode)
+{
+    FS_CHECK_CTX(c);
+    if (mode != FS_DOF_FIRST_ENCOUNTER && mode != FS_DOF_NODE_ID) return fail(c, FS_ERR_ARG, "unknown dof order");
+    if (c->n_nodes) return fail(c, FS_ERR_STATE, "fs_set_dof_order must precede fs_set_mesh");
+    c->dof_mode = mode;
+    return FS_OK;
+}
+
+int fs_set_assembly_mode(fs_context *c, int mode)
+{
+    FS_CHECK_CTX(c);
+    if (mode != FS_ASM_COLORED && mode != FS_ASM_GATHER) return fail(c, FS_ERR_ARG, "unknown assembly mode");
+    c->asm_mode = mode;
+    return FS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mesh ingestion
+// ---------------------------------------------------------------------------------------------
+static int owner_of(int64_t g, int64_t n_g, int world)
+{
+    // rank r owns [r*n_g/world, (r+1)*n_g/world)
+    int r = (int)((g * world) / n_g);
+    while (r > 0 && g < (int64_t)r * n_g / world) r--;
+    while (r < world - 1 && g >= (int64_t)(r + 1) * n_g / world) r++;
+    return r;
+}
+
+int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_elem, const int32_t *etype,
+                const int64_t *eptr, const int32_t *enodes, int64_t n_bc, const int32_t *bc)
+{
+    FS_CHECK_CTX(c);
+    if (n_nodes <= 0 || n_elem <= 0 || !xyz || !etype || !eptr || !enodes || (n_bc > 0 && !bc))
+        return fail(c, FS_ERR_ARG, "empty mesh or null array");
+    if (n_nodes >= (int64_t)1 << 31 || n_elem >= (int64_t)1 << 31) return fail(c, FS_ERR_ARG, "mesh too large for 32-bit ids");
+    FS_CUDA(c, cudaSetDevice(c->device));
+    for (int64_t e = 0; e < n_elem; e++) {
+        int nen = (int)(eptr[e + 1] - eptr[e]);
+        if ((etype[e] == FS_TRI3 && nen != 3) || (etype[e] == FS_QUAD4 && nen != 4) ||
+            (etype[e] != FS_TRI3 && etype[e] != FS_QUAD4))
+            return fail(c, FS_ERR_ARG, "element " + std::to_string(e) + ": only TRI3 (3) and QUAD4 (5) are supported");
+        for (int64_t k = eptr[e]; k < eptr[e + 1]; k++)
+            if (enodes[k] < 0 || enodes[k] >= n_nodes) return fail(c, FS_ERR_ARG, "node id out of range in element " + std::to_string(e));
+    }
+    c->n_nodes = n_nodes;
+    c->n_elem = n_elem;
+    c->pattern_ready = c->assembled = c->loads_set = c->rhs_ready = c->have_solution = false;
+
+    // ---- DOF order (a12) ----
+    c->dofnode.assign(n_nodes, -1);
+    int64_t next = 0;
+    if (c->dof_mode == FS_DOF_FIRST_ENCOUNTER) {
+        for (int64_t k = 0; k < eptr[n_elem]; k++)
+            if (c->dofnode[enodes[k]] < 0) c->dofnode[enodes[k]] = (int32_t)next++;
+    } else {
+        for (int64_t k = 0; k < eptr[n_elem]; k++) c->dofnode[enodes[k]] = 0;
+        for (int64_t i = 0; i < n_nodes; i++)
+            if (c->dofnode[i] == 0) c->dofnode[i] = (int32_t)next++;
+    }
+    const int64_t n_g = next;
+    c->n_dofnodes_global = n_g;
+    c->node_of_dof.assign(n_g, -1);
+    for (int64_t i = 0; i < n_nodes; i++)
+        if (c->dofnode[i] >= 0) c->node_of_dof[c->dofnode[i]] = (int32_t)i;
+
+    // ---- Dirichlet bits (fs.cpp:90-120) and coupling interface (fsp.cpp:55-71) ----
+    c->node_mask.assign(n_nodes, 0);
+    std::vector<uint8_t> is_if(n_nodes, 0);
+    for (int64_t i = 0; i < n_bc; i++) {
+        const int32_t e = bc[3 * i], s = bc[3 * i + 1], id = bc[3 * i + 2];
+        if (e < 0 || e >= n_elem) return fail(c, FS_ERR_ARG, "boundary record " + std::to_string(i) + ": element out of range");
+        const int nen = (int)(eptr[e + 1] - eptr[e]);
+        if (s < 0 || s >= nen) return fail(c, FS_ERR_ARG, "boundary record " + std::to_string(i) + ": side out of range");
+        const int32_t n0 = enodes[eptr[e] + s], n1 = enodes[eptr[e] + (s + 1) % nen];
+        uint8_t m = 0;
+        if (id == 0 || id == 20) m = 0x07;
+        if (id == 1 || id == 21) m = 0x3f;
+        c->node_mask[n0] |= m;
+        c->node_mask[n1] |= m;
+        if (id == 2 || id == 20 || id == 21) is_if[n0] = is_if[n1] = 1;
+    }
+    c->iface_nodes.clear();
+    for (int64_t i = 0; i < n_nodes; i++)
+        if (is_if[i]) c->iface_nodes.push_back((int32_t)i);
+    c->sols.assign(6 * n_nodes, 0.0);
+    c->pre_sols.assign(6 * n_nodes, 0.0);
+
+    // ---- node-block partition of the DOF order ----
+    const int W = c->world, R = c->rank;
+    if (n_g < W) return fail(c, FS_ERR_ARG, "fewer nodes than ranks");
+    c->own_begin = (int64_t)R * n_g / W;
+    c->own_end = (int64_t)(R + 1) * n_g / W;
+    c->n_own = c->own_end - c->own_begin;
+
+    // local elements = elements touching an owned node; local nodes = their nodes + owned nodes
+    std::vector<uint8_t> is_local_node(n_g, 0);
+    for (int64_t g = c->own_begin; g < c->own_end; g++) is_local_node[g] = 1;
+    std::vector<int32_t> loc_elems;
+    std::vector<std::vector<int32_t>> send(W);
+    for (int64_t e = 0; e < n_elem; e++) {
+        bool mine = false;
+        int owners[4];
+        const int nen = (int)(eptr[e + 1] - eptr[e]);
+        for (int k = 0; k < nen; k++) {
+            int64_t g = c->dofnode[enodes[eptr[e] + k]];
+            owners[k] = (W == 1) ? 0 : owner_of(g, n_g, W);
+            mine = mine || owners[k] == R;
+        }
+        if (!mine) continue;
+        loc_elems.push_back((int32_t)e);
+        for (int k = 0; k < nen; k++) {
+            int32_t g = c->dofnode[enodes[eptr[e] + k]];
+            is_local_node[g] = 1;
+            if (owners[k] == R)
+                for (int l = 0; l < nen; l++)
+                    if (owners[l] != R) send[owners[l]].push_back(g);
+        }
+    }
+    c->local_to_global.clear();
+    for (int64_t g = 0; g < n_g; g++)
+        if (is_local_node[g]) c->local_to_global.push_back((int32_t)g);
+    c->n_local = (int64_t)c->local_to_global.size();
+    std::vector<int32_t> g2l(n_g, -1);
+    for (int64_t l = 0; l < c->n_local; l++) g2l[c->local_to_global[l]] = (int32_t)l;
+    c->own_lo = g2l[c->own_begin];
+
+    // halo lists: recv segments are contiguous per owner because local order == global order
+    c->peers.clear();
+    c->send_total = 0;
+    std::vector<int32_t> send_idx;
+    for (int r = 0; r < W; r++) {
+        if (r == R) continue;
+        Peer pr;
+        pr.rank = r;
+        auto &s = send[r];
+        std::sort(s.begin(), s.end());
+        s.erase(std::unique(s.begin(), s.end()), s.end());
+        pr.send_count = (int64_t)s.size();
+        pr.send_off = c->send_total;
+        for (int32_t g : s) send_idx.push_back(g2l[g]);
+        c->send_total += pr.send_count;
+        const int64_t rb = (int64_t)r * n_g / W, re = (int64_t)(r + 1) * n_g / W;
+        int64_t first = -1, cnt = 0;
+        for (int64_t l = 0; l < c->n_local; l++) {
+            int32_t g = c->local_to_global[l];
+            if (g >= rb && g < re) {
+                if (first < 0) first = l;
+                cnt++;
+            }
+        }
+        pr.recv_count = cnt;
+        pr.recv_off = first < 0 ? 0 : first;
+        if (pr.send_count || pr.recv_count) c->peers.push_back(pr);
+    }
+    FS_CUDA(c, c->d_send_idx.alloc(send_idx.size()));
+    FS_CUDA(c, c->d_sendbuf.alloc(6 * send_idx.size()));
+    if (!send_idx.empty())
+        FS_CUDA(c, cudaMemcpy(c->d_send_idx.p, send_idx.data(), sizeof(int32_t) * send_idx.size(), cudaMemcpyHostToDevice));
+
+    // ---- device mesh in local numbering ----
+    std::vector<double> lxyz(3 * c->n_local);
+    std::vector<uint8_t> lmask(c->n_local);
+    for (int64_t l = 0; l < c->n_local; l++) {
+        int32_t node = c->node_of_dof[c->local_to_global[l]];
+        lxyz[3 * l + 0] = xyz[3 * (int64_t)node + 0];
+        lxyz[3 * l + 1] = xyz[3 * (int64_t)node + 1];
+        lxyz[3 * l + 2] = xyz[3 * (int64_t)node + 2];
+        lmask[l] = c->node_mask[node];
+    }
+    FS_CUDA(c, c->d_xyz.alloc(3 * c->n_local));
+    FS_CUDA(c, c->d_mask.alloc(c->n_local));
+    FS_CUDA(c, cudaMemcpy(c->d_xyz.p, lxyz.data(), sizeof(double) * 3 * c->n_local, cudaMemcpyHostToDevice));
+    FS_CUDA(c, cudaMemcpy(c->d_mask.p, lmask.data(), c->n_local, cudaMemcpyHostToDevice));
+
+    std::vector<int32_t> tri, quad, tri_gid, quad_gid;
+    for (int32_t e : loc_elems) {
+        const int nen = (int)(eptr[e + 1] - eptr[e]);
+        auto &dst = (nen == 3) ? tri : quad;
+        for (int k = 0; k < nen; k++) dst.push_back(g2l[c->dofnode[enodes[eptr[e] + k]]]);
+        ((nen == 3) ? tri_gid : quad_gid).push_back(e);
+    }
+    c->n_tri = (int64_t)tri_gid.size();
+    c->n_quad = (int64_t)quad_gid.size();
+
+    // node ids of the owned dof-nodes and the node-id span they cover (load staging)
+    std::vector<int32_t> node_of_own(c->n_own);
+    int64_t lo = n_nodes, hi = -1;
+    for (int64_t p = 0; p < c->n_own; p++) {
+        int32_t node = c->node_of_dof[c->own_begin + p];
+        node_of_own[p] = node;
+        lo = std::min<int64_t>(lo, node);
+        hi = std::max<int64_t>(hi, node);
+    }
+    c->span_lo = lo;
+    c->span_n = hi - lo + 1;
+    FS_CUDA(c, c->d_node_of_own.alloc(c->n_own));
+    FS_CUDA(c, cudaMemcpy(c->d_node_of_own.p, node_of_own.data(), sizeof(int32_t) * c->n_own, cudaMemcpyHostToDevice));
+    FS_CUDA(c, c->d_stage.alloc(6 * c->span_n));
+    FS_CUDA(c, c->d_F.alloc(6 * c->n_own));
+    FS_CUDA(c, cudaMemset(c->d_F.p, 0, sizeof(double) * 6 * c->n_own));
+    for (DevBuf<double> *v : {&c->d_b, &c->d_x, &c->d_r, &c->d_p, &c->d_q, &c->d_z}) {
+        FS_CUDA(c, v->alloc(6 * c->n_local));
+        FS_CUDA(c, cudaMemset(v->p, 0, sizeof(double) * 6 * c->n_local));
+    }
+    c->d_full.release();
+    return build_pattern(c, tri, quad, tri_gid, quad_gid);
+}
+
+// ---------------------------------------------------------------------------------------------
+// loads
+// ---------------------------------------------------------------------------------------------
+__global__ void k_loads_from_stage(int64_t n_own, const int32_t *__restrict__ node_of_own, int64_t span_lo,
+                                   const double *__restrict__ stage, double *__restrict__ F)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= 6 * n_own) return;
+    int64_t p = i / 6;
+    int v = (int)(i - 6 * p);
+    F[i] = stage[6 * ((int64_t)node_of_own[p] - span_lo) + v];
+}
+
+int fs_set_nodal_loads(fs_context *c, const double *F)
+{
+    FS_CHECK_CTX(c);
+    if (!c->pattern_ready) return fail(c, FS_ERR_STATE, "fs_set_nodal_loads before fs_set_mesh");
+    if (!F) return fail(c, FS_ERR_ARG, "null loads");
+    FS_CUDA(c, cudaSetDevice(c->device));
+    FS_CUDA(c, cudaMemcpyAsync(c->d_stage.p, F + 6 * c->span_lo, sizeof(double) * 6 * c->span_n, cudaMemcpyHostToDevice, c->stream));
+    k_loads_from_stage<<<nblk(6 * c->n_own, 256), 256, 0, c->stream>>>(c->n_own, c->d_node_of_own.p, c->span_lo, c->d_stage.p, c->d_F.p);
+    FS_CUDA(c, cudaGetLastError());
+    c->loads_set = true;
+    return build_rhs(c, 1.0);
+}
+
+int fs_set_interface_loads(fs_context *c, int64_t n, const int32_t *node_ids, int dims, char dead_axis, const double *f)
+{
+    FS_CHECK_CTX(c);
+    if (!c->pattern_ready) return fail(c, FS_ERR_STATE, "fs_set_interface_loads before fs_set_mesh");
+    if (dims != 2 && dims != 3) return fail(c, FS_ERR_ARG, "dims must be 2 or 3");
+    if (dims == 2 && dead_axis != 'x' && dead_axis != 'y' && dead_axis != 'z')
+        return fail(c, FS_ERR_ARG, "2-D coupling needs dead axis x, y or z (fsp.cpp:92-98)");
+    if (n > 0 && (!node_ids || !f)) return fail(c, FS_ERR_ARG, "null interface arrays");
+    // fsp.cpp:1400-1432: only interface nodes carry load; map the 2 or 3 values onto u,v,w
+    int c0 = 0, c1 = 1;
+    if (dims == 2) {
+        if (dead_axis == 'y') { c0 = 0; c1 = 2; }
+        else if (dead_axis == 'x') { c0 = 1; c1 = 2; }
+    }
+    std::vector<double> stage((size_t)6 * c->span_n, 0.0);
+    for (int64_t i = 0; i < n; i++) {
+        int64_t node = node_ids[i];
+        if (node < 0 || node >= c->n_nodes) return fail(c, FS_ERR_ARG, "interface node id out of range");
+        if (node < c->span_lo || node >= c->span_lo + c->span_n) continue;
+        double *dst = &stage[6 * (node - c->span_lo)];
+        if (dims == 3) {
+            dst[0] = f[3 * i]; dst[1] = f[3 * i + 1]; dst[2] = f[3 * i + 2];
+        } else {
+            dst[c0] = f[2 * i]; dst[c1] = f[2 * i + 1];
+        }
+    }
+    FS_CUDA(c, cudaSetDevice(c->device));
+    FS_CUDA(c, cudaMemcpyAsync(c->d_stage.p, stage.data(), sizeof(double) * stage.size(), cudaMemcpyHostToDevice, c->stream));
+    k_loads_from_stage<<<nblk(6 * c->n_own, 256), 256, 0, c->stream>>>(c->n_own, c->d_node_of_own.p, c->span_lo, c->d_stage.p, c->d_F.p);
+    FS_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->loads_set = true;
+    return build_rhs(c, 1.0);
+}
+
+int fs_build_rhs(fs_context *c, double scale)
+{
+    FS_CHECK_CTX(c);
+    FS_CUDA(c, cudaSetDevice(c->device));
+    return build_rhs(c, scale);
+}
+
+// ---------------------------------------------------------------------------------------------
+// hot path
+// ---------------------------------------------------------------------------------------------
+int fs_assemble(fs_context *c, float *ms)
+{
+    FS_CHECK_CTX(c);
+    if (!c->pattern_ready) return fail(c, FS_ERR_STATE, "fs_assemble before fs_set_mesh");
+    if (!c->material_set) return fail(c, FS_ERR_STATE, "fs_assemble before fs_set_material");
+    FS_CUDA(c, cudaSetDevice(c->device));
+    return assemble_values(c, ms);
+}
+
+static void default_opts(fs_solve_opts &o)
+{
+    o.rtol = 1e-12;   // libMesh default TOLERANCE^2 (fs.cpp:130-133 leave it untouched)
+    o.max_its = 5000;
+    o.pc = FS_PC_JACOBI;
+    o.norm_type = FS_NORM_UNPRECONDITIONED;
+    o.warm_start = 1;
+    o.check_every = 0;
+}
+
+int fs_solve(fs_context *c, const fs_solve_opts *opts, fs_solve_info *info)
+{
+    FS_CHECK_CTX(c);
+    fs_solve_opts o;
+    if (opts) o = *opts;
+    else default_opts(o);
+    if (!(o.rtol > 0.0) || o.max_its < 0) return fail(c, FS_ERR_ARG, "bad tolerance / iteration limit");
+    FS_CUDA(c, cudaSetDevice(c->device));
+    return solver_run(c, &o, info);
+}
+
+__global__ void k_solution_to_nodes(int64_t n_own, const int32_t *__restrict__ node_of_own,
+                                    const double *__restrict__ x_own, double *__restrict__ full)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= 6 * n_own) return;
+    int64_t p = i / 6;
+    int v = (int)(i - 6 * p);
+    full[6 * (int64_t)node_of_own[p] + v] = x_own[i];
+}
+
+int fs_get_solution(fs_context *c, double *sols)
+{
+    FS_CHECK_CTX(c);
+    if (!c->have_solution) return fail(c, FS_ERR_STATE, "no solution yet");
+    if (!sols) return fail(c, FS_ERR_ARG, "null output");
+    FS_CUDA(c, cudaSetDevice(c->device));
+    if (c->d_full.n < (size_t)6 * c->n_nodes) FS_CUDA(c, c->d_full.alloc(6 * c->n_nodes));
+    FS_CUDA(c, cudaMemsetAsync(c->d_full.p, 0, sizeof(double) * 6 * c->n_nodes, c->stream));
+    k_solution_to_nodes<<<nblk(6 * c->n_own, 256), 256, 0, c->stream>>>(c->n_own, c->d_node_of_own.p,
+                                                                         c->d_x.p + 6 * c->own_lo, c->d_full.p);
+    if (c->world > 1) {
+        ncclResult_t r = ncclAllReduce(c->d_full.p, c->d_full.p, 6 * c->n_nodes, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream);
+        if (r != ncclSuccess) return fail(c, FS_ERR_COMM, std::string("ncclAllReduce: ") + ncclGetErrorString(r));
+    }
+    FS_CUDA(c, cudaMemcpyAsync(sols, c->d_full.p, sizeof(double) * 6 * c->n_nodes, cudaMemcpyDeviceToHost, c->stream));
+    FS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FS_OK;
+}
+
+int fs_solve_host(fs_context *c, const double *F, int reassemble, const fs_solve_opts *opts, double *sols,
+                  fs_solve_info *info)
+{
+    FS_CHECK_CTX(c);
+    if (F) FS_TRY(fs_set_nodal_loads(c, F));
+    if (reassemble || !c->assembled) FS_TRY(fs_assemble(c, nullptr));
+    int rc = fs_solve(c, opts, info);
+    if (rc != FS_OK && rc != FS_ERR_NOT_CONVERGED) return rc;
+    int rc2 = fs_get_solution(c, sols);
+    return rc2 != FS_OK ? rc2 : rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// coupled step (fsp.cpp:257-374)
+// ---------------------------------------------------------------------------------------------
+int fs_interface_nodes(fs_context *c, int64_t *n, int32_t *ids)
+{
+    FS_CHECK_CTX(c);
+    if (!c->n_nodes) return fail(c, FS_ERR_STATE, "no mesh");
+    if (n) *n = (int64_t)c->iface_nodes.size();
+    if (ids) memcpy(ids, c->iface_nodes.data(), sizeof(int32_t) * c->iface_nodes.size());
+    return FS_OK;
+}
+
+static void axis_components(int dims, char dead_axis, int comp[3])
+{
+    comp[0] = 0; comp[1] = 1; comp[2] = 2;
+    if (dims == 2) {
+        if (dead_axis == 'y') { comp[0] = 0; comp[1] = 2; }
+        else if (dead_axis == 'x') { comp[0] = 1; comp[1] = 2; }
+    }
+}
+
+int fs_step(fs_context *c, int dims, char dead_axis, const double *forces_in, const fs_solve_opts *opts,
+            double *displ_out, fs_solve_info *info)
+{
+    FS_CHECK_CTX(c);
+    if (!forces_in || !displ_out) return fail(c, FS_ERR_ARG, "null coupling arrays");
+    const int64_t nif = (int64_t)c->iface_nodes.size();
+    FS_TRY(fs_set_interface_loads(c, nif, c->iface_nodes.data(), dims, dead_axis, forces_in));
+    if (!c->assembled) FS_TRY(fs_assemble(c, nullptr));  // K is constant across coupling iterations
+    int rc = fs_solve(c, opts, info);
+    if (rc != FS_OK && rc != FS_ERR_NOT_CONVERGED) return rc;
+    FS_TRY(fs_get_solution(c, c->sols.data()));
+    int comp[3];
+    axis_components(dims, dead_axis, comp);
+    for (int64_t i = 0; i < nif; i++) {  // fsp.cpp:286-317
+        const int64_t id = c->iface_nodes[i];
+        for (int d = 0; d < dims; d++) displ_out[i * dims + d] = c->sols[6 * id + comp[d]] - c->pre_sols[6 * id + comp[d]];
+    }
+    return rc;
+}
+
+int fs_commit_step(fs_context *c, int dims, char dead_axis)
+{
+    FS_CHECK_CTX(c);
+    if (dims != 2 && dims != 3) return fail(c, FS_ERR_ARG, "dims must be 2 or 3");
+    int comp[3];
+    axis_components(dims, dead_axis, comp);
+    for (int32_t id : c->iface_nodes)  // fsp.cpp:347-368
+        for (int d = 0; d < dims; d++) c->pre_sols[6 * (int64_t)id + comp[d]] = c->sols[6 * (int64_t)id + comp[d]];
+    return FS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// parity / inspection
+// ---------------------------------------------------------------------------------------------
+int fs_get_sizes(fs_context *c, int64_t *n_dofnodes, int64_t *n_blocks, int64_t *n_colors, int64_t *own_begin, int64_t *own_end)
+{
+    FS_CHECK_CTX(c);
+    if (!c->pattern_ready) return fail(c, FS_ERR_STATE, "no mesh");
+    if (n_dofnodes) *n_dofnodes = c->n_dofnodes_global;
+    if (n_blocks) *n_blocks = c->n_blocks;
+    if (n_colors) *n_colors = c->n_colors;
+    if (own_begin) *own_begin = c->own_begin;
+    if (own_end) *own_end = c->own_end;
+    return FS_OK;
+}
+
+int fs_export_dof_order(fs_context *c, int32_t *dofnode)
+{
+    FS_CHECK_CTX(c);
+    if (!c->n_nodes || !dofnode) return fail(c, FS_ERR_STATE, "no mesh");
+    memcpy(dofnode, c->dofnode.data(), sizeof(int32_t) * c->n_nodes);
+    return FS_OK;
+}
+
+int fs_export_csr(fs_context *c, int64_t *rowptr, int32_t *colidx, double *vals)
+{
+    FS_CHECK_CTX(c);
+    if (!c->pattern_ready) return fail(c, FS_ERR_STATE, "no pattern");
+    if (vals && !c->assembled) return fail(c, FS_ERR_STATE, "values requested before fs_assemble");
+    FS_CUDA(c, cudaSetDevice(c->device));
+    std::vector<int32_t> nptr(c->n_own + 1), nadj(c->n_blocks);
+    FS_CUDA(c, cudaMemcpy(nptr.data(), c->d_nptr.p, sizeof(int32_t) * (c->n_own + 1), cudaMemcpyDeviceToHost));
+    FS_CUDA(c, cudaMemcpy(nadj.data(), c->d_nadj.p, sizeof(int32_t) * c->n_blocks, cudaMemcpyDeviceToHost));
+    for (int64_t p = 0; p < c->n_own; p++) {
+        const int64_t deg = nptr[p + 1] - nptr[p];
+        for (int a = 0; a < 6; a++) {
+            const int64_t base = 36 * (int64_t)nptr[p] + a * 6 * deg;
+            if (rowptr) rowptr[6 * p + a] = base;
+            if (colidx)
+                for (int64_t j = 0; j < deg; j++)
+                    for (int b = 0; b < 6; b++)
+                        colidx[base + 6 * j + b] = 6 * c->local_to_global[nadj[nptr[p] + j]] + b;
+        }
+    }
+    if (rowptr) rowptr[6 * c->n_own] = 36 * (int64_t)c->n_blocks;
+    if (vals) FS_CUDA(c, cudaMemcpy(vals, c->d_vals.p, sizeof(double) * 36 * c->n_blocks, cudaMemcpyDeviceToHost));
+    return FS_OK;
+}
+
+int fs_export_rhs(fs_context *c, double *rhs)
+{
+    FS_CHECK_CTX(c);
+    if (!c->rhs_ready) return fail(c, FS_ERR_STATE, "no rhs");
+    FS_CUDA(c, cudaSetDevice(c->device));
+    FS_CUDA(c, cudaStreamSynchronize(c->stream));
+    FS_CUDA(c, cudaMemcpy(rhs, c->d_b.p + 6 * c->own_lo, sizeof(double) * 6 * c->n_own, cudaMemcpyDeviceToHost));
+    return FS_OK;
+}
+
+int fs_debug_element_matrices(fs_context *c, double *out)
+{
+    FS_CHECK_CTX(c);
+    if (!c->pattern_ready || !c->material_set) return fail(c, FS_ERR_STATE, "mesh and material required");
+    if (c->world != 1) return fail(c, FS_ERR_STATE, "single-rank only");
+    FS_CUDA(c, cudaSetDevice(c->device));
+    return debug_element_matrices(c, out);
+}
+
+int fs_spmv_host(fs_context *c, const double *x, double *y)
+{
+    FS_CHECK_CTX(c);
+    if (!c->assembled) return fail(c, FS_ERR_STATE, "not assembled");
+    if (c->world != 1) return fail(c, FS_ERR_STATE, "single-rank only");
+    FS_CUDA(c, cudaSetDevice(c->device));
+    FS_CUDA(c, cudaMemcpyAsync(c->d_p.p, x, sizeof(double) * 6 * c->n_own, cudaMemcpyHostToDevice, c->stream));
+    FS_TRY(spmv_once(c, c->d_p.p, c->d_q.p));
+    FS_CUDA(c, cudaMemcpyAsync(y, c->d_q.p, sizeof(double) * 6 * c->n_own, cudaMemcpyDeviceToHost, c->stream));
+    FS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FS_OK;
+}
+
+int fs_bench_spmv(fs_context *c, int reps, fs_solve_info *info)
+{
+    FS_CHECK_CTX(c);
+    if (!c->assembled || reps <= 0 || !info) return fail(c, FS_ERR_STATE, "not assembled / bad reps");
+    FS_CUDA(c, cudaSetDevice(c->device));
+    FS_TRY(spmv_once(c, c->d_b.p, c->d_q.p));  // warm-up
+    FS_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < reps; i++) FS_TRY(spmv_once(c, c->d_b.p, c->d_q.p));
+    FS_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    FS_CUDA(c, cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    FS_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    info->spmv_ms = ms / reps;
+    return FS_OK;
+}
+
+}  // extern "C"

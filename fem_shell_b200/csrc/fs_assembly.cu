@@ -1,0 +1,577 @@
+// fs_assembly.cu -- sparsity pattern, element colouring and the stiffness values pass.
+//
+// Replaces, on the device, what the reference does per element inside assemble_elasticity
+// (fs.cpp:1160-1233) through libMesh/PETSc: dof_indices (fs.cpp:1205), the element routines
+// (fs.cpp:1211-1221), constrain_element_matrix_and_vector (fs.cpp:1227) and
+// SparseMatrix::add_matrix -> MatSetValues(ADD_VALUES) (fs.cpp:1230), plus the sparsity pattern
+// libMesh builds in equation_systems.init() (fs.cpp:125).
+//
+// Matrix layout in HBM ("block-CSR"): a genuine scalar CSR whose pattern is a dense 6x6 block
+// per node pair sharing an element.  For owned dof-node p with deg = nptr[p+1]-nptr[p] blocks,
+// scalar row 6p+a is the contiguous run  vals[36*nptr[p] + a*6*deg + 6*slot + b]  (slot = position
+// of the column node in the sorted neighbour list, b = column variable).  Column indices are
+// implicit (6*nadj[..]+b) and only materialised by fs_export_csr.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+
+#include "fs_context.hpp"
+#include "fs_elements.cuh"
+
+namespace fs {
+
+// ---------------------------------------------------------------------------------------------
+// pattern build
+// ---------------------------------------------------------------------------------------------
+__global__ void k_count_candidates(const int32_t *__restrict__ conn, int nen, int64_t ne,
+                                   int own_lo, int n_own, unsigned long long *cnt)
+{
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= ne * nen) return;
+    int p = conn[t] - own_lo;
+    if (p >= 0 && p < n_own) atomicAdd(&cnt[p], (unsigned long long)nen);
+}
+
+__global__ void k_fill_candidates(const int32_t *__restrict__ conn, int nen, int64_t ne, int own_lo,
+                                  int n_own, const unsigned long long *__restrict__ off,
+                                  unsigned long long *fill, int32_t *cand)
+{
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= ne * nen) return;
+    int p = conn[t] - own_lo;
+    if (p < 0 || p >= n_own) return;
+    int64_t e = t / nen;
+    unsigned long long slot = atomicAdd(&fill[p], (unsigned long long)nen);
+    for (int l = 0; l < nen; l++) cand[off[p] + slot + l] = conn[e * nen + l];
+}
+
+// one thread per owned row: sort the candidate neighbours, drop duplicates, report the degree
+__global__ void k_sort_unique(int n_own, const unsigned long long *__restrict__ off, int32_t *cand,
+                              int32_t *deg)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_own) return;
+    int32_t *a = cand + off[p];
+    int n = (int)(off[p + 1] - off[p]);
+    for (int i = 1; i < n; i++) {
+        int32_t v = a[i];
+        int j = i - 1;
+        while (j >= 0 && a[j] > v) {
+            a[j + 1] = a[j];
+            j--;
+        }
+        a[j + 1] = v;
+    }
+    int u = 0;
+    for (int i = 0; i < n; i++)
+        if (i == 0 || a[i] != a[i - 1]) a[u++] = a[i];
+    deg[p] = u;
+}
+
+__global__ void k_compact(int n_own, const unsigned long long *__restrict__ off,
+                          const int32_t *__restrict__ cand, const int32_t *__restrict__ nptr,
+                          int32_t *nadj)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_own) return;
+    const int32_t *a = cand + off[p];
+    int b = nptr[p], d = nptr[p + 1] - b;
+    for (int i = 0; i < d; i++) nadj[b + i] = a[i];
+}
+
+// slot of node j in the row of node i for every (element, i, j); -1 when row i is not owned
+__global__ void k_positions(const int32_t *__restrict__ conn, int nen, int64_t ne, int own_lo,
+                            int n_own, const int32_t *__restrict__ nptr,
+                            const int32_t *__restrict__ nadj, int32_t *pos)
+{
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= ne * nen * nen) return;
+    int64_t e = t / (nen * nen);
+    int ij = (int)(t % (nen * nen));
+    int i = ij / nen, j = ij % nen;
+    int p = conn[e * nen + i] - own_lo;
+    int32_t res = -1;
+    if (p >= 0 && p < n_own) {
+        int32_t key = conn[e * nen + j];
+        int lo = nptr[p], hi = nptr[p + 1] - 1, base = lo;
+        while (lo <= hi) {
+            int mid = (lo + hi) >> 1;
+            int32_t v = nadj[mid];
+            if (v < key) lo = mid + 1;
+            else if (v > key) hi = mid - 1;
+            else { res = mid - base; break; }
+        }
+    }
+    pos[t] = res;
+}
+
+// ---------------------------------------------------------------------------------------------
+// element colouring (Jones-Plassmann style with hashed priorities): elements of one colour share
+// no node, so their += into the matrix need no atomics.  Deterministic for a given mesh.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long elem_priority(int32_t gid)
+{
+    unsigned int h = (unsigned int)gid * 2654435761u;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+    return ((unsigned long long)h << 32) | (unsigned int)(gid + 1);
+}
+
+__global__ void k_color_bid(const int32_t *__restrict__ conn, const int32_t *__restrict__ gid,
+                            int nen, int64_t ne, const int32_t *__restrict__ color,
+                            unsigned long long *node_best)
+{
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= ne || color[e] >= 0) return;
+    unsigned long long pr = elem_priority(gid[e]);
+    for (int k = 0; k < nen; k++) atomicMax(&node_best[conn[e * nen + k]], pr);
+}
+
+__global__ void k_color_commit(const int32_t *__restrict__ conn, const int32_t *__restrict__ gid,
+                               int nen, int64_t ne, int32_t *color,
+                               const unsigned long long *__restrict__ node_best,
+                               unsigned long long *node_used, unsigned int *remaining, int *overflow)
+{
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= ne || color[e] >= 0) return;
+    unsigned long long pr = elem_priority(gid[e]);
+    unsigned long long used = 0;
+    bool win = true;
+    for (int k = 0; k < nen; k++) {
+        int n = conn[e * nen + k];
+        win = win && (node_best[n] == pr);
+        used |= node_used[n];
+    }
+    if (!win) {
+        atomicAdd(remaining, 1u);
+        return;
+    }
+    if (~used == 0ull) {
+        *overflow = 1;
+        return;
+    }
+    int c = __ffsll((long long)~used) - 1;
+    color[e] = c;
+    // winners of one round never share a node, so these read-modify-writes do not race
+    for (int k = 0; k < nen; k++) node_used[conn[e * nen + k]] |= (1ull << c);
+}
+
+__global__ void k_histogram(const int32_t *__restrict__ color, int64_t ne, unsigned int *hist)
+{
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e < ne) atomicAdd(&hist[color[e]], 1u);
+}
+
+__global__ void k_permute_elems(const int32_t *__restrict__ conn_in, const int32_t *__restrict__ gid_in,
+                                const int32_t *__restrict__ order, int nen, int64_t ne,
+                                int32_t *conn_out, int32_t *gid_out)
+{
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    int32_t src = order[e];
+    for (int k = 0; k < nen; k++) conn_out[e * nen + k] = conn_in[(int64_t)src * nen + k];
+    gid_out[e] = gid_in[src];
+}
+
+__global__ void k_iota(int32_t *a, int64_t n)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) a[i] = (int32_t)i;
+}
+
+static inline unsigned int nblk(int64_t n, int bs) { return (unsigned int)((n + bs - 1) / bs); }
+
+template <class T>
+static int device_exclusive_scan(fs_context *c, const T *in, T *out, int64_t n)
+{
+    size_t bytes = 0;
+    FS_CUDA(c, cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, c->stream));
+    DevBuf<char> tmp;
+    FS_CUDA(c, tmp.alloc(bytes));
+    FS_CUDA(c, cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, n, c->stream));
+    FS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FS_OK;
+}
+
+// colour one element family (both families share node_used so colours are globally consistent)
+static int color_family(fs_context *c, const int32_t *conn, const int32_t *gid, int nen, int64_t ne,
+                        int32_t *color, unsigned long long *node_best, unsigned long long *node_used,
+                        int64_t n_local)
+{
+    if (ne == 0) return FS_OK;
+    DevBuf<unsigned int> rem;
+    DevBuf<int> ovf;
+    FS_CUDA(c, rem.alloc(1));
+    FS_CUDA(c, ovf.alloc(1));
+    FS_CUDA(c, cudaMemsetAsync(ovf.p, 0, sizeof(int), c->stream));
+    FS_CUDA(c, cudaMemsetAsync(color, 0xff, sizeof(int32_t) * ne, c->stream));
+    for (int round = 0; round < 100000; round++) {
+        FS_CUDA(c, cudaMemsetAsync(node_best, 0, sizeof(unsigned long long) * n_local, c->stream));
+        FS_CUDA(c, cudaMemsetAsync(rem.p, 0, sizeof(unsigned int), c->stream));
+        k_color_bid<<<nblk(ne, 256), 256, 0, c->stream>>>(conn, gid, nen, ne, color, node_best);
+        k_color_commit<<<nblk(ne, 256), 256, 0, c->stream>>>(conn, gid, nen, ne, color, node_best,
+                                                              node_used, rem.p, ovf.p);
+        unsigned int h_rem = 0;
+        int h_ovf = 0;
+        FS_CUDA(c, cudaMemcpyAsync(&h_rem, rem.p, sizeof h_rem, cudaMemcpyDeviceToHost, c->stream));
+        FS_CUDA(c, cudaMemcpyAsync(&h_ovf, ovf.p, sizeof h_ovf, cudaMemcpyDeviceToHost, c->stream));
+        FS_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (h_ovf) return fail(c, FS_ERR_ARG, "element colouring needs more than 64 colours");
+        if (h_rem == 0) return FS_OK;
+    }
+    return fail(c, FS_ERR_STATE, "element colouring did not terminate");
+}
+
+static int sort_family_by_color(fs_context *c, DevBuf<int32_t> &conn, DevBuf<int32_t> &gid, int nen,
+                                int64_t ne, const int32_t *color, int64_t n_colors,
+                                std::vector<int64_t> &off)
+{
+    off.assign(n_colors + 1, 0);
+    if (ne == 0) return FS_OK;
+    DevBuf<int32_t> order_in, order_out, color_out, conn2, gid2;
+    DevBuf<unsigned int> hist;
+    FS_CUDA(c, order_in.alloc(ne));
+    FS_CUDA(c, order_out.alloc(ne));
+    FS_CUDA(c, color_out.alloc(ne));
+    FS_CUDA(c, conn2.alloc(ne * nen));
+    FS_CUDA(c, gid2.alloc(ne));
+    FS_CUDA(c, hist.alloc(64));
+    k_iota<<<nblk(ne, 256), 256, 0, c->stream>>>(order_in.p, ne);
+    size_t bytes = 0;
+    FS_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, bytes, color, color_out.p, order_in.p,
+                                               order_out.p, ne, 0, 7, c->stream));
+    DevBuf<char> tmp;
+    FS_CUDA(c, tmp.alloc(bytes));
+    FS_CUDA(c, cub::DeviceRadixSort::SortPairs(tmp.p, bytes, color, color_out.p, order_in.p,
+                                               order_out.p, ne, 0, 7, c->stream));
+    k_permute_elems<<<nblk(ne, 256), 256, 0, c->stream>>>(conn.p, gid.p, order_out.p, nen, ne,
+                                                           conn2.p, gid2.p);
+    FS_CUDA(c, cudaMemsetAsync(hist.p, 0, 64 * sizeof(unsigned int), c->stream));
+    k_histogram<<<nblk(ne, 256), 256, 0, c->stream>>>(color, ne, hist.p);
+    unsigned int h[64];
+    FS_CUDA(c, cudaMemcpyAsync(h, hist.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    FS_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int64_t k = 0; k < n_colors; k++) off[k + 1] = off[k] + h[k];
+    std::swap(conn.p, conn2.p);
+    std::swap(gid.p, gid2.p);
+    return FS_OK;
+}
+
+__global__ void k_max_color(const int32_t *__restrict__ color, int64_t ne, int *mx)
+{
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e < ne) atomicMax(mx, color[e]);
+}
+
+int build_pattern(fs_context *c, const std::vector<int32_t> &tri, const std::vector<int32_t> &quad,
+                  const std::vector<int32_t> &tri_gid, const std::vector<int32_t> &quad_gid)
+{
+    const int64_t nt = c->n_tri, nq = c->n_quad;
+    const int own_lo = (int)c->own_lo, n_own = (int)c->n_own;
+    cudaStream_t st = c->stream;
+    FS_CUDA(c, c->d_tri.alloc(nt * 3));
+    FS_CUDA(c, c->d_quad.alloc(nq * 4));
+    FS_CUDA(c, c->d_tri_gid.alloc(nt));
+    FS_CUDA(c, c->d_quad_gid.alloc(nq));
+    if (nt) {
+        FS_CUDA(c, cudaMemcpyAsync(c->d_tri.p, tri.data(), sizeof(int32_t) * nt * 3, cudaMemcpyHostToDevice, st));
+        FS_CUDA(c, cudaMemcpyAsync(c->d_tri_gid.p, tri_gid.data(), sizeof(int32_t) * nt, cudaMemcpyHostToDevice, st));
+    }
+    if (nq) {
+        FS_CUDA(c, cudaMemcpyAsync(c->d_quad.p, quad.data(), sizeof(int32_t) * nq * 4, cudaMemcpyHostToDevice, st));
+        FS_CUDA(c, cudaMemcpyAsync(c->d_quad_gid.p, quad_gid.data(), sizeof(int32_t) * nq, cudaMemcpyHostToDevice, st));
+    }
+
+    // ---- node adjacency -> nptr / nadj ----
+    DevBuf<unsigned long long> cnt, off, fill;
+    FS_CUDA(c, cnt.alloc(n_own + 1));
+    FS_CUDA(c, off.alloc(n_own + 1));
+    FS_CUDA(c, fill.alloc(n_own + 1));
+    FS_CUDA(c, cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long) * (n_own + 1), st));
+    FS_CUDA(c, cudaMemsetAsync(fill.p, 0, sizeof(unsigned long long) * (n_own + 1), st));
+    if (nt) k_count_candidates<<<nblk(nt * 3, 256), 256, 0, st>>>(c->d_tri.p, 3, nt, own_lo, n_own, cnt.p);
+    if (nq) k_count_candidates<<<nblk(nq * 4, 256), 256, 0, st>>>(c->d_quad.p, 4, nq, own_lo, n_own, cnt.p);
+    int rc = device_exclusive_scan(c, cnt.p, off.p, (int64_t)n_own + 1);
+    if (rc) return rc;
+    unsigned long long total = 0;
+    FS_CUDA(c, cudaMemcpy(&total, off.p + n_own, sizeof total, cudaMemcpyDeviceToHost));
+    DevBuf<int32_t> cand, deg;
+    FS_CUDA(c, cand.alloc(total));
+    FS_CUDA(c, deg.alloc(n_own + 1));
+    FS_CUDA(c, cudaMemsetAsync(deg.p, 0, sizeof(int32_t) * (n_own + 1), st));
+    if (nt) k_fill_candidates<<<nblk(nt * 3, 256), 256, 0, st>>>(c->d_tri.p, 3, nt, own_lo, n_own, off.p, fill.p, cand.p);
+    if (nq) k_fill_candidates<<<nblk(nq * 4, 256), 256, 0, st>>>(c->d_quad.p, 4, nq, own_lo, n_own, off.p, fill.p, cand.p);
+    k_sort_unique<<<nblk(n_own, 128), 128, 0, st>>>(n_own, off.p, cand.p, deg.p);
+    FS_CUDA(c, c->d_nptr.alloc(n_own + 1));
+    rc = device_exclusive_scan(c, deg.p, c->d_nptr.p, (int64_t)n_own + 1);
+    if (rc) return rc;
+    int32_t nb = 0;
+    FS_CUDA(c, cudaMemcpy(&nb, c->d_nptr.p + n_own, sizeof nb, cudaMemcpyDeviceToHost));
+    if (nb < 0) return fail(c, FS_ERR_ARG, "more than 2^31 node blocks on one GPU");
+    c->n_blocks = nb;
+    FS_CUDA(c, c->d_nadj.alloc(nb));
+    k_compact<<<nblk(n_own, 128), 128, 0, st>>>(n_own, off.p, cand.p, c->d_nptr.p, c->d_nadj.p);
+    FS_CUDA(c, cudaStreamSynchronize(st));
+    cand.release();
+
+    // ---- colouring ----
+    DevBuf<unsigned long long> node_best, node_used;
+    DevBuf<int32_t> tcol, qcol;
+    FS_CUDA(c, node_best.alloc(c->n_local));
+    FS_CUDA(c, node_used.alloc(c->n_local));
+    FS_CUDA(c, tcol.alloc(nt));
+    FS_CUDA(c, qcol.alloc(nq));
+    FS_CUDA(c, cudaMemsetAsync(node_used.p, 0, sizeof(unsigned long long) * c->n_local, st));
+    rc = color_family(c, c->d_tri.p, c->d_tri_gid.p, 3, nt, tcol.p, node_best.p, node_used.p, c->n_local);
+    if (rc) return rc;
+    rc = color_family(c, c->d_quad.p, c->d_quad_gid.p, 4, nq, qcol.p, node_best.p, node_used.p, c->n_local);
+    if (rc) return rc;
+    DevBuf<int> mx;
+    FS_CUDA(c, mx.alloc(1));
+    FS_CUDA(c, cudaMemsetAsync(mx.p, 0xff, sizeof(int), st));
+    if (nt) k_max_color<<<nblk(nt, 256), 256, 0, st>>>(tcol.p, nt, mx.p);
+    if (nq) k_max_color<<<nblk(nq, 256), 256, 0, st>>>(qcol.p, nq, mx.p);
+    int h_mx = -1;
+    FS_CUDA(c, cudaMemcpyAsync(&h_mx, mx.p, sizeof h_mx, cudaMemcpyDeviceToHost, st));
+    FS_CUDA(c, cudaStreamSynchronize(st));
+    c->n_colors = h_mx + 1;
+    rc = sort_family_by_color(c, c->d_tri, c->d_tri_gid, 3, nt, tcol.p, c->n_colors, c->tri_color_off);
+    if (rc) return rc;
+    rc = sort_family_by_color(c, c->d_quad, c->d_quad_gid, 4, nq, qcol.p, c->n_colors, c->quad_color_off);
+    if (rc) return rc;
+
+    // ---- scatter slots ----
+    FS_CUDA(c, c->d_tri_pos.alloc(nt * 9));
+    FS_CUDA(c, c->d_quad_pos.alloc(nq * 16));
+    if (nt) k_positions<<<nblk(nt * 9, 256), 256, 0, st>>>(c->d_tri.p, 3, nt, own_lo, n_own, c->d_nptr.p, c->d_nadj.p, c->d_tri_pos.p);
+    if (nq) k_positions<<<nblk(nq * 16, 256), 256, 0, st>>>(c->d_quad.p, 4, nq, own_lo, n_own, c->d_nptr.p, c->d_nadj.p, c->d_quad_pos.p);
+    FS_CUDA(c, c->d_vals.alloc((size_t)36 * c->n_blocks));
+    FS_CUDA(c, cudaStreamSynchronize(st));
+    FS_CUDA(c, cudaGetLastError());
+    c->pattern_ready = true;
+    return FS_OK;
+}
+
+int upload_element_constants(fs_context *c)
+{
+    // fs.cpp:273-294 initMaterialMatrices
+    ElemConst h;
+    const double nu = c->nu;
+    const double fm = c->E / (1.0 - nu * nu);
+    const double fp = c->E * pow(c->thickness, 3.0) / (12.0 * (1.0 - nu * nu));
+    h.dm11 = 1.0 * fm; h.dm12 = nu * fm; h.dm33 = ((1.0 - nu) / 2.0) * fm;
+    h.dp11 = 1.0 * fp; h.dp12 = nu * fp; h.dp33 = ((1.0 - nu) / 2.0) * fp;
+    h.thickness = c->thickness;
+    h.quirks = c->quirks;
+    FS_CUDA(c, cudaMemcpyToSymbolAsync(c_el, &h, sizeof h, 0, cudaMemcpyHostToDevice, c->stream));
+    return FS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// values pass, coloured scatter.  Block = G groups of NEN warps; warp (g, I) handles node row I of
+// 32 consecutive elements; nodal coordinates are staged once per element through shared memory.
+// ---------------------------------------------------------------------------------------------
+template <int NEN>
+struct ScatterSink {
+    double *row;          // start of scalar row 6p+0
+    int L;                // 6*deg
+    const int *slot;      // slot[j]
+    unsigned mrow;        // Dirichlet bits of the row node
+    const unsigned *mcol; // Dirichlet bits of the element's nodes
+    int I;
+    __device__ __forceinline__ void block(int j, const double G[6][6])
+    {
+        double *dst = row + 6 * slot[j];
+        const unsigned mc = mcol[j];
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            double2 *d2 = reinterpret_cast<double2 *>(dst + (size_t)a * L);
+            const bool ra = (mrow >> a) & 1u;
+#pragma unroll
+            for (int h = 0; h < 3; h++) {
+                double v0 = G[a][2 * h], v1 = G[a][2 * h + 1];
+                // fs.cpp:1227: constrained row/column -> 0, constrained diagonal -> 1 (per element)
+                if (ra || ((mc >> (2 * h)) & 1u)) v0 = (ra && j == I && a == 2 * h) ? 1.0 : 0.0;
+                if (ra || ((mc >> (2 * h + 1)) & 1u)) v1 = (ra && j == I && a == 2 * h + 1) ? 1.0 : 0.0;
+                double2 cur = d2[h];
+                cur.x += v0;
+                cur.y += v1;
+                d2[h] = cur;
+            }
+        }
+    }
+};
+
+template <int NEN, int I>
+__device__ __forceinline__ void scatter_row(const double *X, const int32_t *nodes, const int32_t *pos,
+                                            const uint8_t *__restrict__ mask,
+                                            const int32_t *__restrict__ nptr, double *vals, int own_lo)
+{
+    const int p = nodes[I] - own_lo;
+    int slot[NEN];
+    unsigned mcol[NEN];
+#pragma unroll
+    for (int j = 0; j < NEN; j++) {
+        slot[j] = pos[I * NEN + j];
+        mcol[j] = mask[nodes[j]];
+    }
+    if (slot[I] < 0) return;  // row not owned by this rank
+    const int b0 = nptr[p], deg = nptr[p + 1] - b0;
+    ScatterSink<NEN> sink;
+    sink.row = vals + (size_t)36 * b0;
+    sink.L = 6 * deg;
+    sink.slot = slot;
+    sink.mrow = mcol[I];
+    sink.mcol = mcol;
+    sink.I = I;
+    if (NEN == 3) tri_row_blocks<I>(X, sink);
+    else quad_row_blocks<I>(X, sink);
+}
+
+template <int NEN, int GROUPS>
+__global__ void __launch_bounds__(32 * NEN * GROUPS)
+k_assemble_colored(const int32_t *__restrict__ conn, const int32_t *__restrict__ pos, int64_t e_begin,
+                   int64_t e_end, const double *__restrict__ xyz, const uint8_t *__restrict__ mask,
+                   const int32_t *__restrict__ nptr, double *vals, int own_lo)
+{
+    __shared__ double sX[GROUPS * 32][NEN * 3 + 1];
+    __shared__ int32_t sN[GROUPS * 32][NEN];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = warp / NEN, I = warp % NEN;
+    const int le = grp * 32 + lane;
+    const int64_t e = e_begin + (int64_t)blockIdx.x * (GROUPS * 32) + le;
+    const bool live = e < e_end;
+    if (live) {
+        const int32_t n = conn[e * NEN + I];
+        sN[le][I] = n;
+        sX[le][3 * I + 0] = xyz[3 * (size_t)n + 0];
+        sX[le][3 * I + 1] = xyz[3 * (size_t)n + 1];
+        sX[le][3 * I + 2] = xyz[3 * (size_t)n + 2];
+    }
+    __syncthreads();
+    if (!live) return;
+    double X[NEN * 3];
+    int32_t nodes[NEN];
+#pragma unroll
+    for (int k = 0; k < NEN * 3; k++) X[k] = sX[le][k];
+#pragma unroll
+    for (int k = 0; k < NEN; k++) nodes[k] = sN[le][k];
+    const int32_t *ps = pos + e * (NEN * NEN);
+    if (I == 0) scatter_row<NEN, 0>(X, nodes, ps, mask, nptr, vals, own_lo);
+    else if (I == 1) scatter_row<NEN, 1>(X, nodes, ps, mask, nptr, vals, own_lo);
+    else if (I == 2) scatter_row<NEN, 2>(X, nodes, ps, mask, nptr, vals, own_lo);
+    else if (NEN == 4) scatter_row<NEN, (NEN == 4 ? 3 : 0)>(X, nodes, ps, mask, nptr, vals, own_lo);
+}
+
+int assemble_values(fs_context *c, float *ms)
+{
+    cudaStream_t st = c->stream;
+    int rc = upload_element_constants(c);
+    if (rc) return rc;
+    FS_CUDA(c, cudaEventRecord(c->ev0, st));
+    FS_CUDA(c, cudaMemsetAsync(c->d_vals.p, 0, sizeof(double) * 36 * (size_t)c->n_blocks, st));
+    constexpr int G = 2;
+    for (int64_t k = 0; k < c->n_colors; k++) {
+        int64_t t0 = c->tri_color_off[k], t1 = c->tri_color_off[k + 1];
+        if (t1 > t0)
+            k_assemble_colored<3, G><<<nblk(t1 - t0, 32 * G), 96 * G, 0, st>>>(
+                c->d_tri.p, c->d_tri_pos.p, t0, t1, c->d_xyz.p, c->d_mask.p, c->d_nptr.p, c->d_vals.p, (int)c->own_lo);
+        int64_t q0 = c->quad_color_off[k], q1 = c->quad_color_off[k + 1];
+        if (q1 > q0)
+            k_assemble_colored<4, G><<<nblk(q1 - q0, 32 * G), 128 * G, 0, st>>>(
+                c->d_quad.p, c->d_quad_pos.p, q0, q1, c->d_xyz.p, c->d_mask.p, c->d_nptr.p, c->d_vals.p, (int)c->own_lo);
+    }
+    FS_CUDA(c, cudaEventRecord(c->ev1, st));
+    FS_CUDA(c, cudaStreamSynchronize(st));
+    FS_CUDA(c, cudaGetLastError());
+    if (ms) FS_CUDA(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    c->assembled = true;
+    c->minv_kind = -1;
+    return FS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// rhs: every node loads its six values exactly once (fs.cpp:1118-1153); constrained rows -> 0
+// (fs.cpp:1227).  b lives in the local vector layout (offset own_lo).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_build_rhs(int64_t n_own, const double *__restrict__ F, const uint8_t *__restrict__ mask_own,
+                            double scale, double *b_own)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= 6 * n_own) return;
+    int64_t p = i / 6;
+    int v = (int)(i - 6 * p);
+    b_own[i] = ((mask_own[p] >> v) & 1) ? 0.0 : scale * F[i];
+}
+
+int build_rhs(fs_context *c, double scale)
+{
+    if (!c->loads_set) return fail(c, FS_ERR_STATE, "no loads set");
+    k_build_rhs<<<nblk(6 * c->n_own, 256), 256, 0, c->stream>>>(c->n_own, c->d_F.p, c->d_mask.p + c->own_lo, scale,
+                                                                 c->d_b.p + 6 * c->own_lo);
+    FS_CUDA(c, cudaGetLastError());
+    c->rhs_ready = true;
+    return FS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// debug: dense element matrices (node-major, unconstrained) for kernel-level parity tests
+// ---------------------------------------------------------------------------------------------
+template <int NEN>
+struct DenseSink {
+    double *K;  // (6 NEN)^2 row-major
+    int I;
+    __device__ __forceinline__ void block(int j, const double G[6][6])
+    {
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int b = 0; b < 6; b++) K[(size_t)(6 * I + a) * (6 * NEN) + 6 * j + b] = G[a][b];
+    }
+};
+
+template <int NEN>
+__global__ void k_debug_elements(const int32_t *__restrict__ conn, const int32_t *__restrict__ gid,
+                                 int64_t ne, const double *__restrict__ xyz, double *out)
+{
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t e = t / NEN;
+    int I = (int)(t % NEN);
+    if (e >= ne) return;
+    double X[NEN * 3];
+    for (int k = 0; k < NEN; k++) {
+        int n = conn[e * NEN + k];
+        for (int d = 0; d < 3; d++) X[3 * k + d] = xyz[3 * (size_t)n + d];
+    }
+    DenseSink<NEN> sink;
+    sink.K = out + (size_t)576 * gid[e];
+    sink.I = I;
+    if (NEN == 3) {
+        if (I == 0) tri_row_blocks<0>(X, sink);
+        else if (I == 1) tri_row_blocks<1>(X, sink);
+        else tri_row_blocks<2>(X, sink);
+    } else {
+        if (I == 0) quad_row_blocks<0>(X, sink);
+        else if (I == 1) quad_row_blocks<1>(X, sink);
+        else if (I == 2) quad_row_blocks<2>(X, sink);
+        else quad_row_blocks<3>(X, sink);
+    }
+}
+
+int debug_element_matrices(fs_context *c, double *out_host)
+{
+    int rc = upload_element_constants(c);
+    if (rc) return rc;
+    DevBuf<double> out;
+    FS_CUDA(c, out.alloc((size_t)576 * c->n_elem));
+    FS_CUDA(c, cudaMemsetAsync(out.p, 0, sizeof(double) * 576 * c->n_elem, c->stream));
+    if (c->n_tri)
+        k_debug_elements<3><<<nblk(c->n_tri * 3, 96), 96, 0, c->stream>>>(c->d_tri.p, c->d_tri_gid.p, c->n_tri, c->d_xyz.p, out.p);
+    if (c->n_quad)
+        k_debug_elements<4><<<nblk(c->n_quad * 4, 128), 128, 0, c->stream>>>(c->d_quad.p, c->d_quad_gid.p, c->n_quad, c->d_xyz.p, out.p);
+    FS_CUDA(c, cudaMemcpyAsync(out_host, out.p, sizeof(double) * 576 * c->n_elem, cudaMemcpyDeviceToHost, c->stream));
+    FS_CUDA(c, cudaStreamSynchronize(c->stream));
+    FS_CUDA(c, cudaGetLastError());
+    return FS_OK;
+}
+
+}  // namespace fs

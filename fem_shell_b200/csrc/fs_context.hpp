@@ -1,0 +1,173 @@
+// fs_context.hpp -- internal state behind the opaque fs_context of include/femshell_b200.h
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/femshell_b200.h"
+
+struct ncclComm;
+
+namespace fs {
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+};
+
+// CG scalars living on the device; one cache line, read by every kernel of an iteration
+struct CgState {
+    double rz;        // r.z of the current iterate
+    double pq;        // p.Ap
+    double alpha;     // rz / pq
+    double beta;      // rz_new / rz
+    double nrm2;      // ||r||^2 or ||z||^2 after the update (norm_type)
+    double bnorm2;    // ||b||^2 or ||M^-1 b||^2
+    double tol2;      // (rtol)^2
+    long long iter;
+    long long max_its;
+    int done;         // 1 -> all later kernels of the batch are no-ops
+    int status;       // FS_OK / FS_ERR_NOT_CONVERGED / FS_ERR_BREAKDOWN
+};
+
+struct Peer {
+    int rank = -1;
+    int64_t send_count = 0;   // nodes
+    int64_t recv_count = 0;   // nodes
+    int64_t send_off = 0;     // offset (nodes) into the packed send buffer / send index list
+    int64_t recv_off = 0;     // offset (nodes) into the halo segment of the local vector
+};
+
+}  // namespace fs
+
+struct fs_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+
+    // distributed
+    int rank = 0, world = 1;
+    ncclComm *comm = nullptr;
+
+    // material / switches
+    double nu = 0.3, E = 1e7, thickness = 1.0;
+    bool material_set = false;
+    int quirks = FS_QUIRKS_REFERENCE;
+    int dof_mode = FS_DOF_FIRST_ENCOUNTER;
+    int asm_mode = FS_ASM_COLORED;
+
+    // host copy of the (replicated) mesh description that later calls need
+    int64_t n_nodes = 0, n_elem = 0;
+    std::vector<int32_t> dofnode;        // node id -> global dof-node (-1 orphan)
+    std::vector<int32_t> node_of_dof;    // global dof-node -> node id
+    std::vector<uint8_t> node_mask;      // Dirichlet bits per node id
+    std::vector<int32_t> iface_nodes;    // coupling interface nodes (ids 2,20,21), ascending
+    int64_t n_dofnodes_global = 0;
+
+    // rank-local numbering: local nodes = owned + halo dof-nodes sorted by GLOBAL dof-node id, so the
+    // owned range [own_begin, own_end) is the contiguous local range [own_lo, own_lo + n_own) and
+    // local order == global order (the CSR columns stay sorted without a second key)
+    int64_t own_begin = 0, own_end = 0, n_own = 0, n_local = 0, own_lo = 0;
+    std::vector<int32_t> local_to_global;  // local dof-node -> global dof-node
+    int64_t span_lo = 0, span_n = 0;       // node-id span covering the owned nodes (load staging)
+    std::vector<fs::Peer> peers;
+    int64_t send_total = 0;
+
+    // device mesh (local numbering)
+    int64_t n_tri = 0, n_quad = 0;         // local elements (touching owned nodes)
+    fs::DevBuf<double> d_xyz;              // n_local * 3
+    fs::DevBuf<uint8_t> d_mask;            // n_local
+    fs::DevBuf<int32_t> d_tri, d_quad;     // connectivity, local dof-node ids, sorted by colour
+    fs::DevBuf<int32_t> d_tri_pos, d_quad_pos;  // block slot of node j in the row of node i (or -1)
+    fs::DevBuf<int32_t> d_tri_gid, d_quad_gid;  // original element id (debug / determinism)
+    std::vector<int64_t> tri_color_off, quad_color_off;  // n_colors+1 offsets
+    int64_t n_colors = 0;
+    // node -> incident (element,row) lists for the gather assembly
+    fs::DevBuf<int32_t> d_inc_ptr, d_inc;
+
+    // block-CSR matrix of the owned rows: row 6p+a occupies vals[36*nptr[p] + a*6*deg ...]
+    fs::DevBuf<int32_t> d_nptr;            // n_own+1
+    fs::DevBuf<int32_t> d_nadj;            // n_blocks, LOCAL column dof-nodes, ascending in GLOBAL order
+    fs::DevBuf<double> d_vals;             // 36*n_blocks
+    int64_t n_blocks = 0;
+    bool pattern_ready = false, assembled = false;
+
+    // loads / vectors (length 6*n_local unless noted)
+    fs::DevBuf<double> d_F;                // 6*n_own loads in dof order (unconstrained values)
+    fs::DevBuf<double> d_stage;            // 6*span_n node-ordered staging for loads / solution
+    fs::DevBuf<int32_t> d_node_of_own;     // n_own: mesh node id of owned dof-node p
+    fs::DevBuf<double> d_full;             // 6*n_nodes gather buffer (multi-rank solution)
+    fs::DevBuf<double> d_b, d_x, d_r, d_p, d_q, d_z;
+    fs::DevBuf<double> d_minv;             // 6*n_own (Jacobi) or 36*n_own (block)
+    int minv_kind = -1;
+    fs::DevBuf<double> d_partials;         // per-block partial sums
+    fs::DevBuf<fs::CgState> d_state;
+    fs::DevBuf<unsigned int> d_counter;
+    fs::DevBuf<double> d_sendbuf;          // 6*send_total
+    fs::DevBuf<int32_t> d_send_idx;        // send_total local node ids
+    fs::CgState *h_state = nullptr;        // pinned
+    bool loads_set = false, rhs_ready = false, have_solution = false;
+
+    // coupled step
+    std::vector<double> sols, pre_sols;
+
+    int sm_count = 148;
+    int spmv_blocks_per_sm = 4, vec_blocks_per_sm = 4;
+};
+
+namespace fs {
+
+inline int fail(fs_context *c, int code, const std::string &msg)
+{
+    if (c) c->err = msg;
+    return code;
+}
+
+#define FS_CUDA(ctx, call)                                                                     \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fs::fail(ctx, FS_ERR_CUDA,                                                  \
+                            std::string(#call) + ": " + cudaGetErrorString(e__) + " (" +      \
+                                __FILE__ + ":" + std::to_string(__LINE__) + ")");              \
+    } while (0)
+
+// assembly.cu
+int upload_element_constants(fs_context *c);
+int build_pattern(fs_context *c, const std::vector<int32_t> &tri, const std::vector<int32_t> &quad,
+                  const std::vector<int32_t> &tri_gid, const std::vector<int32_t> &quad_gid);
+int assemble_values(fs_context *c, float *ms);
+int build_rhs(fs_context *c, double scale);
+int debug_element_matrices(fs_context *c, double *out_host);
+
+// solver.cu
+int solver_query_occupancy(fs_context *c);
+int solver_prepare(fs_context *c, int pc);
+int solver_run(fs_context *c, const fs_solve_opts *o, fs_solve_info *info);
+int spmv_once(fs_context *c, const double *d_in, double *d_out);
+int halo_exchange(fs_context *c, double *d_vec);
+
+}  // namespace fs

@@ -1,0 +1,254 @@
+// fs_meshio.cpp -- host-side input formats of the path: in-memory meshGen, XDA and load files.
+//
+// Reference anchors:
+//   meshGen            src/meshgen/main_all.cpp:133-387
+//   XDA reader         fs.cpp:37 (libMesh XdrIO, ASCII "libMesh-0.7.0+" layout written at main_all.cpp:233-339)
+//   load file reader   fs.cpp:44-67
+// The generator reproduces the text round trip the reference imposes on its own output: node
+// coordinates and the load factor pass through operator<< of a default std::ostream (6 significant
+// digits, "%g") before fem-shell reads them back (main_all.cpp:261,351,373).
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/femshell_b200.h"
+
+namespace {
+
+double g6(double v)
+{
+    char buf[64];
+    snprintf(buf, sizeof buf, "%g", v);
+    return strtod(buf, nullptr);
+}
+
+// next non-empty line with any "# comment" tail removed
+bool next_line(std::istream &in, std::string &line)
+{
+    while (std::getline(in, line)) {
+        size_t h = line.find('#');
+        if (h != std::string::npos) line.resize(h);
+        if (line.find_first_not_of(" \t\r\n") != std::string::npos) return true;
+    }
+    return false;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fs_meshgen(char kind, int nx, int ny, double min_x, double min_y, double max_x, double max_y,
+               const int bcids[4], double factor, int loading, int ul_lr, char dead_axis, int64_t *n_nodes_o,
+               int64_t *n_elem_o, int64_t *n_bc_o, double *xyz, int32_t *etype, int64_t *eptr, int32_t *enodes,
+               int32_t *bc, double *forces)
+{
+    if (kind == 'Q') kind = 'q';
+    if (kind == 'T') kind = 't';
+    if ((kind != 'q' && kind != 't') || nx <= 0 || ny <= 0 || !bcids) return FS_ERR_ARG;       // main_all.cpp:40-66
+    if (dead_axis != 'x' && dead_axis != 'y' && dead_axis != 'z') return FS_ERR_ARG;           // main_all.cpp:127-131
+    const int t_id = bcids[0], b_id = bcids[1], l_id = bcids[2], r_id = bcids[3];
+    const int64_t n_nodes = (int64_t)(nx + 1) * (ny + 1);
+    const int64_t n_elem = (int64_t)nx * ny * (kind == 't' ? 2 : 1);
+    int64_t n_bc = 0;
+    if (l_id >= 0) n_bc += ny;
+    if (r_id >= 0) n_bc += ny;
+    if (t_id >= 0) n_bc += nx;
+    if (b_id >= 0) n_bc += nx;
+    if (n_nodes_o) *n_nodes_o = n_nodes;
+    if (n_elem_o) *n_elem_o = n_elem;
+    if (n_bc_o) *n_bc_o = n_bc;
+    const int nen = kind == 't' ? 3 : 4;
+    const int64_t W = nx + 1;
+
+    if (xyz) {  // main_all.cpp:141-160
+        const double fracx = (max_x - min_x) / (double)nx, fracy = (max_y - min_y) / (double)ny;
+        std::vector<double> xs(nx + 1), ys(ny + 1);
+        for (int x = 0; x <= nx; x++) xs[x] = g6(min_x + x * fracx);
+        for (int y = 0; y <= ny; y++) ys[y] = g6(min_y + y * fracy);
+        const int pa = dead_axis == 'x' ? 1 : 0, sa = dead_axis == 'z' ? 1 : 2;
+        for (int y = 0; y <= ny; y++)
+            for (int x = 0; x <= nx; x++) {
+                double *p = xyz + 3 * ((int64_t)y * W + x);
+                p[0] = p[1] = p[2] = 0.0;
+                p[sa] = ys[y];
+                p[pa] = xs[x];
+            }
+    }
+    if (etype && eptr && enodes) {  // main_all.cpp:163-224
+        int64_t e = 0;
+        eptr[0] = 0;
+        for (int y = 0; y < ny; y++)
+            for (int x = 0; x < nx; x++) {
+                const int32_t n = (int32_t)(x + (int64_t)y * W);
+                const int32_t A = n, B = n + 1, C = (int32_t)(n + W + 1), D = (int32_t)(n + W);
+                if (kind == 'q') {
+                    int32_t *q = enodes + 4 * e;
+                    q[0] = A; q[1] = B; q[2] = C; q[3] = D;
+                    etype[e] = FS_QUAD4;
+                    eptr[e + 1] = 4 * (e + 1);
+                    e++;
+                } else {
+                    int32_t *t1 = enodes + 3 * e, *t2 = t1 + 3;
+                    if (ul_lr) {
+                        t1[0] = A; t1[1] = B; t1[2] = D;
+                        t2[0] = B; t2[1] = C; t2[2] = D;
+                    } else {
+                        t1[0] = A; t1[1] = C; t1[2] = B;
+                        t2[0] = C; t2[1] = A; t2[2] = D;
+                    }
+                    etype[e] = etype[e + 1] = FS_TRI3;
+                    eptr[e + 1] = 3 * (e + 1);
+                    eptr[e + 2] = 3 * (e + 2);
+                    e += 2;
+                }
+            }
+    }
+    if (bc) {  // main_all.cpp:284-338, same record order
+        int64_t k = 0;
+        auto put = [&](int64_t el, int side, int id) {
+            bc[3 * k] = (int32_t)el; bc[3 * k + 1] = side; bc[3 * k + 2] = id;
+            k++;
+        };
+        const int64_t nxy = (int64_t)nx * ny;
+        for (int i = 0; i < nx; i++) {
+            if (kind == 't') {
+                if (b_id >= 0) put(2 * i, ul_lr ? 0 : 2, b_id);
+                if (t_id >= 0) put(2 * nxy - 2 * i - 1, ul_lr ? 1 : 2, t_id);
+            } else {
+                if (b_id >= 0) put(i, 0, b_id);
+                if (t_id >= 0) put(nxy - 1 - i, 2, t_id);
+            }
+        }
+        for (int i = 0; i < ny; i++) {
+            if (kind == 't') {
+                if (ul_lr) {
+                    if (l_id >= 0) put(2 * (int64_t)nx * i, 2, l_id);
+                    if (r_id >= 0) put(2 * (int64_t)nx * (i + 1) - 1, 0, r_id);
+                } else {
+                    if (l_id >= 0) put(2 * (int64_t)nx * i + 1, 1, l_id);
+                    if (r_id >= 0) put(2 * (int64_t)nx * (i + 1) - 2, 1, r_id);
+                }
+            } else {
+                if (l_id >= 0) put((int64_t)nx * i, 3, l_id);
+                if (r_id >= 0) put((int64_t)nx * (i + 1) - 1, 1, r_id);
+            }
+        }
+    }
+    if (forces) {  // main_all.cpp:343-387 followed by fs.cpp:52-66
+        memset(forces, 0, sizeof(double) * 6 * n_nodes);
+        const int comp = dead_axis == 'x' ? 0 : (dead_axis == 'y' ? 1 : 2);
+        if (loading == 1) {
+            const double f = g6(factor);
+            if (n_nodes / 2 < n_nodes - 1) forces[6 * (n_nodes / 2) + comp] = 1.0 * f;
+        } else if (loading == 2) {
+            const double f = g6(factor * ((max_x - min_x) / (double)nx) * ((max_y - min_y) / (double)ny));
+            for (int64_t i = 0; i < n_nodes - 1; i++) forces[6 * i + comp] = 1.0 * f;  // the last node gets no row
+        }
+    }
+    (void)nen;
+    return FS_OK;
+}
+
+int fs_read_xda(const char *path, int64_t *n_nodes_o, int64_t *n_elem_o, int64_t *n_enodes_o, int64_t *n_bc_o,
+                double *xyz, int32_t *etype, int64_t *eptr, int32_t *enodes, int32_t *bc)
+{
+    if (!path) return FS_ERR_ARG;
+    std::ifstream in(path);
+    if (!in) return FS_ERR_IO;
+    std::string line;
+    if (!std::getline(in, line) || line.compare(0, 7, "libMesh") != 0) return FS_ERR_IO;
+    int64_t n_elem = 0, n_nodes = 0;
+    if (!next_line(in, line)) return FS_ERR_IO;
+    n_elem = strtoll(line.c_str(), nullptr, 10);
+    if (!next_line(in, line)) return FS_ERR_IO;
+    n_nodes = strtoll(line.c_str(), nullptr, 10);
+    for (int i = 0; i < 4; i++)  // bc / subdomain / processor / p-level specification lines
+        if (!std::getline(in, line)) return FS_ERR_IO;
+    if (!next_line(in, line)) return FS_ERR_IO;  // n_elem at level 0
+    if (n_elem <= 0 || n_nodes <= 0) return FS_ERR_IO;
+    int64_t n_en = 0;
+    if (eptr) eptr[0] = 0;
+    for (int64_t e = 0; e < n_elem; e++) {
+        if (!next_line(in, line)) return FS_ERR_IO;
+        std::istringstream ss(line);
+        int t;
+        ss >> t;
+        int nen = (t == FS_TRI3) ? 3 : (t == FS_QUAD4 ? 4 : 0);
+        if (!nen) return FS_ERR_ARG;  // only the two element types fem-shell handles (fs.cpp:315,342)
+        for (int k = 0; k < nen; k++) {
+            long long id;
+            if (!(ss >> id)) return FS_ERR_IO;
+            if (enodes) enodes[n_en + k] = (int32_t)id;
+        }
+        if (etype) etype[e] = t;
+        n_en += nen;
+        if (eptr) eptr[e + 1] = n_en;
+    }
+    for (int64_t i = 0; i < n_nodes; i++) {
+        if (!next_line(in, line)) return FS_ERR_IO;
+        double a, b, c;
+        if (sscanf(line.c_str(), "%lf %lf %lf", &a, &b, &c) != 3) return FS_ERR_IO;
+        if (xyz) { xyz[3 * i] = a; xyz[3 * i + 1] = b; xyz[3 * i + 2] = c; }
+    }
+    int64_t n_bc = 0;
+    if (next_line(in, line)) n_bc = strtoll(line.c_str(), nullptr, 10);
+    for (int64_t i = 0; i < n_bc; i++) {
+        if (!next_line(in, line)) return FS_ERR_IO;
+        int a, b, c;
+        if (sscanf(line.c_str(), "%d %d %d", &a, &b, &c) != 3) return FS_ERR_IO;
+        if (bc) { bc[3 * i] = a; bc[3 * i + 1] = b; bc[3 * i + 2] = c; }
+    }
+    if (n_nodes_o) *n_nodes_o = n_nodes;
+    if (n_elem_o) *n_elem_o = n_elem;
+    if (n_enodes_o) *n_enodes_o = n_en;
+    if (n_bc_o) *n_bc_o = n_bc;
+    return FS_OK;
+}
+
+int fs_read_forces(const char *path, int64_t n_nodes, double *forces)
+{
+    if (!path || !forces || n_nodes <= 0) return FS_ERR_ARG;
+    memset(forces, 0, sizeof(double) * 6 * n_nodes);
+    std::ifstream in(path);
+    if (!in) return FS_ERR_IO;  // the reference silently runs without loads (fs.cpp:52); callers decide
+    long long n = 0;
+    double factor = 1.0;
+    in >> n;
+    in >> factor;
+    // fs.cpp:59-66: a failed extraction leaves the zero-initialised DenseVector entries untouched
+    for (long long i = 0; i < n && i < n_nodes; i++)
+        for (int j = 0; j < 6; j++) {
+            double v;
+            if (in >> v) forces[6 * i + j] = v * factor;
+        }
+    return FS_OK;
+}
+
+int fs_write_xda(const char *path, int64_t n_nodes, const double *xyz, int64_t n_elem, const int32_t *etype,
+                 const int64_t *eptr, const int32_t *enodes, int64_t n_bc, const int32_t *bc)
+{
+    if (!path || !xyz || !etype || !eptr || !enodes) return FS_ERR_ARG;
+    FILE *f = fopen(path, "w");
+    if (!f) return FS_ERR_IO;
+    fprintf(f, "libMesh-0.7.0+\n%lld      # number of elements\n%lld      # number of nodes\n", (long long)n_elem, (long long)n_nodes);
+    fprintf(f, ".        # boundary condition specification file\nn/a      # subdomain id specification file\n");
+    fprintf(f, "n/a      # processor id specification file\nn/a      # p-level specification file\n");
+    fprintf(f, "%lld      # n_elem at level 0, [ type (n0 ... nN-1) ]\n", (long long)n_elem);
+    for (int64_t e = 0; e < n_elem; e++) {
+        fprintf(f, "%d", etype[e]);
+        for (int64_t k = eptr[e]; k < eptr[e + 1]; k++) fprintf(f, " %d", enodes[k]);
+        fputc('\n', f);
+    }
+    for (int64_t i = 0; i < n_nodes; i++) fprintf(f, "%g %g %g\n", xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    fprintf(f, "%lld        # number of boundary conditions\n", (long long)n_bc);
+    for (int64_t i = 0; i < n_bc; i++) fprintf(f, "%d %d %d\n", bc[3 * i], bc[3 * i + 1], bc[3 * i + 2]);
+    fclose(f);
+    return FS_OK;
+}
+
+}  // extern "C"

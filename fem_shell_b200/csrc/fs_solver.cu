@@ -1,0 +1,599 @@
+// fs_solver.cu -- preconditioned conjugate gradients on the block-CSR matrix.
+//
+// Replaces LinearImplicitSystem::solve -> PetscLinearSolver -> KSPSolve (fs.cpp:138, fsp.cpp:271)
+// for the PETSc options the reference passes through (-ksp_type cg, -pc_type none|jacobi|pbjacobi,
+// doc/implementation.tex:68-72).  All scalars of the recurrence stay on the device (CgState); the
+// host only enqueues batches of iterations and polls one flag, so an iteration costs three kernel
+// launches and no synchronisation:
+//   k_spmv_dot     q = A p,  partial p.q            -> alpha = rz / p.q
+//   k_update       x += alpha p, r -= alpha q, z = M^-1 r, partial r.z and ||r||^2 (or ||z||^2)
+//                                                   -> beta, convergence flag
+//   k_direction    p = z + beta p
+// Reductions are deterministic: per-block partials, the last block to arrive sums them in index
+// order.  Multi-GPU: halo exchange of p before k_spmv_dot (ncclSend/Recv), ncclAllReduce of the
+// partial sums, then a one-thread finalise kernel.
+#include <nccl.h>
+
+#include "fs_context.hpp"
+
+namespace fs {
+
+#define FS_NCCL(ctx, call)                                                                     \
+    do {                                                                                       \
+        ncclResult_t r__ = (call);                                                             \
+        if (r__ != ncclSuccess)                                                                \
+            return fs::fail(ctx, FS_ERR_COMM, std::string(#call) + ": " + ncclGetErrorString(r__)); \
+    } while (0)
+
+static inline unsigned int nblk(int64_t n, int bs) { return (unsigned int)((n + bs - 1) / bs); }
+
+// ---------------------------------------------------------------------------------------------
+// deterministic grid reduction of NV values; returns true in the block that arrives last, with
+// the totals in out[] (valid for thread 0 of that block)
+// ---------------------------------------------------------------------------------------------
+template <int NV, int BLOCK>
+__device__ __forceinline__ bool grid_reduce(double (&v)[NV], double *partials, unsigned int *counter,
+                                            double (&out)[NV])
+{
+    __shared__ double s_red[NV][BLOCK / 32];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        double x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) s_red[k][warp] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            double x = 0.0;
+            for (int w = 0; w < BLOCK / 32; w++) x += s_red[k][w];
+            partials[(size_t)blockIdx.x * NV + k] = x;
+        }
+        __threadfence();
+        unsigned int ticket = atomicInc(counter, gridDim.x - 1);  // wraps back to 0 for the next use
+        s_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    // fixed-order sum of the per-block partials
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        double x = 0.0;
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += BLOCK) x += partials[(size_t)b * NV + k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        __syncthreads();
+        if (lane == 0) s_red[k][warp] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            double x = 0.0;
+            for (int w = 0; w < BLOCK / 32; w++) x += s_red[k][w];
+            out[k] = x;
+        }
+    }
+    return true;
+}
+
+// ---- scalar recurrences (run by one thread) --------------------------------------------------
+__device__ __forceinline__ void finalize_pq(CgState *s, double pq)
+{
+    s->pq = pq;
+    s->alpha = s->rz / pq;
+    if (!(pq > 0.0)) {  // not SPD (SURVEY.md section 7 "SPD is empirical")
+        s->status = FS_ERR_BREAKDOWN;
+        s->done = 1;
+    }
+}
+
+__device__ __forceinline__ void finalize_update(CgState *s, double rz_new, double nrm2)
+{
+    s->beta = rz_new / s->rz;
+    s->rz = rz_new;
+    s->nrm2 = nrm2;
+    s->iter += 1;
+    if (nrm2 <= s->tol2 * s->bnorm2) {
+        s->status = FS_OK;
+        s->done = 1;
+    } else if (s->iter >= s->max_its) {
+        s->status = FS_ERR_NOT_CONVERGED;
+        s->done = 1;
+    }
+}
+
+__device__ __forceinline__ void finalize_init(CgState *s, double rz, double nrm2, double bnorm2)
+{
+    s->rz = rz;
+    s->nrm2 = nrm2;
+    s->bnorm2 = bnorm2;
+    s->iter = 0;
+    s->status = FS_ERR_NOT_CONVERGED;
+    s->done = 0;
+    if (bnorm2 == 0.0) {  // b = 0 -> x = 0 (host zeroes x when it sees nrm2 < 0)
+        s->bnorm2 = 1.0;
+        s->nrm2 = -1.0;
+        s->status = FS_OK;
+        s->done = 1;
+    } else if (nrm2 <= s->tol2 * bnorm2) {
+        s->status = FS_OK;
+        s->done = 1;
+    } else if (s->max_its <= 0) {
+        s->done = 1;
+    }
+}
+
+// which: 0 init (red = rz, nrm2, bnorm2), 1 after spmv (red = pq), 2 after update (red = rz_new, nrm2)
+__global__ void k_finalize(CgState *s, const double *red, int which)
+{
+    if (which == 0) finalize_init(s, red[0], red[1], red[2]);
+    else if (s->done) return;
+    else if (which == 1) finalize_pq(s, red[0]);
+    else finalize_update(s, red[0], red[1]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// SpMV: one warp per block row (6 scalar rows of one node).  Lane l owns the double2 at position l
+// of every one of the six rows (row length 6*deg doubles = 3*deg double2), so each row is one
+// fully coalesced 128-bit load per lane and the x pair is loaded once for all six rows.
+// ---------------------------------------------------------------------------------------------
+template <bool WITH_DOT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_spmv(int n_own, const int32_t *__restrict__ nptr, const int32_t *__restrict__ nadj,
+       const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y_own,
+       const double *__restrict__ x_own, double *partials, unsigned int *counter, CgState *state,
+       double *red, int inline_finalize)
+{
+    if (WITH_DOT && state->done) return;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = BLOCK / 32;
+    const int gw = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int nw = gridDim.x * warps_per_block;
+    double dot = 0.0;
+    for (int p = gw; p < n_own; p += nw) {
+        const int b0 = nptr[p], deg = nptr[p + 1] - b0;
+        const int L2 = 3 * deg;  // double2 per scalar row
+        const double2 *base = reinterpret_cast<const double2 *>(vals + (size_t)36 * b0);
+        double acc[6] = {0, 0, 0, 0, 0, 0};
+        for (int l = lane; l < L2; l += 32) {
+            const int j = l / 3, h = l - 3 * j;
+            const int col = nadj[b0 + j];
+            const double2 xv = *reinterpret_cast<const double2 *>(x + 6 * (size_t)col + 2 * h);
+            double2 v[6];
+#pragma unroll
+            for (int a = 0; a < 6; a++) v[a] = __ldcs(base + (size_t)a * L2 + l);
+#pragma unroll
+            for (int a = 0; a < 6; a++) acc[a] += v[a].x * xv.x + v[a].y * xv.y;
+        }
+        // transposing butterfly: 6 sums over 32 lanes in 3+2+1+1+1 exchanges
+        double t3[4];
+        {
+            const bool hi = lane & 16;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                double send = hi ? acc[k] : acc[k + 3];
+                double keep = hi ? acc[k + 3] : acc[k];
+                t3[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+            t3[3] = 0.0;
+        }
+        double t2[2];
+        {
+            const bool hi = lane & 8;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                double send = hi ? t3[k] : t3[k + 2];
+                double keep = hi ? t3[k + 2] : t3[k];
+                t2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+        }
+        double t1;
+        {
+            const bool hi = lane & 4;
+            double send = hi ? t2[0] : t2[1];
+            double keep = hi ? t2[1] : t2[0];
+            t1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        t1 += __shfl_xor_sync(0xffffffffu, t1, 2);
+        t1 += __shfl_xor_sync(0xffffffffu, t1, 1);
+        // lane bits: 16 -> rows {0,1,2} vs {3,4,5}; 8 -> k in {0,1} vs {2,3}; 4 -> k even vs odd
+        const int row = ((lane & 16) ? 3 : 0) + ((lane & 8) ? 2 : 0) + ((lane & 4) ? 1 : 0);
+        const bool writer = ((lane & 3) == 0) && (((lane >> 2) & 3) != 3);
+        if (writer) {
+            y_own[6 * (size_t)p + row] = t1;
+            if (WITH_DOT) dot += t1 * x_own[6 * (size_t)p + row];
+        }
+    }
+    if (WITH_DOT) {
+        double v[1] = {dot}, out[1];
+        if (grid_reduce<1, BLOCK>(v, partials, counter, out) && threadIdx.x == 0) {
+            red[0] = out[0];
+            if (inline_finalize) finalize_pq(state, out[0]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// x += alpha p ; r -= alpha q ; z = M^-1 r ; partial r.z and norm
+// PC: 0 none, 1 Jacobi (minv = 1/diag, 6 per node), 2 block Jacobi (minv = 6x6 inverse per node)
+// one thread per node (6 dofs = three double2), grid-stride
+// ---------------------------------------------------------------------------------------------
+template <int PC>
+__device__ __forceinline__ void apply_pc_node(const double *__restrict__ minv, int64_t p, const double r[6],
+                                              double z[6])
+{
+    if (PC == 0) {
+#pragma unroll
+        for (int a = 0; a < 6; a++) z[a] = r[a];
+    } else if (PC == 1) {
+        const double2 *m = reinterpret_cast<const double2 *>(minv + 6 * p);
+#pragma unroll
+        for (int h = 0; h < 3; h++) {
+            double2 mm = m[h];
+            z[2 * h] = mm.x * r[2 * h];
+            z[2 * h + 1] = mm.y * r[2 * h + 1];
+        }
+    } else {
+        const double2 *m = reinterpret_cast<const double2 *>(minv + 36 * p);
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            double s = 0.0;
+#pragma unroll
+            for (int h = 0; h < 3; h++) {
+                double2 mm = m[3 * a + h];
+                s += mm.x * r[2 * h] + mm.y * r[2 * h + 1];
+            }
+            z[a] = s;
+        }
+    }
+}
+
+__device__ __forceinline__ void load6(const double *p, double v[6])
+{
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+#pragma unroll
+    for (int h = 0; h < 3; h++) {
+        double2 t = q[h];
+        v[2 * h] = t.x;
+        v[2 * h + 1] = t.y;
+    }
+}
+__device__ __forceinline__ void store6(double *p, const double v[6])
+{
+    double2 *q = reinterpret_cast<double2 *>(p);
+#pragma unroll
+    for (int h = 0; h < 3; h++) q[h] = make_double2(v[2 * h], v[2 * h + 1]);
+}
+
+template <int PC, int NORM, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_update(int64_t n_own, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
+         const double *__restrict__ q, double *__restrict__ z, const double *__restrict__ minv,
+         double *partials, unsigned int *counter, CgState *state, double *red, int inline_finalize)
+{
+    if (state->done) return;
+    const double alpha = state->alpha;
+    double rz = 0.0, nn = 0.0;
+    for (int64_t n = blockIdx.x * (int64_t)BLOCK + threadIdx.x; n < n_own; n += (int64_t)gridDim.x * BLOCK) {
+        double xv[6], rv[6], pv[6], qv[6], zv[6];
+        load6(x + 6 * n, xv);
+        load6(r + 6 * n, rv);
+        load6(p + 6 * n, pv);
+        load6(q + 6 * n, qv);
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            xv[a] += alpha * pv[a];
+            rv[a] -= alpha * qv[a];
+        }
+        apply_pc_node<PC>(minv, n, rv, zv);
+        store6(x + 6 * n, xv);
+        store6(r + 6 * n, rv);
+        store6(z + 6 * n, zv);
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            rz += rv[a] * zv[a];
+            nn += NORM ? zv[a] * zv[a] : rv[a] * rv[a];
+        }
+    }
+    double v[2] = {rz, nn}, out[2];
+    if (grid_reduce<2, BLOCK>(v, partials, counter, out) && threadIdx.x == 0) {
+        red[0] = out[0];
+        red[1] = out[1];
+        if (inline_finalize) finalize_update(state, out[0], out[1]);
+    }
+}
+
+// p = z + beta p
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_direction(int64_t n_own, const double *__restrict__ z, double *__restrict__ p, CgState *state)
+{
+    // after convergence x is final; p is not needed any more
+    if (state->done) return;
+    const double beta = state->beta;
+    const int64_t n2 = 3 * n_own;
+    const double2 *z2 = reinterpret_cast<const double2 *>(z);
+    double2 *p2 = reinterpret_cast<double2 *>(p);
+    for (int64_t i = blockIdx.x * (int64_t)BLOCK + threadIdx.x; i < n2; i += (int64_t)gridDim.x * BLOCK) {
+        double2 zz = z2[i], pp = p2[i];
+        pp.x = zz.x + beta * pp.x;
+        pp.y = zz.y + beta * pp.y;
+        p2[i] = pp;
+    }
+}
+
+// r = b - q ; z = M^-1 r ; p = z ; sums r.z, norm(r|z), norm(b|M^-1 b)
+template <int PC, int NORM, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_init(int64_t n_own, const double *__restrict__ b, const double *__restrict__ q, double *__restrict__ r,
+       double *__restrict__ z, double *__restrict__ p, const double *__restrict__ minv, double *partials,
+       unsigned int *counter, CgState *state, double *red, int inline_finalize)
+{
+    double rz = 0.0, nn = 0.0, bb = 0.0;
+    for (int64_t n = blockIdx.x * (int64_t)BLOCK + threadIdx.x; n < n_own; n += (int64_t)gridDim.x * BLOCK) {
+        double bv[6], qv[6], rv[6], zv[6], mb[6];
+        load6(b + 6 * n, bv);
+        load6(q + 6 * n, qv);
+#pragma unroll
+        for (int a = 0; a < 6; a++) rv[a] = bv[a] - qv[a];
+        apply_pc_node<PC>(minv, n, rv, zv);
+        store6(r + 6 * n, rv);
+        store6(z + 6 * n, zv);
+        store6(p + 6 * n, zv);
+        if (NORM) apply_pc_node<PC>(minv, n, bv, mb);
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            rz += rv[a] * zv[a];
+            nn += NORM ? zv[a] * zv[a] : rv[a] * rv[a];
+            bb += NORM ? mb[a] * mb[a] : bv[a] * bv[a];
+        }
+    }
+    double v[3] = {rz, nn, bb}, out[3];
+    if (grid_reduce<3, BLOCK>(v, partials, counter, out) && threadIdx.x == 0) {
+        red[0] = out[0];
+        red[1] = out[1];
+        red[2] = out[2];
+        if (inline_finalize) finalize_init(state, out[0], out[1], out[2]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// preconditioner setup: diagonal (or 6x6 diagonal block inverse) of the assembled matrix
+// ---------------------------------------------------------------------------------------------
+__global__ void k_extract_minv(int n_own, int own_lo, const int32_t *__restrict__ nptr,
+                               const int32_t *__restrict__ nadj, const double *__restrict__ vals, int pc,
+                               double *minv, int *bad)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_own) return;
+    const int b0 = nptr[p], deg = nptr[p + 1] - b0;
+    int slot = -1;
+    for (int j = 0; j < deg; j++)
+        if (nadj[b0 + j] == p + own_lo) slot = j;
+    if (slot < 0) { *bad = 1; return; }
+    const double *blk = vals + (size_t)36 * b0 + 6 * slot;
+    const int L = 6 * deg;
+    if (pc == 1) {
+        for (int a = 0; a < 6; a++) minv[6 * (size_t)p + a] = 1.0 / blk[(size_t)a * L + a];
+        return;
+    }
+    double M[6][12];
+    for (int a = 0; a < 6; a++)
+        for (int b = 0; b < 6; b++) {
+            M[a][b] = blk[(size_t)a * L + b];
+            M[a][6 + b] = (a == b) ? 1.0 : 0.0;
+        }
+    for (int c = 0; c < 6; c++) {
+        int piv = c;
+        for (int r = c + 1; r < 6; r++)
+            if (fabs(M[r][c]) > fabs(M[piv][c])) piv = r;
+        if (M[piv][c] == 0.0) { *bad = 1; return; }
+        if (piv != c)
+            for (int j = 0; j < 12; j++) { double t = M[c][j]; M[c][j] = M[piv][j]; M[piv][j] = t; }
+        double d = 1.0 / M[c][c];
+        for (int j = 0; j < 12; j++) M[c][j] *= d;
+        for (int r = 0; r < 6; r++)
+            if (r != c) {
+                double f = M[r][c];
+                for (int j = 0; j < 12; j++) M[r][j] -= f * M[c][j];
+            }
+    }
+    for (int a = 0; a < 6; a++)
+        for (int b = 0; b < 6; b++) minv[36 * (size_t)p + 6 * a + b] = M[a][6 + b];
+}
+
+int solver_query_occupancy(fs_context *c)
+{
+    int nb = 0;
+    FS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_spmv<true, 256>, 256, 0));
+    c->spmv_blocks_per_sm = std::max(1, nb);
+    FS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_update<1, 0, 256>, 256, 0));
+    c->vec_blocks_per_sm = std::max(1, nb);
+    return FS_OK;
+}
+
+int solver_prepare(fs_context *c, int pc)
+{
+    if (!c->assembled) return fail(c, FS_ERR_STATE, "fs_solve before fs_assemble");
+    if (pc < 0 || pc > 2) return fail(c, FS_ERR_ARG, "unknown preconditioner");
+    if (c->minv_kind == pc) return FS_OK;
+    if (pc != FS_PC_NONE) {
+        FS_CUDA(c, c->d_minv.alloc((size_t)(pc == 1 ? 6 : 36) * c->n_own));
+        DevBuf<int> bad;
+        FS_CUDA(c, bad.alloc(1));
+        FS_CUDA(c, cudaMemsetAsync(bad.p, 0, sizeof(int), c->stream));
+        k_extract_minv<<<nblk(c->n_own, 128), 128, 0, c->stream>>>((int)c->n_own, (int)c->own_lo, c->d_nptr.p,
+                                                                    c->d_nadj.p, c->d_vals.p, pc, c->d_minv.p, bad.p);
+        int h_bad = 0;
+        FS_CUDA(c, cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        FS_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (h_bad) return fail(c, FS_ERR_BREAKDOWN, "singular diagonal block in the preconditioner");
+    }
+    c->minv_kind = pc;
+    return FS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// halo exchange (multi-GPU): owned boundary values -> neighbours' halo segments
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pack(int64_t n_send, const int32_t *__restrict__ idx, const double *__restrict__ vec,
+                       double *__restrict__ buf)
+{
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= 3 * n_send) return;
+    int64_t s = t / 3;
+    int h = (int)(t - 3 * s);
+    reinterpret_cast<double2 *>(buf)[t] = reinterpret_cast<const double2 *>(vec + 6 * (size_t)idx[s])[h];
+}
+
+int halo_exchange(fs_context *c, double *d_vec)
+{
+    if (c->world == 1 || c->peers.empty()) return FS_OK;
+    if (c->send_total)
+        k_pack<<<nblk(3 * c->send_total, 256), 256, 0, c->stream>>>(c->send_total, c->d_send_idx.p, d_vec, c->d_sendbuf.p);
+    FS_NCCL(c, ncclGroupStart());
+    for (const Peer &pr : c->peers) {
+        if (pr.send_count)
+            FS_NCCL(c, ncclSend(c->d_sendbuf.p + 6 * pr.send_off, 6 * pr.send_count, ncclDouble, pr.rank, (ncclComm_t)c->comm, c->stream));
+        if (pr.recv_count)
+            FS_NCCL(c, ncclRecv(d_vec + 6 * pr.recv_off, 6 * pr.recv_count, ncclDouble, pr.rank, (ncclComm_t)c->comm, c->stream));
+    }
+    FS_NCCL(c, ncclGroupEnd());
+    return FS_OK;
+}
+
+static int spmv_grid(fs_context *c)
+{
+    // persistent grid: a multiple of the SM count, one warp per block row, grid-stride
+    int64_t want = ((int64_t)c->n_own + 7) / 8;
+    int64_t cap = (int64_t)c->sm_count * c->spmv_blocks_per_sm;
+    return (int)std::max<int64_t>(1, std::min(want, cap));
+}
+
+static int vec_grid(fs_context *c)
+{
+    int64_t want = ((int64_t)c->n_own + 255) / 256;
+    int64_t cap = (int64_t)c->sm_count * c->vec_blocks_per_sm;
+    return (int)std::max<int64_t>(1, std::min(want, cap));
+}
+
+int spmv_once(fs_context *c, const double *d_in, double *d_out)
+{
+    int rc = halo_exchange(c, const_cast<double *>(d_in));
+    if (rc) return rc;
+    k_spmv<false, 256><<<spmv_grid(c), 256, 0, c->stream>>>((int)c->n_own, c->d_nptr.p, c->d_nadj.p, c->d_vals.p, d_in,
+                                                           d_out + 6 * c->own_lo, nullptr, nullptr, nullptr, nullptr,
+                                                           nullptr, 0);
+    FS_CUDA(c, cudaGetLastError());
+    return FS_OK;
+}
+
+template <int PC, int NORM>
+static int enqueue_iteration(fs_context *c, double *red, int sg, int vg)
+{
+    const int single = (c->world == 1);
+    const int64_t o6 = 6 * c->own_lo;
+    int rc = halo_exchange(c, c->d_p.p);
+    if (rc) return rc;
+    k_spmv<true, 256><<<sg, 256, 0, c->stream>>>((int)c->n_own, c->d_nptr.p, c->d_nadj.p, c->d_vals.p, c->d_p.p,
+                                                 c->d_q.p + o6, c->d_p.p + o6, c->d_partials.p, c->d_counter.p,
+                                                 c->d_state.p, red, single);
+    if (!single) {
+        FS_NCCL(c, ncclAllReduce(red, red, 1, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
+        k_finalize<<<1, 1, 0, c->stream>>>(c->d_state.p, red, 1);
+    }
+    k_update<PC, NORM, 256><<<vg, 256, 0, c->stream>>>(c->n_own, c->d_x.p + o6, c->d_r.p + o6, c->d_p.p + o6,
+                                                       c->d_q.p + o6, c->d_z.p + o6, c->d_minv.p, c->d_partials.p,
+                                                       c->d_counter.p, c->d_state.p, red + 4, single);
+    if (!single) {
+        FS_NCCL(c, ncclAllReduce(red + 4, red + 4, 2, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
+        k_finalize<<<1, 1, 0, c->stream>>>(c->d_state.p, red + 4, 2);
+    }
+    k_direction<256><<<vg, 256, 0, c->stream>>>(c->n_own, c->d_z.p + o6, c->d_p.p + o6, c->d_state.p);
+    return FS_OK;
+}
+
+template <int PC, int NORM>
+static int run_pcg(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
+{
+    cudaStream_t st = c->stream;
+    const int single = (c->world == 1);
+    const int64_t o6 = 6 * c->own_lo;
+    const int sg = spmv_grid(c), vg = vec_grid(c);
+    const int maxgrid = std::max(sg, vg);
+    if (c->d_partials.n < (size_t)maxgrid * 4) FS_CUDA(c, c->d_partials.alloc((size_t)maxgrid * 4 + 16));
+    double *red = c->d_partials.p + (size_t)maxgrid * 4;  // 16 spare doubles behind the partials
+
+    CgState h = {};
+    h.tol2 = o->rtol * o->rtol;
+    h.max_its = o->max_its;
+    h.status = FS_ERR_NOT_CONVERGED;
+    FS_CUDA(c, cudaMemcpyAsync(c->d_state.p, &h, sizeof h, cudaMemcpyHostToDevice, st));
+    FS_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned int), st));
+    if (!o->warm_start || !c->have_solution)
+        FS_CUDA(c, cudaMemsetAsync(c->d_x.p, 0, sizeof(double) * 6 * c->n_local, st));
+
+    FS_CUDA(c, cudaEventRecord(c->ev0, st));
+    // r = b - A x0
+    int rc = spmv_once(c, c->d_x.p, c->d_q.p);
+    if (rc) return rc;
+    k_init<PC, NORM, 256><<<vg, 256, 0, st>>>(c->n_own, c->d_b.p + o6, c->d_q.p + o6, c->d_r.p + o6, c->d_z.p + o6,
+                                              c->d_p.p + o6, c->d_minv.p, c->d_partials.p, c->d_counter.p,
+                                              c->d_state.p, red + 8, single);
+    if (!single) {
+        FS_NCCL(c, ncclAllReduce(red + 8, red + 8, 3, ncclDouble, ncclSum, (ncclComm_t)c->comm, st));
+        k_finalize<<<1, 1, 0, st>>>(c->d_state.p, red + 8, 0);
+    }
+    const int batch = o->check_every > 0 ? o->check_every : 64;
+    for (;;) {
+        FS_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state.p, sizeof(CgState), cudaMemcpyDeviceToHost, st));
+        FS_CUDA(c, cudaStreamSynchronize(st));
+        if (c->h_state->done) break;
+        int64_t left = c->h_state->max_its - c->h_state->iter;
+        int n = (int)std::min<int64_t>(batch, std::max<int64_t>(left, 1));
+        for (int k = 0; k < n; k++) {
+            rc = enqueue_iteration<PC, NORM>(c, red, sg, vg);
+            if (rc) return rc;
+        }
+        FS_CUDA(c, cudaGetLastError());
+    }
+    FS_CUDA(c, cudaEventRecord(c->ev1, st));
+    FS_CUDA(c, cudaStreamSynchronize(st));
+    const CgState &s = *c->h_state;
+    if (s.nrm2 < 0.0) FS_CUDA(c, cudaMemsetAsync(c->d_x.p, 0, sizeof(double) * 6 * c->n_local, st));
+    c->have_solution = true;
+    if (info) {
+        info->iterations = s.iter;
+        info->rel_residual = s.nrm2 < 0.0 ? 0.0 : sqrt(s.nrm2 / s.bnorm2);
+        info->status = s.status;
+        info->spmv_ms = 0.f;
+        FS_CUDA(c, cudaEventElapsedTime(&info->solve_ms, c->ev0, c->ev1));
+    }
+    if (s.status == FS_ERR_BREAKDOWN) return fail(c, FS_ERR_BREAKDOWN, "CG breakdown: p.Ap <= 0 (matrix not positive definite)");
+    if (s.status == FS_ERR_NOT_CONVERGED) return fail(c, FS_ERR_NOT_CONVERGED, "CG did not reach rtol within max_its");
+    return FS_OK;
+}
+
+int solver_run(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
+{
+    if (!c->rhs_ready) return fail(c, FS_ERR_STATE, "no right-hand side: set loads first");
+    int rc = solver_prepare(c, o->pc);
+    if (rc) return rc;
+    const int nt = o->norm_type ? 1 : 0;
+    switch (o->pc * 2 + nt) {
+    case 0: return run_pcg<0, 0>(c, o, info);
+    case 1: return run_pcg<0, 1>(c, o, info);
+    case 2: return run_pcg<1, 0>(c, o, info);
+    case 3: return run_pcg<1, 1>(c, o, info);
+    case 4: return run_pcg<2, 0>(c, o, info);
+    default: return run_pcg<2, 1>(c, o, info);
+    }
+}
+
+}  // namespace fs

@@ -1,0 +1,186 @@
+/*
+ * femshell_b200.h -- C ABI of the B200-native fem-shell hot path
+ * (flat-shell element-stiffness assembly -> sparse PCG solve).
+ *
+ * Every entry point replaces one piece of the reference's path through
+ * libMesh/PETSc (reference = precice/fem-shell; "fs.cpp" =
+ * src/fem-shell/fem-shell.cpp, "fsp.cpp" =
+ * src/fem-shell/preCICE/fem-shell_precice.cpp).  The reference has no FFI of
+ * its own: its boundary is the libMesh assemble callback
+ *     void assemble_elasticity(EquationSystems&, const std::string&)
+ * (src/fem-shell/fem-shell.h:75, fs.cpp:1160) registered at fs.cpp:85 and
+ * driven by equation_systems.solve() (fs.cpp:138, fsp.cpp:271).  A maintainer
+ * binds this library by replacing those calls; INTEGRATION.md shows the stub.
+ *
+ * Conventions: plain pointers and sizes only; all host arrays are borrowed for
+ * the duration of the call; every function returns 0 (FS_OK) or a negative
+ * fs_status and leaves a message retrievable with fs_last_error(); no C++
+ * exception crosses this boundary.  One context = one GPU = one CUDA stream;
+ * calls on one context must be serialised by the caller.  There is no CPU
+ * fallback: without a CUDA device fs_create fails.
+ */
+#ifndef FEMSHELL_B200_H
+#define FEMSHELL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fs_context fs_context;
+
+typedef enum fs_status {
+    FS_OK = 0,
+    FS_ERR_ARG = -1,            /* bad argument / malformed mesh */
+    FS_ERR_CUDA = -2,           /* CUDA runtime error (message has the detail) */
+    FS_ERR_STATE = -3,          /* call order violated (e.g. solve before assemble) */
+    FS_ERR_NOT_CONVERGED = -4,  /* max_its reached before rtol */
+    FS_ERR_BREAKDOWN = -5,      /* p.Ap <= 0 : matrix not positive definite */
+    FS_ERR_COMM = -6,           /* NCCL error */
+    FS_ERR_IO = -7              /* file could not be read / written */
+} fs_status;
+
+/* XDA element type ids (src/meshgen/main_all.cpp:245-247; libMesh TRI3 / QUAD4) */
+enum { FS_TRI3 = 3, FS_QUAD4 = 5 };
+
+/* DOF numbering of the assembled system (libMesh DofMap, call site fs.cpp:125,1205).
+ * FIRST_ENCOUNTER = libMesh's var-major distribution: node bases in first-encounter order
+ * over elements in id order.  NODE_ID = 6*node_id+var.  SURVEY.md section 8a (a12). */
+enum { FS_DOF_FIRST_ENCOUNTER = 0, FS_DOF_NODE_ID = 1 };
+
+/* -pc_type none | jacobi | pbjacobi (PETSc flags passed through by the reference, doc/implementation.tex:68-72) */
+enum { FS_PC_NONE = 0, FS_PC_JACOBI = 1, FS_PC_BJACOBI6 = 2 };
+
+/* convergence norm: ||r||/||b|| or PETSc's default preconditioned ||M^-1 r||/||M^-1 b|| */
+enum { FS_NORM_UNPRECONDITIONED = 0, FS_NORM_PRECONDITIONED = 1 };
+
+/* arithmetic quirks of the reference, reproduced by default */
+enum { FS_QUIRK_Y21 = 1 /* fs.cpp:586 */, FS_QUIRK_DET_LU = 2 /* fs.cpp:512,652 */, FS_QUIRKS_REFERENCE = 3 };
+
+/* assembly strategy: graph-coloured scatter-add (default) or row-gather (owner computes) */
+enum { FS_ASM_COLORED = 0, FS_ASM_GATHER = 1 };
+
+typedef struct fs_solve_opts {
+    double rtol;        /* relative tolerance (reference default 1e-12 = TOLERANCE^2, fs.cpp:130-133) */
+    int64_t max_its;    /* reference default 5000 */
+    int pc;             /* FS_PC_* */
+    int norm_type;      /* FS_NORM_* */
+    int warm_start;     /* 1: start from the previous solution (libMesh/PETSc default, fsp.cpp:271) */
+    int check_every;    /* iterations enqueued between host polls of the device flag; <=0 -> default */
+} fs_solve_opts;
+
+typedef struct fs_solve_info {
+    int64_t iterations;
+    double rel_residual;  /* in the norm selected by norm_type */
+    int status;           /* FS_OK, FS_ERR_NOT_CONVERGED or FS_ERR_BREAKDOWN */
+    float solve_ms;       /* device time of the Krylov loop (CUDA events on the context stream) */
+    float spmv_ms;        /* filled by fs_bench_spmv only */
+} fs_solve_info;
+
+/* ---- life cycle -------------------------------------------------------- */
+/* replaces LibMeshInit (fs.cpp:28): binds the context to CUDA device `device` */
+int fs_create(fs_context **ctx, int device);
+int fs_destroy(fs_context *ctx);
+const char *fs_last_error(const fs_context *ctx);
+/* CUDA stream of the context as a cudaStream_t (for callers timing with their own events) */
+void *fs_get_stream(fs_context *ctx);
+
+/* ---- multi-GPU: one process per GPU ------------------------------------ */
+/* Call BEFORE fs_set_mesh.  nccl_unique_id = the 128 bytes of an ncclUniqueId created on
+ * rank 0 (fs_dist_unique_id) and broadcast by the host program.  Replaces the MPI
+ * communicator libMesh/PETSc use (fs.cpp:28,35). */
+int fs_dist_unique_id(uint8_t id_out[128]);
+int fs_dist_init(fs_context *ctx, int rank, int world, const uint8_t nccl_unique_id[128]);
+
+/* ---- inputs ------------------------------------------------------------ */
+/* replaces the globals nu, em, thickness + initMaterialMatrices (fs.cpp:273-294) */
+int fs_set_material(fs_context *ctx, double nu, double E, double thickness);
+int fs_set_quirks(fs_context *ctx, int quirk_flags);
+int fs_set_dof_order(fs_context *ctx, int mode);
+int fs_set_assembly_mode(fs_context *ctx, int mode);
+
+/* replaces mesh.read + the DirichletBoundary setup (fs.cpp:35-37, 90-120) + equation_systems.init
+ * (fs.cpp:125: DOF numbering, sparsity, constraints).  The whole (replicated) mesh is passed on
+ * every rank, like the reference's replicated Mesh.
+ *   xyz     n_nodes*3            etype  n_elem (FS_TRI3|FS_QUAD4)
+ *   eptr    n_elem+1 offsets     enodes node ids, local order
+ *   bc      n_bc rows (element, side, boundary id); ids {0,20} fix u,v,w, {1,21} fix all six,
+ *           {2,20,21} mark the coupling interface (fsp.cpp:68) */
+int fs_set_mesh(fs_context *ctx, int64_t n_nodes, const double *xyz, int64_t n_elem,
+                const int32_t *etype, const int64_t *eptr, const int32_t *enodes, int64_t n_bc,
+                const int32_t *bc);
+
+/* replaces the `forces` global filled from <mesh>_f (fs.cpp:44-67): F[n_nodes][6], already scaled */
+int fs_set_nodal_loads(fs_context *ctx, const double *F);
+/* replaces the coupled contribRHS (fsp.cpp:1377-1438): n interface nodes, `dims` (2|3) values each,
+ * dead_axis 'x'|'y'|'z' for dims==2; all other nodal loads are zero */
+int fs_set_interface_loads(fs_context *ctx, int64_t n, const int32_t *node_ids, int dims,
+                           char dead_axis, const double *f);
+/* scales the CURRENT device-resident load vector into the rhs: b = scale * F (constrained rows 0).
+ * Used for repeated solves with a changing pressure amplitude (BASELINE config 4). */
+int fs_build_rhs(fs_context *ctx, double scale);
+
+/* ---- the hot path ------------------------------------------------------ */
+/* replaces assemble_elasticity (fs.cpp:1160-1233): element kernels, Dirichlet constraint, add into
+ * the block-CSR matrix, rhs.  The sparsity pattern and the element colouring are built on the
+ * first call and kept.  *ms (optional) receives the device time of the values pass. */
+int fs_assemble(fs_context *ctx, float *ms);
+/* replaces LinearImplicitSystem::solve -> KSPSolve (fs.cpp:138) for an already assembled system */
+int fs_solve(fs_context *ctx, const fs_solve_opts *opts, fs_solve_info *info);
+/* replaces build_solution_vector (fs.cpp:140-141): sols[6*node_id+var]; every rank gets the full vector */
+int fs_get_solution(fs_context *ctx, double *sols);
+/* equation_systems.solve() + build_solution_vector in one call with HOST buffers, as the
+ * reference's coupling loop does per iteration (fsp.cpp:271-274).  F may be NULL (keep loads).
+ * reassemble != 0 re-runs the values pass like the reference does on every solve. */
+int fs_solve_host(fs_context *ctx, const double *F, int reassemble, const fs_solve_opts *opts,
+                  double *sols, fs_solve_info *info);
+
+/* ---- coupled step (fsp.cpp:257-374) ------------------------------------ */
+/* interface nodes = nodes on sides with boundary id 2, 20 or 21, ascending node id (fsp.cpp:55-71) */
+int fs_interface_nodes(fs_context *ctx, int64_t *n, int32_t *node_ids /* may be NULL */);
+/* forces in (dims*n_if) -> solve (K cached) -> displacement increment since the last committed
+ * step out (dims*n_if), fsp.cpp:286-317 */
+int fs_step(fs_context *ctx, int dims, char dead_axis, const double *forces_in, const fs_solve_opts *opts,
+            double *displ_delta_out, fs_solve_info *info);
+/* time step converged: preSols <- sols on the interface nodes (fsp.cpp:331-374) */
+int fs_commit_step(fs_context *ctx, int dims, char dead_axis);
+
+/* ---- parity / inspection ------------------------------------------------ */
+/* sizes of the (rank-local) system: numbered nodes, 6x6 blocks, owned node range */
+int fs_get_sizes(fs_context *ctx, int64_t *n_dofnodes, int64_t *n_blocks, int64_t *n_colors,
+                 int64_t *own_begin, int64_t *own_end);
+/* node -> position in the DOF order (-1 for nodes no element references), n_nodes entries */
+int fs_export_dof_order(fs_context *ctx, int32_t *dofnode);
+/* scalar CSR of the owned rows exactly as stored on the device: rowptr (6*n_own+1, int64),
+ * colidx (int32, GLOBAL dof ids; may be NULL), vals (may be NULL).  This is what `-d 1` prints
+ * (fs.cpp:143-150) / -ksp_view_mat would dump. */
+int fs_export_csr(fs_context *ctx, int64_t *rowptr, int32_t *colidx, double *vals);
+int fs_export_rhs(fs_context *ctx, double *rhs /* 6*n_own */);
+/* element matrices as the element kernel forms them, node-major, before the Dirichlet
+ * constraint: Ke[e] is (6 nen)^2 doubles at out + 576*e (row stride 6 nen) */
+int fs_debug_element_matrices(fs_context *ctx, double *out);
+/* y = A x on the device matrix; x, y in DOF order, length 6*n_dofnodes (single rank only) */
+int fs_spmv_host(fs_context *ctx, const double *x, double *y);
+/* times `reps` SpMV launches with CUDA events on the context stream (info->spmv_ms = mean) */
+int fs_bench_spmv(fs_context *ctx, int reps, fs_solve_info *info);
+
+/* ---- reference file formats and generator (host side) ------------------ */
+/* in-memory meshGen (src/meshgen/main_all.cpp:133-387), incl. the 6-significant-digit text
+ * round trip of coordinates and load factor.  Two-call protocol: pass NULL arrays to get sizes. */
+int fs_meshgen(char kind, int nx, int ny, double min_x, double min_y, double max_x, double max_y,
+               const int bcids_tblr[4], double factor, int loading, int ul_lr, char dead_axis,
+               int64_t *n_nodes, int64_t *n_elem, int64_t *n_bc, double *xyz, int32_t *etype,
+               int64_t *eptr, int32_t *enodes, int32_t *bc, double *forces);
+/* XDA reader (fs.cpp:37) and <base>_f reader (fs.cpp:44-67); two-call protocol as above */
+int fs_read_xda(const char *path, int64_t *n_nodes, int64_t *n_elem, int64_t *n_enodes, int64_t *n_bc,
+                double *xyz, int32_t *etype, int64_t *eptr, int32_t *enodes, int32_t *bc);
+int fs_read_forces(const char *path, int64_t n_nodes, double *forces);
+int fs_write_xda(const char *path, int64_t n_nodes, const double *xyz, int64_t n_elem,
+                 const int32_t *etype, const int64_t *eptr, const int32_t *enodes, int64_t n_bc,
+                 const int32_t *bc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEMSHELL_B200_H */
