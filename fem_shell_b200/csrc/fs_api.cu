@@ -5,14 +5,13 @@
 //   Dirichlet sets     fs.cpp:90-120
 //   interface nodes    fsp.cpp:55-71
 //   solution layout    fs.cpp:140-141,163-169
-#include <nccl.h>
-
 #include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <numeric>
 
 #include "fs_context.hpp"
+#include "fs_nccl.hpp"
 
 using namespace fs;
 
@@ -61,7 +60,7 @@ int fs_destroy(fs_context *c)
     FS_CHECK_CTX(c);
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    if (c->comm) ncclCommDestroy((ncclComm_t)c->comm);
+    if (c->comm && nccl().ok) nccl().CommDestroy((ncclComm_t)c->comm);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -79,7 +78,7 @@ int fs_dist_unique_id(uint8_t id_out[128])
 {
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
     ncclUniqueId id;
-    if (ncclGetUniqueId(&id) != ncclSuccess) return FS_ERR_COMM;
+    if (!nccl().ok || nccl().GetUniqueId(&id) != ncclSuccess) return FS_ERR_COMM;
     memcpy(id_out, &id, 128);
     return FS_OK;
 }
@@ -96,8 +95,9 @@ int fs_dist_init(fs_context *c, int rank, int world, const uint8_t id_bytes[128]
         ncclUniqueId id;
         memcpy(&id, id_bytes, 128);
         ncclComm_t comm;
-        ncclResult_t r = ncclCommInitRank(&comm, world, id, rank);
-        if (r != ncclSuccess) return fail(c, FS_ERR_COMM, std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
+        if (!nccl().ok) return fail(c, FS_ERR_COMM, "libnccl.so.2 could not be loaded");
+        ncclResult_t r = nccl().CommInitRank(&comm, world, id, rank);
+        if (r != ncclSuccess) return fail(c, FS_ERR_COMM, std::string("ncclCommInitRank: ") + nccl().GetErrorString(r));
         c->comm = (ncclComm *)comm;
     }
     return FS_OK;
@@ -451,8 +451,8 @@ int fs_get_solution(fs_context *c, double *sols)
     k_solution_to_nodes<<<nblk(6 * c->n_own, 256), 256, 0, c->stream>>>(c->n_own, c->d_node_of_own.p,
                                                                          c->d_x.p + 6 * c->own_lo, c->d_full.p);
     if (c->world > 1) {
-        ncclResult_t r = ncclAllReduce(c->d_full.p, c->d_full.p, 6 * c->n_nodes, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream);
-        if (r != ncclSuccess) return fail(c, FS_ERR_COMM, std::string("ncclAllReduce: ") + ncclGetErrorString(r));
+        ncclResult_t r = nccl().AllReduce(c->d_full.p, c->d_full.p, 6 * c->n_nodes, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream);
+        if (r != ncclSuccess) return fail(c, FS_ERR_COMM, std::string("ncclAllReduce: ") + nccl().GetErrorString(r));
     }
     FS_CUDA(c, cudaMemcpyAsync(sols, c->d_full.p, sizeof(double) * 6 * c->n_nodes, cudaMemcpyDeviceToHost, c->stream));
     FS_CUDA(c, cudaStreamSynchronize(c->stream));

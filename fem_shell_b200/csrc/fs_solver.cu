@@ -12,9 +12,8 @@
 // Reductions are deterministic: per-block partials, the last block to arrive sums them in index
 // order.  Multi-GPU: halo exchange of p before k_spmv_dot (ncclSend/Recv), ncclAllReduce of the
 // partial sums, then a one-thread finalise kernel.
-#include <nccl.h>
-
 #include "fs_context.hpp"
+#include "fs_nccl.hpp"
 
 namespace fs {
 
@@ -22,7 +21,7 @@ namespace fs {
     do {                                                                                       \
         ncclResult_t r__ = (call);                                                             \
         if (r__ != ncclSuccess)                                                                \
-            return fs::fail(ctx, FS_ERR_COMM, std::string(#call) + ": " + ncclGetErrorString(r__)); \
+            return fs::fail(ctx, FS_ERR_COMM, std::string(#call) + ": " + fs::nccl().GetErrorString(r__)); \
     } while (0)
 
 static inline unsigned int nblk(int64_t n, int bs) { return (unsigned int)((n + bs - 1) / bs); }
@@ -457,14 +456,14 @@ int halo_exchange(fs_context *c, double *d_vec)
     if (c->world == 1 || c->peers.empty()) return FS_OK;
     if (c->send_total)
         k_pack<<<nblk(3 * c->send_total, 256), 256, 0, c->stream>>>(c->send_total, c->d_send_idx.p, d_vec, c->d_sendbuf.p);
-    FS_NCCL(c, ncclGroupStart());
+    FS_NCCL(c, nccl().GroupStart());
     for (const Peer &pr : c->peers) {
         if (pr.send_count)
-            FS_NCCL(c, ncclSend(c->d_sendbuf.p + 6 * pr.send_off, 6 * pr.send_count, ncclDouble, pr.rank, (ncclComm_t)c->comm, c->stream));
+            FS_NCCL(c, nccl().Send(c->d_sendbuf.p + 6 * pr.send_off, 6 * pr.send_count, ncclDouble, pr.rank, (ncclComm_t)c->comm, c->stream));
         if (pr.recv_count)
-            FS_NCCL(c, ncclRecv(d_vec + 6 * pr.recv_off, 6 * pr.recv_count, ncclDouble, pr.rank, (ncclComm_t)c->comm, c->stream));
+            FS_NCCL(c, nccl().Recv(d_vec + 6 * pr.recv_off, 6 * pr.recv_count, ncclDouble, pr.rank, (ncclComm_t)c->comm, c->stream));
     }
-    FS_NCCL(c, ncclGroupEnd());
+    FS_NCCL(c, nccl().GroupEnd());
     return FS_OK;
 }
 
@@ -505,14 +504,14 @@ static int enqueue_iteration(fs_context *c, double *red, int sg, int vg)
                                                  c->d_q.p + o6, c->d_p.p + o6, c->d_partials.p, c->d_counter.p,
                                                  c->d_state.p, red, single);
     if (!single) {
-        FS_NCCL(c, ncclAllReduce(red, red, 1, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
+        FS_NCCL(c, nccl().AllReduce(red, red, 1, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
         k_finalize<<<1, 1, 0, c->stream>>>(c->d_state.p, red, 1);
     }
     k_update<PC, NORM, 256><<<vg, 256, 0, c->stream>>>(c->n_own, c->d_x.p + o6, c->d_r.p + o6, c->d_p.p + o6,
                                                        c->d_q.p + o6, c->d_z.p + o6, c->d_minv.p, c->d_partials.p,
                                                        c->d_counter.p, c->d_state.p, red + 4, single);
     if (!single) {
-        FS_NCCL(c, ncclAllReduce(red + 4, red + 4, 2, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
+        FS_NCCL(c, nccl().AllReduce(red + 4, red + 4, 2, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
         k_finalize<<<1, 1, 0, c->stream>>>(c->d_state.p, red + 4, 2);
     }
     k_direction<256><<<vg, 256, 0, c->stream>>>(c->n_own, c->d_z.p + o6, c->d_p.p + o6, c->d_state.p);
@@ -547,7 +546,7 @@ static int run_pcg(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
                                               c->d_p.p + o6, c->d_minv.p, c->d_partials.p, c->d_counter.p,
                                               c->d_state.p, red + 8, single);
     if (!single) {
-        FS_NCCL(c, ncclAllReduce(red + 8, red + 8, 3, ncclDouble, ncclSum, (ncclComm_t)c->comm, st));
+        FS_NCCL(c, nccl().AllReduce(red + 8, red + 8, 3, ncclDouble, ncclSum, (ncclComm_t)c->comm, st));
         k_finalize<<<1, 1, 0, st>>>(c->d_state.p, red + 8, 0);
     }
     const int batch = o->check_every > 0 ? o->check_every : 64;
