@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "fs_set_nodal_loads", "fs_set_interface_loads", "fs_build_rhs", "fs_assemble", "fs_solve",
     "fs_get_solution", "fs_solve_host", "fs_interface_nodes", "fs_step", "fs_commit_step", "fs_get_sizes",
     "fs_export_dof_order", "fs_export_csr", "fs_export_rhs", "fs_debug_element_matrices", "fs_spmv_host",
-    "fs_bench_spmv", "fs_meshgen", "fs_read_xda", "fs_read_forces", "fs_write_xda",
+    "fs_bench_spmv", "fs_partition_plan", "fs_meshgen", "fs_read_xda", "fs_read_forces", "fs_write_xda",
 ]
 
 
@@ -112,6 +112,25 @@ def meshgen(kind, nx, ny, min_x, min_y, max_x, max_y, bcids, factor, loading, ul
     if rc:
         raise FemShellError(rc, "fs_meshgen failed")
     return dict(xyz=xyz, etype=etype, eptr=eptr, enodes=enodes, bc=bc, forces=F)
+
+
+def partition_plan(eptr, enodes, n_nodes, rank, world, dof_mode=DOF_FIRST_ENCOUNTER):
+    """host-only node-block partition plan of one rank (fs_partition_plan)"""
+    lib = load_library()
+    eptr, enodes = _i64(eptr), _i32(enodes)
+    sizes = np.zeros(8, np.int64)
+    args = [C.c_int64(n_nodes), C.c_int64(eptr.size - 1), _p(eptr), _p(enodes), C.c_int(dof_mode), C.c_int(rank), C.c_int(world)]
+    rc = lib.fs_partition_plan(*args, _p(sizes), None, None, None, None)
+    if rc:
+        raise FemShellError(rc, "fs_partition_plan: bad arguments")
+    l2g = np.empty(sizes[4], np.int32); le = np.empty(sizes[5], np.int32); si = np.empty(sizes[6], np.int32)
+    pt = np.empty((sizes[7], 5), np.int64)
+    rc = lib.fs_partition_plan(*args, _p(sizes), _p(l2g), _p(le), _p(si), _p(pt))
+    if rc:
+        raise FemShellError(rc, "fs_partition_plan failed")
+    return dict(n_global=int(sizes[0]), own_begin=int(sizes[1]), own_end=int(sizes[2]), own_lo=int(sizes[3]),
+                local_to_global=l2g, loc_elems=le, send_idx=si,
+                peers=[dict(rank=int(r[0]), send_count=int(r[1]), send_off=int(r[2]), recv_count=int(r[3]), recv_off=int(r[4])) for r in pt])
 
 
 def read_xda(path):

@@ -12,6 +12,7 @@
 
 #include "fs_context.hpp"
 #include "fs_nccl.hpp"
+#include "fs_partition.hpp"
 
 using namespace fs;
 
@@ -141,15 +142,6 @@ int fs_set_assembly_mode(fs_context *c, int mode)
 // ---------------------------------------------------------------------------------------------
 // mesh ingestion
 // ---------------------------------------------------------------------------------------------
-static int owner_of(int64_t g, int64_t n_g, int world)
-{
-    // rank r owns [r*n_g/world, (r+1)*n_g/world)
-    int r = (int)((g * world) / n_g);
-    while (r > 0 && g < (int64_t)r * n_g / world) r--;
-    while (r < world - 1 && g >= (int64_t)(r + 1) * n_g / world) r++;
-    return r;
-}
-
 int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_elem, const int32_t *etype,
                 const int64_t *eptr, const int32_t *enodes, int64_t n_bc, const int32_t *bc)
 {
@@ -171,17 +163,7 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
     c->pattern_ready = c->assembled = c->loads_set = c->rhs_ready = c->have_solution = false;
 
     // ---- DOF order (a12) ----
-    c->dofnode.assign(n_nodes, -1);
-    int64_t next = 0;
-    if (c->dof_mode == FS_DOF_FIRST_ENCOUNTER) {
-        for (int64_t k = 0; k < eptr[n_elem]; k++)
-            if (c->dofnode[enodes[k]] < 0) c->dofnode[enodes[k]] = (int32_t)next++;
-    } else {
-        for (int64_t k = 0; k < eptr[n_elem]; k++) c->dofnode[enodes[k]] = 0;
-        for (int64_t i = 0; i < n_nodes; i++)
-            if (c->dofnode[i] == 0) c->dofnode[i] = (int32_t)next++;
-    }
-    const int64_t n_g = next;
+    const int64_t n_g = compute_dof_order(c->dof_mode, n_nodes, n_elem, eptr, enodes, c->dofnode);
     c->n_dofnodes_global = n_g;
     c->node_of_dof.assign(n_g, -1);
     for (int64_t i = 0; i < n_nodes; i++)
@@ -209,73 +191,29 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
     c->sols.assign(6 * n_nodes, 0.0);
     c->pre_sols.assign(6 * n_nodes, 0.0);
 
-    // ---- node-block partition of the DOF order ----
-    const int W = c->world, R = c->rank;
-    if (n_g < W) return fail(c, FS_ERR_ARG, "fewer nodes than ranks");
-    c->own_begin = (int64_t)R * n_g / W;
-    c->own_end = (int64_t)(R + 1) * n_g / W;
-    c->n_own = c->own_end - c->own_begin;
-
-    // local elements = elements touching an owned node; local nodes = their nodes + owned nodes
-    std::vector<uint8_t> is_local_node(n_g, 0);
-    for (int64_t g = c->own_begin; g < c->own_end; g++) is_local_node[g] = 1;
-    std::vector<int32_t> loc_elems;
-    std::vector<std::vector<int32_t>> send(W);
-    for (int64_t e = 0; e < n_elem; e++) {
-        bool mine = false;
-        int owners[4];
-        const int nen = (int)(eptr[e + 1] - eptr[e]);
-        for (int k = 0; k < nen; k++) {
-            int64_t g = c->dofnode[enodes[eptr[e] + k]];
-            owners[k] = (W == 1) ? 0 : owner_of(g, n_g, W);
-            mine = mine || owners[k] == R;
-        }
-        if (!mine) continue;
-        loc_elems.push_back((int32_t)e);
-        for (int k = 0; k < nen; k++) {
-            int32_t g = c->dofnode[enodes[eptr[e] + k]];
-            is_local_node[g] = 1;
-            if (owners[k] == R)
-                for (int l = 0; l < nen; l++)
-                    if (owners[l] != R) send[owners[l]].push_back(g);
-        }
-    }
-    c->local_to_global.clear();
-    for (int64_t g = 0; g < n_g; g++)
-        if (is_local_node[g]) c->local_to_global.push_back((int32_t)g);
+    // ---- node-block partition of the DOF order (fs_partition.cpp) ----
+    PartitionPlan plan;
+    if (plan_partition(c->dofnode, n_g, n_elem, eptr, enodes, c->rank, c->world, plan) != FS_OK)
+        return fail(c, FS_ERR_ARG, "fewer nodes than ranks");
+    c->own_begin = plan.own_begin;
+    c->own_end = plan.own_end;
+    c->n_own = plan.own_end - plan.own_begin;
+    c->own_lo = plan.own_lo;
+    c->local_to_global = plan.local_to_global;
     c->n_local = (int64_t)c->local_to_global.size();
     std::vector<int32_t> g2l(n_g, -1);
     for (int64_t l = 0; l < c->n_local; l++) g2l[c->local_to_global[l]] = (int32_t)l;
-    c->own_lo = g2l[c->own_begin];
-
-    // halo lists: recv segments are contiguous per owner because local order == global order
+    const std::vector<int32_t> &loc_elems = plan.loc_elems;
+    const std::vector<int32_t> &send_idx = plan.send_idx;
     c->peers.clear();
-    c->send_total = 0;
-    std::vector<int32_t> send_idx;
-    for (int r = 0; r < W; r++) {
-        if (r == R) continue;
+    for (const PeerPlan &pp : plan.peers) {
         Peer pr;
-        pr.rank = r;
-        auto &s = send[r];
-        std::sort(s.begin(), s.end());
-        s.erase(std::unique(s.begin(), s.end()), s.end());
-        pr.send_count = (int64_t)s.size();
-        pr.send_off = c->send_total;
-        for (int32_t g : s) send_idx.push_back(g2l[g]);
-        c->send_total += pr.send_count;
-        const int64_t rb = (int64_t)r * n_g / W, re = (int64_t)(r + 1) * n_g / W;
-        int64_t first = -1, cnt = 0;
-        for (int64_t l = 0; l < c->n_local; l++) {
-            int32_t g = c->local_to_global[l];
-            if (g >= rb && g < re) {
-                if (first < 0) first = l;
-                cnt++;
-            }
-        }
-        pr.recv_count = cnt;
-        pr.recv_off = first < 0 ? 0 : first;
-        if (pr.send_count || pr.recv_count) c->peers.push_back(pr);
+        pr.rank = pp.rank;
+        pr.send_count = pp.send_count; pr.send_off = pp.send_off;
+        pr.recv_count = pp.recv_count; pr.recv_off = pp.recv_off;
+        c->peers.push_back(pr);
     }
+    c->send_total = (int64_t)send_idx.size();
     FS_CUDA(c, c->d_send_idx.alloc(send_idx.size()));
     FS_CUDA(c, c->d_sendbuf.alloc(6 * send_idx.size()));
     if (!send_idx.empty())

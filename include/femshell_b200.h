@@ -165,6 +165,15 @@ int fs_spmv_host(fs_context *ctx, const double *x, double *y);
 /* times `reps` SpMV launches with CUDA events on the context stream (info->spmv_ms = mean) */
 int fs_bench_spmv(fs_context *ctx, int reps, fs_solve_info *info);
 
+/* host-only (no GPU): the node-block partition plan rank `rank` of `world` derives from the replicated
+ * mesh -- owned range, local nodes, local elements, halo send lists and recv segments.  Two-call
+ * protocol (NULL arrays -> sizes only).  sizes = {n_dofnodes, own_begin, own_end, own_lo, n_local,
+ * n_local_elems, n_send, n_peers}; peer_table rows = {rank, send_count, send_off, recv_count, recv_off}.
+ * Mirrors libMesh's partitioned element loop / PETSc's VecScatter setup (fs.cpp:1197). */
+int fs_partition_plan(int64_t n_nodes, int64_t n_elem, const int64_t *eptr, const int32_t *enodes, int dof_mode,
+                      int rank, int world, int64_t sizes[8], int32_t *local_to_global, int32_t *loc_elems,
+                      int32_t *send_idx, int64_t *peer_table);
+
 /* ---- reference file formats and generator (host side) ------------------ */
 /* in-memory meshGen (src/meshgen/main_all.cpp:133-387), incl. the 6-significant-digit text
  * round trip of coordinates and load factor.  Two-call protocol: pass NULL arrays to get sizes. */

@@ -1,0 +1,72 @@
+"""torchrun worker for the multi-GPU parity test (tests/test_gpu_multi.py): every rank drives one GPU
+through the C ABI; rank-local CSR rows and the distributed solve are checked against the CPU oracle
+and against a single-GPU context."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch
+import torch.distributed as dist
+
+import fem_shell_b200 as fsb
+import meshes
+from oracle import fso
+
+
+def main():
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    ids = [fsb.FemShell.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    cases = {
+        "tri": (fsb.meshgen("t", 40, 33, 0, 0, 10, 10, (1, 1, 1, 1), 300.0, 2, 1), 0.3, 1e7, 0.5),
+        "quad": (fsb.meshgen("q", 31, 47, 0, 0, 10, 10, (0, 1, 0, 1), 300.0, 2, 1), 0.3, 1e7, 0.5),
+        "mixed": (meshes.folded_cantilever(nx=24, ny=10, skew=0.3), 0.3, 1e4, 0.25),
+    }
+    for name, (m, nu, E, t) in cases.items():
+        om = fso.Mesh(np.asarray(m["xyz"], float), m["etype"], m["eptr"], m["enodes"], m["bc"])
+        ref = fso.assemble(om, m["forces"], nu, E, t)
+        s = fsb.FemShell(device=lr, rank=rank, world=world, nccl_id=ids[0])
+        s.set_material(nu, E, t)
+        s.set_mesh(m["xyz"], m["etype"], m["eptr"], m["enodes"], m["bc"])
+        s.set_nodal_loads(m["forces"])
+        s.assemble()
+        sz = s.sizes()
+        ob, oe = sz["own_begin"], sz["own_end"]
+        rowptr, colidx, vals = s.export_csr()
+        rr, rc, rv = ref.csr()
+        lo, hi = rr[6 * ob], rr[6 * oe]
+        assert np.array_equal(rowptr, rr[6 * ob:6 * oe + 1] - lo), name
+        assert np.array_equal(colidx, rc[lo:hi]), name
+        assert np.abs(vals - rv[lo:hi]).max() <= 1e-12 * np.abs(rv).max(), name
+        assert np.array_equal(s.export_rhs(), ref.rhs[6 * ob:6 * oe]), name
+        info = s.solve(rtol=1e-12, max_its=400000, pc=fsb.PC_BJACOBI6, warm_start=False)
+        u = s.solution()
+        uo = fso.direct_solve(om, ref)
+        err = np.linalg.norm(u - uo) / np.linalg.norm(uo)
+        assert err <= 1e-8, (name, err)
+        # same iteration count (+-1%) as a single-GPU context on the same mesh
+        s1 = fsb.FemShell(device=lr)
+        s1.set_material(nu, E, t)
+        s1.set_mesh(m["xyz"], m["etype"], m["eptr"], m["enodes"], m["bc"])
+        s1.set_nodal_loads(m["forces"])
+        s1.assemble()
+        i1 = s1.solve(rtol=1e-12, max_its=400000, pc=fsb.PC_BJACOBI6, warm_start=False)
+        assert abs(i1.iterations - info.iterations) <= max(3, i1.iterations // 50), (name, i1.iterations, info.iterations)
+        u1 = s1.solution()
+        assert np.linalg.norm(u - u1) <= 1e-8 * np.linalg.norm(u1)
+        if rank == 0:
+            print("dist ok %-6s world=%d iterations %d (single %d) err %.2e" % (name, world, info.iterations, i1.iterations, err), flush=True)
+        s.close(); s1.close()
+        dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
