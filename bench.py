@@ -162,6 +162,7 @@ def run_ours(args):
     n_nodes, n_elem = m["xyz"].shape[0], m["etype"].size
     s = fsb.FemShell(device=local_rank, rank=rank, world=world, nccl_id=nccl_id)
     s.set_material(NU, EM, THICK)
+    s.set_assembly_mode(fsb.ASM_GATHER if args.asm == "gather" else fsb.ASM_COLORED)
     t0 = time.perf_counter()
     s.set_mesh(m["xyz"], m["etype"], m["eptr"], m["enodes"], m["bc"])
     t_setup = time.perf_counter() - t0
@@ -296,7 +297,7 @@ def run_ours(args):
                    "parallelism": "node-block strips x%d" % world},
         "metrics": {"cg_dof_iterations_per_s": value, "elements_assembled_per_s": n_elem / (asm_ms * 1e-3),
                     "assemble_ms": asm_ms, "time_to_solution": tts, "setup_s_pattern_colouring_upload": t_setup,
-                    "colors": sz["n_colors"]},
+                    "colors": sz["n_colors"], "assembly_mode": args.asm},
         "roofline": {"bound": "hbm", "kernel": "k_spmv", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "bytes_per_launch": actual_b, "csr_equiv_bytes_per_launch": csr_b,
                      "csr_equiv_gbs": csr_b / (spmv_ms * 1e-3) / 1e9, "ms_per_launch": spmv_ms,
@@ -326,6 +327,7 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=30)
     ap.add_argument("--ref-nodes", type=int, default=1000)
     ap.add_argument("--ref-iters", type=int, default=10)
+    ap.add_argument("--asm", default="gather", choices=["colored", "gather"])
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes/launch of k_spmv from an ncu --set full capture")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

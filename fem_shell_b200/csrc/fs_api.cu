@@ -161,6 +161,7 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
     c->n_nodes = n_nodes;
     c->n_elem = n_elem;
     c->pattern_ready = c->assembled = c->loads_set = c->rhs_ready = c->have_solution = false;
+    c->gather_ready = c->gather_unavailable = false;
 
     // ---- DOF order (a12) ----
     const int64_t n_g = compute_dof_order(c->dof_mode, n_nodes, n_elem, eptr, enodes, c->dofnode);

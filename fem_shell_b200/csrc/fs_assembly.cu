@@ -14,6 +14,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cstring>
 
 #include "fs_context.hpp"
 #include "fs_elements.cuh"
@@ -462,12 +463,241 @@ k_assemble_colored(const int32_t *__restrict__ conn, const int32_t *__restrict__
     else if (NEN == 4) scatter_row<NEN, (NEN == 4 ? 3 : 0)>(X, nodes, ps, mask, nptr, vals, own_lo);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// values pass, row gather ("owner computes").  A thread block owns a run of block rows whose CSR
+// values fit in shared memory.  Thread = one (element, node row I) incidence of those rows; it
+// forms its row slice in registers, then the incidences of a row add their 6x6 blocks into shared
+// memory in a fixed order (round r = r-th incident element of the row, ordered by type and
+// element id; rows are disjoint, so a round needs no atomics).  Finally the block streams its rows
+// to HBM: every CSR value is written exactly once, fully coalesced, and never read.
+// Warps are uniform in (element type, I): the thread table is grouped and padded per group.
+// ---------------------------------------------------------------------------------------------
+constexpr int GATHER_THREADS = 128;
+constexpr int GATHER_MAX_VALS = 10240;  // doubles of shared memory per block (80 KB, two blocks per SM)
+
+template <int NEN>
+__device__ __forceinline__ void gather_emit(const double T[3][3], double Km[4][2][2], double Kp[4][3][3], int I,
+                                            const int *slot, const unsigned *mcol, double *srow, int L)
+{
+    const unsigned mrow = mcol[I];
+#pragma unroll
+    for (int j = 0; j < NEN; j++) {
+        double G[6][6];
+        rotate_block(T, Km[j], Kp[j], G);
+        double *dst = srow + 6 * slot[j];
+        const unsigned mc = mcol[j];
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            const bool ra = (mrow >> a) & 1u;
+#pragma unroll
+            for (int b = 0; b < 6; b++) {
+                double v = G[a][b];
+                if (ra || ((mc >> b) & 1u)) v = (ra && j == I && a == b) ? 1.0 : 0.0;  // fs.cpp:1227
+                dst[a * L + b] += v;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(GATHER_THREADS, 2)
+k_assemble_gather(const GatherChunk *__restrict__ chunks, const int32_t *__restrict__ g_elem,
+                  const int32_t *__restrict__ g_meta, const int32_t *__restrict__ tri,
+                  const int32_t *__restrict__ tri_pos, const int32_t *__restrict__ quad,
+                  const int32_t *__restrict__ quad_pos, const double *__restrict__ xyz,
+                  const uint8_t *__restrict__ mask, const int32_t *__restrict__ nptr, double *__restrict__ vals,
+                  int own_lo)
+{
+    extern __shared__ double sv[];
+    const GatherChunk ch = chunks[blockIdx.x];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < ch.val_count; i += GATHER_THREADS) sv[i] = 0.0;
+
+    int e = -1, meta = 0;
+    if (tid < ch.n_threads) {
+        e = g_elem[ch.thread_off + tid];
+        meta = g_meta[ch.thread_off + tid];
+    }
+    const int I = meta & 3, is_quad = (meta >> 2) & 1, round = (meta >> 3) & 31;
+    double Km[4][2][2], Kp[4][3][3], T[3][3];
+    int slot[4];
+    unsigned mcol[4];
+    double *srow = sv;
+    int L = 0;
+    if (e >= 0) {
+        if (is_quad) {
+            double X[12];
+            int row = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int n = quad[4 * (size_t)e + k];
+                if (k == I) row = n - own_lo;
+                mcol[k] = mask[n];
+                slot[k] = quad_pos[16 * (size_t)e + 4 * I + k];
+                X[3 * k] = xyz[3 * (size_t)n]; X[3 * k + 1] = xyz[3 * (size_t)n + 1]; X[3 * k + 2] = xyz[3 * (size_t)n + 2];
+            }
+            const int b0 = nptr[row];
+            L = 6 * (nptr[row + 1] - b0);
+            srow = sv + 36 * (size_t)(b0 - nptr[ch.row0]);
+            QuadGeom g;
+            quad_geom(X, g);
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int c2 = 0; c2 < 3; c2++) T[r][c2] = g.T[r][c2];
+            quad_membrane_row_rt(g, I, Km);
+            quad_plate_row_rt(g, I, Kp);
+        } else {
+            double X[9];
+            int row = 0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int n = tri[3 * (size_t)e + k];
+                if (k == I) row = n - own_lo;
+                mcol[k] = mask[n];
+                slot[k] = tri_pos[9 * (size_t)e + 3 * I + k];
+                X[3 * k] = xyz[3 * (size_t)n]; X[3 * k + 1] = xyz[3 * (size_t)n + 1]; X[3 * k + 2] = xyz[3 * (size_t)n + 2];
+            }
+            mcol[3] = 0; slot[3] = 0;
+            const int b0 = nptr[row];
+            L = 6 * (nptr[row + 1] - b0);
+            srow = sv + 36 * (size_t)(b0 - nptr[ch.row0]);
+            TriGeom g;
+            tri_geom(X, g);
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int c2 = 0; c2 < 3; c2++) T[r][c2] = g.T[r][c2];
+            tri_membrane_row_rt(g, I, Km);
+            tri_plate_row_rt(g, I, Kp);
+        }
+    }
+    __syncthreads();
+    for (int r = 0; r < ch.n_rounds; r++) {
+        if (e >= 0 && round == r) {
+            if (is_quad) gather_emit<4>(T, Km, Kp, I, slot, mcol, srow, L);
+            else gather_emit<3>(T, Km, Kp, I, slot, mcol, srow, L);
+        }
+        __syncthreads();
+    }
+    // stream the finished rows out (contiguous in the CSR value array)
+    double2 *out = reinterpret_cast<double2 *>(vals + 36 * (size_t)nptr[ch.row0]);
+    const double2 *s2 = reinterpret_cast<const double2 *>(sv);
+    for (int i = tid; i < ch.val_count / 2; i += GATHER_THREADS) __stcs(out + i, s2[i]);
+}
+
+// host: build the thread table of the row-gather pass from the colour-sorted element arrays
+int build_gather_schedule(fs_context *c)
+{
+    if (c->gather_ready || c->gather_unavailable) return FS_OK;
+    const int64_t nt = c->n_tri, nq = c->n_quad, n_own = c->n_own;
+    const int own_lo = (int)c->own_lo;
+    std::vector<int32_t> tri(3 * nt), quad(4 * nq), tgid(nt), qgid(nq), nptr(n_own + 1);
+    if (nt) {
+        FS_CUDA(c, cudaMemcpy(tri.data(), c->d_tri.p, sizeof(int32_t) * 3 * nt, cudaMemcpyDeviceToHost));
+        FS_CUDA(c, cudaMemcpy(tgid.data(), c->d_tri_gid.p, sizeof(int32_t) * nt, cudaMemcpyDeviceToHost));
+    }
+    if (nq) {
+        FS_CUDA(c, cudaMemcpy(quad.data(), c->d_quad.p, sizeof(int32_t) * 4 * nq, cudaMemcpyDeviceToHost));
+        FS_CUDA(c, cudaMemcpy(qgid.data(), c->d_quad_gid.p, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost));
+    }
+    FS_CUDA(c, cudaMemcpy(nptr.data(), c->d_nptr.p, sizeof(int32_t) * (n_own + 1), cudaMemcpyDeviceToHost));
+
+    struct Inc { int32_t row, gid, eidx; uint8_t type, I; };
+    std::vector<int32_t> cnt(n_own + 1, 0);
+    for (int64_t e = 0; e < nt; e++)
+        for (int k = 0; k < 3; k++) { int p = tri[3 * e + k] - own_lo; if (p >= 0 && p < n_own) cnt[p + 1]++; }
+    for (int64_t e = 0; e < nq; e++)
+        for (int k = 0; k < 4; k++) { int p = quad[4 * e + k] - own_lo; if (p >= 0 && p < n_own) cnt[p + 1]++; }
+    for (int64_t p = 0; p < n_own; p++) cnt[p + 1] += cnt[p];
+    std::vector<Inc> inc(cnt[n_own]);
+    std::vector<int32_t> fill(cnt.begin(), cnt.end() - 1);
+    for (int64_t e = 0; e < nt; e++)
+        for (int k = 0; k < 3; k++) { int p = tri[3 * e + k] - own_lo; if (p >= 0 && p < n_own) inc[fill[p]++] = {(int32_t)p, tgid[e], (int32_t)e, 0, (uint8_t)k}; }
+    for (int64_t e = 0; e < nq; e++)
+        for (int k = 0; k < 4; k++) { int p = quad[4 * e + k] - own_lo; if (p >= 0 && p < n_own) inc[fill[p]++] = {(int32_t)p, qgid[e], (int32_t)e, 1, (uint8_t)k}; }
+    for (int64_t p = 0; p < n_own; p++)  // fixed summation order inside a row: triangles first, then by element id
+        std::sort(inc.begin() + cnt[p], inc.begin() + cnt[p + 1], [](const Inc &a, const Inc &b) {
+            return a.type != b.type ? a.type < b.type : a.gid < b.gid;
+        });
+
+    std::vector<GatherChunk> chunks;
+    std::vector<int32_t> g_elem, g_meta;
+    auto padded = [](const int gc[7]) { int t = 0; for (int g = 0; g < 7; g++) t += (gc[g] + 31) / 32 * 32; return t; };
+    int64_t row = 0;
+    while (row < n_own) {
+        int gc[7] = {0, 0, 0, 0, 0, 0, 0};
+        int64_t r1 = row, vals = 0;
+        int rounds = 0;
+        while (r1 < n_own) {
+            int g2[7];
+            memcpy(g2, gc, sizeof gc);
+            for (int k = cnt[r1]; k < cnt[r1 + 1]; k++) g2[inc[k].type * 3 + inc[k].I]++;
+            const int64_t v2 = vals + 36 * (int64_t)(nptr[r1 + 1] - nptr[r1]);
+            if (padded(g2) > GATHER_THREADS || v2 > GATHER_MAX_VALS || r1 - row >= 4095) break;
+            memcpy(gc, g2, sizeof gc);
+            vals = v2;
+            rounds = std::max(rounds, cnt[r1 + 1] - cnt[r1]);
+            r1++;
+        }
+        if (r1 == row || rounds > 31) {  // a single row does not fit: leave this mesh to the coloured pass
+            c->gather_unavailable = true;
+            return FS_OK;
+        }
+        GatherChunk ch;
+        ch.row0 = (int)row; ch.row1 = (int)r1;
+        ch.thread_off = (int)g_elem.size();
+        ch.n_rounds = rounds;
+        ch.val_count = (int)vals;
+        for (int g = 0; g < 7; g++) {
+            int n = 0;
+            for (int64_t p = row; p < r1; p++)
+                for (int k = cnt[p]; k < cnt[p + 1]; k++)
+                    if (inc[k].type * 3 + inc[k].I == g) {
+                        g_elem.push_back(inc[k].eidx);
+                        g_meta.push_back(inc[k].I | (inc[k].type << 2) | ((k - cnt[p]) << 3));
+                        n++;
+                    }
+            for (; n % 32; n++) { g_elem.push_back(-1); g_meta.push_back(0); }
+        }
+        ch.n_threads = (int)g_elem.size() - ch.thread_off;
+        chunks.push_back(ch);
+        row = r1;
+    }
+    c->n_g_chunks = (int64_t)chunks.size();
+    FS_CUDA(c, c->d_g_chunks.alloc(chunks.size()));
+    FS_CUDA(c, c->d_g_elem.alloc(g_elem.size()));
+    FS_CUDA(c, c->d_g_meta.alloc(g_meta.size()));
+    FS_CUDA(c, cudaMemcpy(c->d_g_chunks.p, chunks.data(), sizeof(GatherChunk) * chunks.size(), cudaMemcpyHostToDevice));
+    FS_CUDA(c, cudaMemcpy(c->d_g_elem.p, g_elem.data(), sizeof(int32_t) * g_elem.size(), cudaMemcpyHostToDevice));
+    FS_CUDA(c, cudaMemcpy(c->d_g_meta.p, g_meta.data(), sizeof(int32_t) * g_meta.size(), cudaMemcpyHostToDevice));
+    FS_CUDA(c, cudaFuncSetAttribute(k_assemble_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, GATHER_MAX_VALS * (int)sizeof(double)));
+    c->gather_ready = true;
+    return FS_OK;
+}
+
 int assemble_values(fs_context *c, float *ms)
 {
     cudaStream_t st = c->stream;
     int rc = upload_element_constants(c);
     if (rc) return rc;
+    if (c->asm_mode == FS_ASM_GATHER) {
+        rc = build_gather_schedule(c);
+        if (rc) return rc;
+    }
     FS_CUDA(c, cudaEventRecord(c->ev0, st));
+    if (c->asm_mode == FS_ASM_GATHER && c->gather_ready) {
+        k_assemble_gather<<<(unsigned)c->n_g_chunks, GATHER_THREADS, GATHER_MAX_VALS * sizeof(double), st>>>(
+            c->d_g_chunks.p, c->d_g_elem.p, c->d_g_meta.p, c->d_tri.p, c->d_tri_pos.p, c->d_quad.p, c->d_quad_pos.p,
+            c->d_xyz.p, c->d_mask.p, c->d_nptr.p, c->d_vals.p, (int)c->own_lo);
+        FS_CUDA(c, cudaEventRecord(c->ev1, st));
+        FS_CUDA(c, cudaStreamSynchronize(st));
+        FS_CUDA(c, cudaGetLastError());
+        if (ms) FS_CUDA(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
+        c->assembled = true;
+        c->minv_kind = -1;
+        return FS_OK;
+    }
     FS_CUDA(c, cudaMemsetAsync(c->d_vals.p, 0, sizeof(double) * 36 * (size_t)c->n_blocks, st));
     constexpr int G = 2;
     for (int64_t k = 0; k < c->n_colors; k++) {

@@ -52,6 +52,15 @@ struct CgState {
     int status;       // FS_OK / FS_ERR_NOT_CONVERGED / FS_ERR_BREAKDOWN
 };
 
+// one thread block of the row-gather assembly: block rows [row0,row1) accumulated in shared memory
+struct GatherChunk {
+    int row0, row1;      // owned block rows
+    int thread_off;      // first entry of this chunk in the thread table
+    int n_threads;       // entries (padded per (type, I) group to whole warps)
+    int n_rounds;        // max number of elements incident to one row of the chunk
+    int val_count;       // 36 * (nptr[row1] - nptr[row0]) doubles staged in shared memory
+};
+
 struct Peer {
     int rank = -1;
     int64_t send_count = 0;   // nodes
@@ -105,8 +114,11 @@ struct fs_context {
     fs::DevBuf<int32_t> d_tri_gid, d_quad_gid;  // original element id (debug / determinism)
     std::vector<int64_t> tri_color_off, quad_color_off;  // n_colors+1 offsets
     int64_t n_colors = 0;
-    // node -> incident (element,row) lists for the gather assembly
-    fs::DevBuf<int32_t> d_inc_ptr, d_inc;
+    // row-gather assembly schedule (fs_assembly.cu, build_gather_schedule)
+    fs::DevBuf<fs::GatherChunk> d_g_chunks;
+    fs::DevBuf<int32_t> d_g_elem, d_g_meta;
+    int64_t n_g_chunks = 0;
+    bool gather_ready = false, gather_unavailable = false;
 
     // block-CSR matrix of the owned rows: row 6p+a occupies vals[36*nptr[p] + a*6*deg ...]
     fs::DevBuf<int32_t> d_nptr;            // n_own+1
@@ -160,6 +172,7 @@ int upload_element_constants(fs_context *c);
 int build_pattern(fs_context *c, const std::vector<int32_t> &tri, const std::vector<int32_t> &quad,
                   const std::vector<int32_t> &tri_gid, const std::vector<int32_t> &quad_gid);
 int assemble_values(fs_context *c, float *ms);
+int build_gather_schedule(fs_context *c);
 int build_rhs(fs_context *c, double scale);
 int debug_element_matrices(fs_context *c, double *out_host);
 

@@ -86,8 +86,8 @@ __device__ __forceinline__ void cross3(const double a[3], const double b[3], dou
 
 __device__ __forceinline__ void unit3(double a[3])
 {
-    double l = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
-    a[0] /= l; a[1] /= l; a[2] /= l;
+    const double li = 1.0 / sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    a[0] *= li; a[1] *= li; a[2] *= li;
 }
 
 // X: 3 nodes x 3 coordinates
@@ -224,6 +224,61 @@ __device__ __forceinline__ void quad_membrane_row(const QuadGeom &g, double Km[4
         const double f = det * c_el.thickness;
 #pragma unroll
         for (int j = 0; j < 4; j++) membrane_accum(f, px[I], py[I], px[j], py[j], Km[j]);
+    }
+}
+
+// run-time node row (callers keep I warp-uniform): same arithmetic, one copy of the code
+__device__ __forceinline__ double pick3(int I, const double v[3]) { return I == 0 ? v[0] : (I == 1 ? v[1] : v[2]); }
+__device__ __forceinline__ double pick4(int I, const double v[4]) { return I == 0 ? v[0] : (I == 1 ? v[1] : (I == 2 ? v[2] : v[3])); }
+
+__device__ __forceinline__ void tri_membrane_row_rt(const TriGeom &g, int I, double Km[4][2][2])
+{
+    const double s = 1.0 / (2.0 * g.area);
+    const double px[3] = {g.y23 * s, g.y31 * s, g.y12 * s};
+    const double py[3] = {-g.x23 * s, -g.x31 * s, -g.x12 * s};
+    const double f = c_el.thickness * g.area;
+    const double pxI = pick3(I, px), pyI = pick3(I, py);
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        Km[j][0][0] = Km[j][0][1] = Km[j][1][0] = Km[j][1][1] = 0.0;
+        membrane_accum(f, pxI, pyI, px[j], py[j], Km[j]);
+    }
+}
+
+__device__ __forceinline__ void quad_membrane_row_rt(const QuadGeom &g, int I, double Km[4][2][2])
+{
+    const double root = 0.57735026918962584;
+    const bool quirk = (c_el.quirks & FS_Q_DETLU) != 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) Km[j][0][0] = Km[j][0][1] = Km[j][1][0] = Km[j][1][1] = 0.0;
+#pragma unroll
+    for (int gp = 0; gp < 4; gp++) {
+        const double r = (gp & 2) ? -root : root;
+        const double s = (gp & 1) ? -root : root;
+        const double dr[4] = {-0.25 * (1 - s), 0.25 * (1 - s), 0.25 * (1 + s), -0.25 * (1 + s)};
+        const double ds[4] = {-0.25 * (1 - r), -0.25 * (1 + r), 0.25 * (1 + r), 0.25 * (1 - r)};
+        double j00 = 0, j01 = 0, j10 = 0, j11 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            j00 += dr[k] * g.lx[k];
+            j01 += dr[k] * g.ly[k];
+            j10 += ds[k] * g.lx[k];
+            j11 += ds[k] * g.ly[k];
+        }
+        Lu2State st = {false, false};
+        const double det = det2_quirk(j00, j01, j10, j11, st, quirk);
+        const double di = 1.0 / det;
+        const double b00 = j11 * di, b01 = -j01 * di, b12 = -j10 * di, b13 = j00 * di;
+        double px[4], py[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            px[k] = b00 * dr[k] + b01 * ds[k];
+            py[k] = b12 * dr[k] + b13 * ds[k];
+        }
+        const double f = det * c_el.thickness;
+        const double pxI = pick4(I, px), pyI = pick4(I, py);
+#pragma unroll
+        for (int j = 0; j < 4; j++) membrane_accum(f, pxI, pyI, px[j], py[j], Km[j]);
     }
 }
 
@@ -380,6 +435,73 @@ __device__ __forceinline__ void tri_plate_row(const TriGeom &g, double Kp[3][3][
             for (int c = 0; c < 3; c++) Kp[j][r][c] *= f;
 }
 
+__device__ __forceinline__ void tri_plate_row_rt(const TriGeom &g, int I, double Kp[4][3][3])
+{
+    const double C0 = g.x12 * g.x12 + g.y12 * g.y12;
+    const double C1 = g.x31 * g.x31 + g.y31 * g.y31;
+    const double C2 = g.x23 * g.x23 + g.y23 * g.y23;
+    const double mu1 = (C0 - C1) / C2, mu2 = (C2 - C0) / C1, mu3 = (C1 - C2) / C0;
+    const double sc = 1.0 / (4.0 * g.area * g.area);
+    double Y[3][3];
+    Y[0][0] = g.y23 * g.y23 * sc;
+    Y[0][1] = g.y31 * g.y31 * sc;
+    Y[0][2] = g.y23 * g.y31 * sc;
+    Y[1][0] = g.x23 * g.x23 * sc;
+    Y[1][1] = g.x31 * g.x31 * sc;
+    Y[1][2] = g.x31 * g.x23 * sc;
+    Y[2][0] = -2.0 * g.x23 * g.y23 * sc;
+    Y[2][1] = ((c_el.quirks & FS_Q_Y21) ? -2.0 * g.x31 * g.x31 : -2.0 * g.x31 * g.y31) * sc;
+    Y[2][2] = (-g.x23 * g.y31 - g.x31 * g.y23) * sc;
+    const double d11 = c_el.dp11, d12 = c_el.dp12, d33 = c_el.dp33;
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) Kp[j][r][0] = Kp[j][r][1] = Kp[j][r][2] = 0.0;
+#pragma unroll
+    for (int gp = 0; gp < 3; gp++) {
+        const double L1 = (gp == 1) ? 2.0 / 3.0 : 1.0 / 6.0;
+        const double L2 = (gp == 2) ? 2.0 / 3.0 : 1.0 / 6.0;
+        TriGp t;
+        tri_gp_terms(L1, L2, mu1, mu2, mu3, t);
+        double M[3][3][3];  // M[j] = Y * B_j
+#define FS_TRI_M(J)                                                                                \
+    {                                                                                              \
+        double Bc[3][3];                                                                           \
+        tri_bcols<J>(g, t, Bc);                                                                    \
+        _Pragma("unroll") for (int k = 0; k < 3; k++) _Pragma("unroll") for (int c = 0; c < 3; c++) \
+            M[J][k][c] = Y[k][0] * Bc[0][c] + Y[k][1] * Bc[1][c] + Y[k][2] * Bc[2][c];            \
+    }
+        FS_TRI_M(0)
+        FS_TRI_M(1)
+        FS_TRI_M(2)
+#undef FS_TRI_M
+        double E[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double m0 = I == 0 ? M[0][0][c] : (I == 1 ? M[1][0][c] : M[2][0][c]);
+            const double m1 = I == 0 ? M[0][1][c] : (I == 1 ? M[1][1][c] : M[2][1][c]);
+            const double m2 = I == 0 ? M[0][2][c] : (I == 1 ? M[1][2][c] : M[2][2][c]);
+            E[0][c] = d11 * m0 + d12 * m1;
+            E[1][c] = d12 * m0 + d11 * m1;
+            E[2][c] = d33 * m2;
+        }
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    Kp[j][r][c] += (E[0][r] * M[j][0][c] + E[1][r] * M[j][1][c] + E[2][r] * M[j][2][c]) * (1.0 / 6.0);
+    }
+    const double f = 2.0 * g.area;
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) Kp[j][r][c] *= f;
+}
+
 // ---------------------------------------------------------------------------------------------
 // DKQ, fs.cpp:604-687 + evalBQuad fs.cpp:901-990
 // ---------------------------------------------------------------------------------------------
@@ -476,6 +598,63 @@ __device__ __forceinline__ void quad_plate_row(const QuadGeom &g, double Kp[4][3
         FS_QUAD_ACC(2)
         FS_QUAD_ACC(3)
 #undef FS_QUAD_ACC
+    }
+}
+
+__device__ __forceinline__ void quad_plate_row_rt(const QuadGeom &g, int I, double Kp[4][3][3])
+{
+    QuadH h;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const double dx = g.dx[k], dy = g.dy[k];
+        const double sl = dx * dx + dy * dy;
+        h.a[k] = -dx / sl;
+        h.b[k] = 0.75 * dx * dy / sl;
+        h.c[k] = (0.25 * dx * dx - 0.5 * dy * dy) / sl;
+        h.d[k] = -dy / sl;
+        h.e[k] = (0.25 * dy * dy - 0.5 * dx * dx) / sl;
+    }
+    const double d11 = c_el.dp11, d12 = c_el.dp12, d33 = c_el.dp33;
+    const double root = 0.57735026918962584;
+    const bool quirk = (c_el.quirks & FS_Q_DETLU) != 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) Kp[j][r][0] = Kp[j][r][1] = Kp[j][r][2] = 0.0;
+    Lu2State st = {false, false};
+#pragma unroll
+    for (int gp = 0; gp < 4; gp++) {
+        const double r = (gp & 2) ? -root : root;
+        const double s = (gp & 1) ? -root : root;
+        double j00 = 0.25 * ((g.dx[0] + g.dx[2]) * s - g.dx[0] + g.dx[2]);
+        double j01 = 0.25 * ((g.dy[0] + g.dy[2]) * s - g.dy[0] + g.dy[2]);
+        double j10 = 0.25 * ((g.dx[0] + g.dx[2]) * r - g.dx[1] + g.dx[3]);
+        double j11 = 0.25 * ((g.dy[0] + g.dy[2]) * r - g.dy[1] + g.dy[3]);
+        const double det = det2_quirk(j00, j01, j10, j11, st, quirk);
+        const double di = 1.0 / det;
+        const double i00 = j11 * di, i01 = -j01 * di, i10 = -j10 * di, i11 = j00 * di;
+        double B[4][3][3];
+        quad_bcols<0>(h, r, s, i00, i01, i10, i11, B[0]);
+        quad_bcols<1>(h, r, s, i00, i01, i10, i11, B[1]);
+        quad_bcols<2>(h, r, s, i00, i01, i10, i11, B[2]);
+        quad_bcols<3>(h, r, s, i00, i01, i10, i11, B[3]);
+        double E[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double b0 = I == 0 ? B[0][0][c] : (I == 1 ? B[1][0][c] : (I == 2 ? B[2][0][c] : B[3][0][c]));
+            const double b1 = I == 0 ? B[0][1][c] : (I == 1 ? B[1][1][c] : (I == 2 ? B[2][1][c] : B[3][1][c]));
+            const double b2 = I == 0 ? B[0][2][c] : (I == 1 ? B[1][2][c] : (I == 2 ? B[2][2][c] : B[3][2][c]));
+            E[0][c] = (d11 * b0 + d12 * b1) * det;
+            E[1][c] = (d12 * b0 + d11 * b1) * det;
+            E[2][c] = d33 * b2 * det;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int rr = 0; rr < 3; rr++)
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    Kp[j][rr][c] += E[0][rr] * B[j][0][c] + E[1][rr] * B[j][1][c] + E[2][rr] * B[j][2][c];
     }
 }
 

@@ -22,8 +22,6 @@ def main():
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-    ids = [fsb.FemShell.unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(ids, src=0)
     cases = {
         "tri": (fsb.meshgen("t", 40, 33, 0, 0, 10, 10, (1, 1, 1, 1), 300.0, 2, 1), 0.3, 1e7, 0.5),
         "quad": (fsb.meshgen("q", 31, 47, 0, 0, 10, 10, (0, 1, 0, 1), 300.0, 2, 1), 0.3, 1e7, 0.5),
@@ -32,7 +30,10 @@ def main():
     for name, (m, nu, E, t) in cases.items():
         om = fso.Mesh(np.asarray(m["xyz"], float), m["etype"], m["eptr"], m["enodes"], m["bc"])
         ref = fso.assemble(om, m["forces"], nu, E, t)
+        ids = [fsb.FemShell.unique_id() if rank == 0 else None]   # an ncclUniqueId serves one communicator
+        dist.broadcast_object_list(ids, src=0)
         s = fsb.FemShell(device=lr, rank=rank, world=world, nccl_id=ids[0])
+        s.set_assembly_mode(fsb.ASM_GATHER if name != "quad" else fsb.ASM_COLORED)
         s.set_material(nu, E, t)
         s.set_mesh(m["xyz"], m["etype"], m["eptr"], m["enodes"], m["bc"])
         s.set_nodal_loads(m["forces"])
