@@ -22,7 +22,7 @@ DOF_FIRST_ENCOUNTER, DOF_NODE_ID = 0, 1
 PC_NONE, PC_JACOBI, PC_BJACOBI6 = 0, 1, 2
 NORM_UNPRECONDITIONED, NORM_PRECONDITIONED = 0, 1
 QUIRKS_REFERENCE = 3
-ASM_COLORED, ASM_GATHER = 0, 1
+ASM_COLORED, ASM_GATHER = 0, 1   # gather is the default; it falls back to coloured if a row is too dense
 FS_OK, FS_ERR_ARG, FS_ERR_CUDA, FS_ERR_STATE, FS_ERR_NOT_CONVERGED, FS_ERR_BREAKDOWN, FS_ERR_COMM, FS_ERR_IO = 0, -1, -2, -3, -4, -5, -6, -7
 
 # every symbol include/femshell_b200.h declares (checked by tests/test_abi.py)

@@ -465,58 +465,79 @@ k_assemble_colored(const int32_t *__restrict__ conn, const int32_t *__restrict__
 
 
 // ---------------------------------------------------------------------------------------------
-// values pass, row gather ("owner computes").  A thread block owns a run of block rows whose CSR
-// values fit in shared memory.  Thread = one (element, node row I) incidence of those rows; it
-// forms its row slice in registers, then the incidences of a row add their 6x6 blocks into shared
-// memory in a fixed order (round r = r-th incident element of the row, ordered by type and
-// element id; rows are disjoint, so a round needs no atomics).  Finally the block streams its rows
-// to HBM: every CSR value is written exactly once, fully coalesced, and never read.
-// Warps are uniform in (element type, I): the thread table is grouped and padded per group.
+// values pass, row gather ("owner computes").  A WARP owns a run of block rows whose CSR values fit
+// in its slice of shared memory.  Lane = one (element, node row I) incidence of those rows; it forms
+// its row slice in registers (run-time I, selects only, so lanes with different I do not diverge),
+// then the incidences of a row add their 6x6 blocks into shared memory in a fixed order (round r =
+// r-th incident element of the row, triangles first, then by element id; rows are disjoint, so a
+// round needs no atomics and only __syncwarp).  Finally the warp streams its rows to HBM: every CSR
+// value is written exactly once, coalesced, and never read.  Warps never wait for each other.
 // ---------------------------------------------------------------------------------------------
-constexpr int GATHER_THREADS = 128;
-constexpr int GATHER_MAX_VALS = 10240;  // doubles of shared memory per block (80 KB, two blocks per SM)
+constexpr int GATHER_WARPS = 4;                       // warps (= chunks) per thread block
+constexpr int GATHER_THREADS = 32 * GATHER_WARPS;
+constexpr int GATHER_WARP_VALS = 2816;                // doubles of shared memory per warp (22 KB)
 
+// rotate block j once (all lanes busy), then let the incidences of a row add it in their rounds;
+// a round is 18 128-bit shared-memory read-modify-writes per lane
 template <int NEN>
 __device__ __forceinline__ void gather_emit(const double T[3][3], double Km[4][2][2], double Kp[4][3][3], int I,
-                                            const int *slot, const unsigned *mcol, double *srow, int L)
+                                            const int *slot, const unsigned *mcol, double *srow, int L,
+                                            bool active, int round, int n_rounds)
 {
-    const unsigned mrow = mcol[I];
+    const unsigned mrow = I == 0 ? mcol[0] : (I == 1 ? mcol[1] : (I == 2 ? mcol[2] : mcol[3]));
 #pragma unroll
     for (int j = 0; j < NEN; j++) {
         double G[6][6];
         rotate_block(T, Km[j], Kp[j], G);
-        double *dst = srow + 6 * slot[j];
         const unsigned mc = mcol[j];
+        if (__any_sync(0xffffffffu, active && (mrow | mc))) {  // fs.cpp:1227, only where a Dirichlet node is involved
 #pragma unroll
-        for (int a = 0; a < 6; a++) {
-            const bool ra = (mrow >> a) & 1u;
+            for (int a = 0; a < 6; a++) {
+                const bool ra = (mrow >> a) & 1u;
 #pragma unroll
-            for (int b = 0; b < 6; b++) {
-                double v = G[a][b];
-                if (ra || ((mc >> b) & 1u)) v = (ra && j == I && a == b) ? 1.0 : 0.0;  // fs.cpp:1227
-                dst[a * L + b] += v;
+                for (int b = 0; b < 6; b++)
+                    if (ra || ((mc >> b) & 1u)) G[a][b] = (ra && j == I && a == b) ? 1.0 : 0.0;
             }
+        }
+        double2 *dst = reinterpret_cast<double2 *>(srow + 6 * slot[j]);
+        const int L2 = L >> 1;
+        for (int r = 0; r < n_rounds; r++) {
+            if (active && round == r) {
+#pragma unroll
+                for (int a = 0; a < 6; a++)
+#pragma unroll
+                    for (int h = 0; h < 3; h++) {
+                        double2 cur = dst[a * L2 + h];
+                        cur.x += G[a][2 * h];
+                        cur.y += G[a][2 * h + 1];
+                        dst[a * L2 + h] = cur;
+                    }
+            }
+            __syncwarp();
         }
     }
 }
 
 __global__ void __launch_bounds__(GATHER_THREADS, 2)
-k_assemble_gather(const GatherChunk *__restrict__ chunks, const int32_t *__restrict__ g_elem,
+k_assemble_gather(const GatherChunk *__restrict__ chunks, int n_chunks, const int32_t *__restrict__ g_elem,
                   const int32_t *__restrict__ g_meta, const int32_t *__restrict__ tri,
                   const int32_t *__restrict__ tri_pos, const int32_t *__restrict__ quad,
                   const int32_t *__restrict__ quad_pos, const double *__restrict__ xyz,
                   const uint8_t *__restrict__ mask, const int32_t *__restrict__ nptr, double *__restrict__ vals,
                   int own_lo)
 {
-    extern __shared__ double sv[];
-    const GatherChunk ch = chunks[blockIdx.x];
-    const int tid = threadIdx.x;
-    for (int i = tid; i < ch.val_count; i += GATHER_THREADS) sv[i] = 0.0;
+    extern __shared__ double sv_all[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ci = blockIdx.x * GATHER_WARPS + warp;
+    if (ci >= n_chunks) return;
+    double *sv = sv_all + (size_t)warp * GATHER_WARP_VALS;
+    const GatherChunk ch = chunks[ci];
+    for (int i = lane; i < ch.val_count; i += 32) sv[i] = 0.0;
 
     int e = -1, meta = 0;
-    if (tid < ch.n_threads) {
-        e = g_elem[ch.thread_off + tid];
-        meta = g_meta[ch.thread_off + tid];
+    if (lane < ch.n_threads) {
+        e = g_elem[ch.thread_off + lane];
+        meta = g_meta[ch.thread_off + lane];
     }
     const int I = meta & 3, is_quad = (meta >> 2) & 1, round = (meta >> 3) & 31;
     double Km[4][2][2], Kp[4][3][3], T[3][3];
@@ -572,18 +593,16 @@ k_assemble_gather(const GatherChunk *__restrict__ chunks, const int32_t *__restr
             tri_plate_row_rt(g, I, Kp);
         }
     }
-    __syncthreads();
-    for (int r = 0; r < ch.n_rounds; r++) {
-        if (e >= 0 && round == r) {
-            if (is_quad) gather_emit<4>(T, Km, Kp, I, slot, mcol, srow, L);
-            else gather_emit<3>(T, Km, Kp, I, slot, mcol, srow, L);
-        }
-        __syncthreads();
-    }
+    __syncwarp();
+    // a chunk holds quads in its leading lanes and triangles behind them (both only in mixed meshes)
+    const bool any_quad = __any_sync(0xffffffffu, e >= 0 && is_quad);
+    const bool any_tri = __any_sync(0xffffffffu, e >= 0 && !is_quad);
+    if (any_quad) gather_emit<4>(T, Km, Kp, I, slot, mcol, srow, L, e >= 0 && is_quad, round, ch.n_rounds);
+    if (any_tri) gather_emit<3>(T, Km, Kp, I, slot, mcol, srow, L, e >= 0 && !is_quad, round, ch.n_rounds);
     // stream the finished rows out (contiguous in the CSR value array)
     double2 *out = reinterpret_cast<double2 *>(vals + 36 * (size_t)nptr[ch.row0]);
     const double2 *s2 = reinterpret_cast<const double2 *>(sv);
-    for (int i = tid; i < ch.val_count / 2; i += GATHER_THREADS) __stcs(out + i, s2[i]);
+    for (int i = lane; i < ch.val_count / 2; i += 32) __stcs(out + i, s2[i]);
 }
 
 // host: build the thread table of the row-gather pass from the colour-sorted element arrays
@@ -623,44 +642,37 @@ int build_gather_schedule(fs_context *c)
 
     std::vector<GatherChunk> chunks;
     std::vector<int32_t> g_elem, g_meta;
-    auto padded = [](const int gc[7]) { int t = 0; for (int g = 0; g < 7; g++) t += (gc[g] + 31) / 32 * 32; return t; };
     int64_t row = 0;
     while (row < n_own) {
-        int gc[7] = {0, 0, 0, 0, 0, 0, 0};
         int64_t r1 = row, vals = 0;
-        int rounds = 0;
+        int threads = 0, rounds = 0;
         while (r1 < n_own) {
-            int g2[7];
-            memcpy(g2, gc, sizeof gc);
-            for (int k = cnt[r1]; k < cnt[r1 + 1]; k++) g2[inc[k].type * 3 + inc[k].I]++;
+            const int t2 = threads + (cnt[r1 + 1] - cnt[r1]);
             const int64_t v2 = vals + 36 * (int64_t)(nptr[r1 + 1] - nptr[r1]);
-            if (padded(g2) > GATHER_THREADS || v2 > GATHER_MAX_VALS || r1 - row >= 4095) break;
-            memcpy(gc, g2, sizeof gc);
+            if (t2 > 32 || v2 > GATHER_WARP_VALS) break;
+            threads = t2;
             vals = v2;
             rounds = std::max(rounds, cnt[r1 + 1] - cnt[r1]);
             r1++;
         }
-        if (r1 == row || rounds > 31) {  // a single row does not fit: leave this mesh to the coloured pass
+        if (r1 == row) {  // a single row does not fit a warp: leave this mesh to the coloured pass
             c->gather_unavailable = true;
             return FS_OK;
         }
         GatherChunk ch;
         ch.row0 = (int)row; ch.row1 = (int)r1;
         ch.thread_off = (int)g_elem.size();
+        ch.n_threads = threads;
         ch.n_rounds = rounds;
         ch.val_count = (int)vals;
-        for (int g = 0; g < 7; g++) {
-            int n = 0;
+        // quads first so that a mixed chunk splits into at most two divergent halves
+        for (int pass = 1; pass >= 0; pass--)
             for (int64_t p = row; p < r1; p++)
                 for (int k = cnt[p]; k < cnt[p + 1]; k++)
-                    if (inc[k].type * 3 + inc[k].I == g) {
+                    if (inc[k].type == pass) {
                         g_elem.push_back(inc[k].eidx);
                         g_meta.push_back(inc[k].I | (inc[k].type << 2) | ((k - cnt[p]) << 3));
-                        n++;
                     }
-            for (; n % 32; n++) { g_elem.push_back(-1); g_meta.push_back(0); }
-        }
-        ch.n_threads = (int)g_elem.size() - ch.thread_off;
         chunks.push_back(ch);
         row = r1;
     }
@@ -671,7 +683,7 @@ int build_gather_schedule(fs_context *c)
     FS_CUDA(c, cudaMemcpy(c->d_g_chunks.p, chunks.data(), sizeof(GatherChunk) * chunks.size(), cudaMemcpyHostToDevice));
     FS_CUDA(c, cudaMemcpy(c->d_g_elem.p, g_elem.data(), sizeof(int32_t) * g_elem.size(), cudaMemcpyHostToDevice));
     FS_CUDA(c, cudaMemcpy(c->d_g_meta.p, g_meta.data(), sizeof(int32_t) * g_meta.size(), cudaMemcpyHostToDevice));
-    FS_CUDA(c, cudaFuncSetAttribute(k_assemble_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, GATHER_MAX_VALS * (int)sizeof(double)));
+    FS_CUDA(c, cudaFuncSetAttribute(k_assemble_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, GATHER_WARPS * GATHER_WARP_VALS * (int)sizeof(double)));
     c->gather_ready = true;
     return FS_OK;
 }
@@ -687,8 +699,8 @@ int assemble_values(fs_context *c, float *ms)
     }
     FS_CUDA(c, cudaEventRecord(c->ev0, st));
     if (c->asm_mode == FS_ASM_GATHER && c->gather_ready) {
-        k_assemble_gather<<<(unsigned)c->n_g_chunks, GATHER_THREADS, GATHER_MAX_VALS * sizeof(double), st>>>(
-            c->d_g_chunks.p, c->d_g_elem.p, c->d_g_meta.p, c->d_tri.p, c->d_tri_pos.p, c->d_quad.p, c->d_quad_pos.p,
+        k_assemble_gather<<<nblk(c->n_g_chunks, GATHER_WARPS), GATHER_THREADS, GATHER_WARPS * GATHER_WARP_VALS * sizeof(double), st>>>(
+            c->d_g_chunks.p, (int)c->n_g_chunks, c->d_g_elem.p, c->d_g_meta.p, c->d_tri.p, c->d_tri_pos.p, c->d_quad.p, c->d_quad_pos.p,
             c->d_xyz.p, c->d_mask.p, c->d_nptr.p, c->d_vals.p, (int)c->own_lo);
         FS_CUDA(c, cudaEventRecord(c->ev1, st));
         FS_CUDA(c, cudaStreamSynchronize(st));

@@ -86,7 +86,7 @@ struct fs_context {
     bool material_set = false;
     int quirks = FS_QUIRKS_REFERENCE;
     int dof_mode = FS_DOF_FIRST_ENCOUNTER;
-    int asm_mode = FS_ASM_COLORED;
+    int asm_mode = FS_ASM_GATHER;
 
     // host copy of the (replicated) mesh description that later calls need
     int64_t n_nodes = 0, n_elem = 0;

@@ -601,18 +601,56 @@ __device__ __forceinline__ void quad_plate_row(const QuadGeom &g, double Kp[4][3
     }
 }
 
+// columns of node K chosen at run time (selects only, no branches): K picks the corner derivative and
+// the coefficients of the two adjacent sides; xi, eta are compile-time constants after unrolling
+__device__ __forceinline__ void quad_bcols_rt(const QuadH &h, int K, double xi, double eta, double i00, double i01,
+                                              double i10, double i11, double Bc[3][3])
+{
+    const double Nx_c[4] = {0.25 * (2.0 * xi + eta) * (1.0 - eta), 0.25 * (2.0 * xi - eta) * (1.0 - eta),
+                            0.25 * (2.0 * xi + eta) * (1.0 + eta), 0.25 * (2.0 * xi - eta) * (1.0 + eta)};
+    const double Ne_c[4] = {0.25 * (2.0 * eta + xi) * (1.0 - xi), 0.25 * (2.0 * eta - xi) * (1.0 + xi),
+                            0.25 * (2.0 * eta + xi) * (1.0 + xi), 0.25 * (2.0 * eta - xi) * (1.0 - xi)};
+    const double Nx_mid[4] = {-xi * (1.0 - eta), 0.5 * (1.0 - eta * eta), -xi * (1.0 + eta), -0.5 * (1.0 - eta * eta)};
+    const double Ne_mid[4] = {-0.5 * (1.0 - xi * xi), -eta * (1.0 + xi), 0.5 * (1.0 - xi * xi), -eta * (1.0 - xi)};
+    const int P = (K + 3) & 3;
+    const double Nxk = pick4(K, Nx_c), Nek = pick4(K, Ne_c);
+    const double nxs = pick4(K, Nx_mid), nxp = pick4(P, Nx_mid), nes = pick4(K, Ne_mid), nep = pick4(P, Ne_mid);
+    const double aS = pick4(K, h.a), aP = pick4(P, h.a), bS = pick4(K, h.b), bP = pick4(P, h.b);
+    const double cS = pick4(K, h.c), cP = pick4(P, h.c), dS = pick4(K, h.d), dP = pick4(P, h.d);
+    const double eS = pick4(K, h.e), eP = pick4(P, h.e);
+    double hxx[3], hxe[3], hyx[3], hye[3];
+    hxx[0] = 1.5 * (aS * nxs - aP * nxp);
+    hxx[1] = bS * nxs + bP * nxp;
+    hxx[2] = Nxk - cS * nxs - cP * nxp;
+    hyx[0] = 1.5 * (dS * nxs - dP * nxp);
+    hyx[1] = -Nxk + eS * nxs + eP * nxp;
+    hyx[2] = -hxx[1];
+    hxe[0] = 1.5 * (aS * nes - aP * nep);
+    hxe[1] = bS * nes + bP * nep;
+    hxe[2] = Nek - cS * nes - cP * nep;
+    hye[0] = 1.5 * (dS * nes - dP * nep);
+    hye[1] = -Nek + eS * nes + eP * nep;
+    hye[2] = -hxe[1];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        Bc[0][c] = i00 * hxx[c] + i01 * hxe[c];
+        Bc[1][c] = i10 * hyx[c] + i11 * hye[c];
+        Bc[2][c] = i00 * hyx[c] + i01 * hye[c] + i10 * hxx[c] + i11 * hxe[c];
+    }
+}
+
 __device__ __forceinline__ void quad_plate_row_rt(const QuadGeom &g, int I, double Kp[4][3][3])
 {
     QuadH h;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const double dx = g.dx[k], dy = g.dy[k];
-        const double sl = dx * dx + dy * dy;
-        h.a[k] = -dx / sl;
-        h.b[k] = 0.75 * dx * dy / sl;
-        h.c[k] = (0.25 * dx * dx - 0.5 * dy * dy) / sl;
-        h.d[k] = -dy / sl;
-        h.e[k] = (0.25 * dy * dy - 0.5 * dx * dx) / sl;
+        const double si = 1.0 / (dx * dx + dy * dy);  // one reciprocal per side instead of five divisions
+        h.a[k] = -dx * si;
+        h.b[k] = 0.75 * dx * dy * si;
+        h.c[k] = (0.25 * dx * dx - 0.5 * dy * dy) * si;
+        h.d[k] = -dy * si;
+        h.e[k] = (0.25 * dy * dy - 0.5 * dx * dx) * si;
     }
     const double d11 = c_el.dp11, d12 = c_el.dp12, d33 = c_el.dp33;
     const double root = 0.57735026918962584;
@@ -633,28 +671,25 @@ __device__ __forceinline__ void quad_plate_row_rt(const QuadGeom &g, int I, doub
         const double det = det2_quirk(j00, j01, j10, j11, st, quirk);
         const double di = 1.0 / det;
         const double i00 = j11 * di, i01 = -j01 * di, i10 = -j10 * di, i11 = j00 * di;
-        double B[4][3][3];
-        quad_bcols<0>(h, r, s, i00, i01, i10, i11, B[0]);
-        quad_bcols<1>(h, r, s, i00, i01, i10, i11, B[1]);
-        quad_bcols<2>(h, r, s, i00, i01, i10, i11, B[2]);
-        quad_bcols<3>(h, r, s, i00, i01, i10, i11, B[3]);
-        double E[3][3];
+        double Bc[3][3], E[3][3];
+        quad_bcols_rt(h, I, r, s, i00, i01, i10, i11, Bc);
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            const double b0 = I == 0 ? B[0][0][c] : (I == 1 ? B[1][0][c] : (I == 2 ? B[2][0][c] : B[3][0][c]));
-            const double b1 = I == 0 ? B[0][1][c] : (I == 1 ? B[1][1][c] : (I == 2 ? B[2][1][c] : B[3][1][c]));
-            const double b2 = I == 0 ? B[0][2][c] : (I == 1 ? B[1][2][c] : (I == 2 ? B[2][2][c] : B[3][2][c]));
-            E[0][c] = (d11 * b0 + d12 * b1) * det;
-            E[1][c] = (d12 * b0 + d11 * b1) * det;
-            E[2][c] = d33 * b2 * det;
+            E[0][c] = (d11 * Bc[0][c] + d12 * Bc[1][c]) * det;
+            E[1][c] = (d12 * Bc[0][c] + d11 * Bc[1][c]) * det;
+            E[2][c] = d33 * Bc[2][c] * det;
         }
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-#pragma unroll
-            for (int rr = 0; rr < 3; rr++)
-#pragma unroll
-                for (int c = 0; c < 3; c++)
-                    Kp[j][rr][c] += E[0][rr] * B[j][0][c] + E[1][rr] * B[j][1][c] + E[2][rr] * B[j][2][c];
+#define FS_QUAD_ACC_RT(J)                                                                          \
+    {                                                                                              \
+        quad_bcols<J>(h, r, s, i00, i01, i10, i11, Bc);                                            \
+        _Pragma("unroll") for (int rr = 0; rr < 3; rr++) _Pragma("unroll") for (int c = 0; c < 3; c++) \
+            Kp[J][rr][c] += E[0][rr] * Bc[0][c] + E[1][rr] * Bc[1][c] + E[2][rr] * Bc[2][c];       \
+    }
+        FS_QUAD_ACC_RT(0)
+        FS_QUAD_ACC_RT(1)
+        FS_QUAD_ACC_RT(2)
+        FS_QUAD_ACC_RT(3)
+#undef FS_QUAD_ACC_RT
     }
 }
 

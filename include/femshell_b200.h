@@ -58,7 +58,9 @@ enum { FS_NORM_UNPRECONDITIONED = 0, FS_NORM_PRECONDITIONED = 1 };
 /* arithmetic quirks of the reference, reproduced by default */
 enum { FS_QUIRK_Y21 = 1 /* fs.cpp:586 */, FS_QUIRK_DET_LU = 2 /* fs.cpp:512,652 */, FS_QUIRKS_REFERENCE = 3 };
 
-/* assembly strategy: graph-coloured scatter-add (default) or row-gather (owner computes) */
+/* assembly strategy: row-gather (default: every CSR value written once, deterministic, no atomics;
+ * falls back to the coloured pass if one block row exceeds a warp's shared-memory slice) or
+ * graph-coloured scatter-add (one launch per colour, atomics-free read-modify-write) */
 enum { FS_ASM_COLORED = 0, FS_ASM_GATHER = 1 };
 
 typedef struct fs_solve_opts {
