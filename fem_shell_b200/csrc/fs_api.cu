@@ -47,7 +47,7 @@ int fs_create(fs_context **out, int device)
     }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
-    if (c->d_state.alloc(1) != cudaSuccess || c->d_counter.alloc(1) != cudaSuccess) {
+    if (c->d_state.alloc(1) != cudaSuccess || c->d_counter.alloc(1) != cudaSuccess || c->d_flag.alloc(1) != cudaSuccess) {
         delete c;
         return FS_ERR_CUDA;
     }
@@ -61,6 +61,7 @@ int fs_destroy(fs_context *c)
     FS_CHECK_CTX(c);
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->cg_graph_exec) cudaGraphExecDestroy(c->cg_graph_exec);
     if (c->comm && nccl().ok) nccl().CommDestroy((ncclComm_t)c->comm);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -162,6 +163,7 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
     c->n_elem = n_elem;
     c->pattern_ready = c->assembled = c->loads_set = c->rhs_ready = c->have_solution = false;
     c->gather_ready = c->gather_unavailable = false;
+    if (c->cg_graph_exec) { cudaGraphExecDestroy(c->cg_graph_exec); c->cg_graph_exec = nullptr; }
 
     // ---- DOF order (a12) ----
     const int64_t n_g = compute_dof_order(c->dof_mode, n_nodes, n_elem, eptr, enodes, c->dofnode);

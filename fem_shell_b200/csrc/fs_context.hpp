@@ -138,9 +138,13 @@ struct fs_context {
     fs::DevBuf<double> d_partials;         // per-block partial sums
     fs::DevBuf<fs::CgState> d_state;
     fs::DevBuf<unsigned int> d_counter;
+    fs::DevBuf<int> d_flag;                // scratch error flag
     fs::DevBuf<double> d_sendbuf;          // 6*send_total
     fs::DevBuf<int32_t> d_send_idx;        // send_total local node ids
     fs::CgState *h_state = nullptr;        // pinned
+    cudaGraphExec_t cg_graph_exec = nullptr;  // captured CG iterations (invalidated with the mesh / preconditioner)
+    int cg_graph_key = -1;
+    double *cg_graph_red = nullptr;
     bool loads_set = false, rhs_ready = false, have_solution = false;
 
     // coupled step

@@ -142,8 +142,13 @@ __global__ void k_finalize(CgState *s, const double *red, int which)
 // of every one of the six rows (row length 6*deg doubles = 3*deg double2), so each row is one
 // fully coalesced 128-bit load per lane and the x pair is loaded once for all six rows.
 // ---------------------------------------------------------------------------------------------
+// Occupancy is what this kernel lives on (tools/spmv_lab.cu): capped at 64 registers so that 32 warps
+// are resident per SM, it streams at 6.25 TB/s on the 1000x1000-node Quad-4 matrix (0.62 of that at 16 warps).
+constexpr int SPMV_BLOCK = 128;
+constexpr int SPMV_MIN_BLOCKS = 8;
+
 template <bool WITH_DOT, int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, SPMV_MIN_BLOCKS)
 k_spmv(int n_own, const int32_t *__restrict__ nptr, const int32_t *__restrict__ nadj,
        const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y_own,
        const double *__restrict__ x_own, double *partials, unsigned int *counter, CgState *state,
@@ -410,7 +415,7 @@ __global__ void k_extract_minv(int n_own, int own_lo, const int32_t *__restrict_
 int solver_query_occupancy(fs_context *c)
 {
     int nb = 0;
-    FS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_spmv<true, 256>, 256, 0));
+    FS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_spmv<true, SPMV_BLOCK>, SPMV_BLOCK, 0));
     c->spmv_blocks_per_sm = std::max(1, nb);
     FS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_update<1, 0, 256>, 256, 0));
     c->vec_blocks_per_sm = std::max(1, nb);
@@ -423,9 +428,12 @@ int solver_prepare(fs_context *c, int pc)
     if (pc < 0 || pc > 2) return fail(c, FS_ERR_ARG, "unknown preconditioner");
     if (c->minv_kind == pc) return FS_OK;
     if (pc != FS_PC_NONE) {
-        FS_CUDA(c, c->d_minv.alloc((size_t)(pc == 1 ? 6 : 36) * c->n_own));
-        DevBuf<int> bad;
-        FS_CUDA(c, bad.alloc(1));
+        const size_t need = (size_t)(pc == 1 ? 6 : 36) * c->n_own;
+        if (c->d_minv.n < need) {  // the captured CG graph holds this pointer: only re-capture when it moves
+            if (c->cg_graph_exec) { cudaGraphExecDestroy(c->cg_graph_exec); c->cg_graph_exec = nullptr; }
+            FS_CUDA(c, c->d_minv.alloc(need));
+        }
+        DevBuf<int> &bad = c->d_flag;
         FS_CUDA(c, cudaMemsetAsync(bad.p, 0, sizeof(int), c->stream));
         k_extract_minv<<<nblk(c->n_own, 128), 128, 0, c->stream>>>((int)c->n_own, (int)c->own_lo, c->d_nptr.p,
                                                                     c->d_nadj.p, c->d_vals.p, pc, c->d_minv.p, bad.p);
@@ -470,7 +478,7 @@ int halo_exchange(fs_context *c, double *d_vec)
 static int spmv_grid(fs_context *c)
 {
     // persistent grid: a multiple of the SM count, one warp per block row, grid-stride
-    int64_t want = ((int64_t)c->n_own + 7) / 8;
+    int64_t want = ((int64_t)c->n_own + SPMV_BLOCK / 32 - 1) / (SPMV_BLOCK / 32);
     int64_t cap = (int64_t)c->sm_count * c->spmv_blocks_per_sm;
     return (int)std::max<int64_t>(1, std::min(want, cap));
 }
@@ -486,7 +494,7 @@ int spmv_once(fs_context *c, const double *d_in, double *d_out)
 {
     int rc = halo_exchange(c, const_cast<double *>(d_in));
     if (rc) return rc;
-    k_spmv<false, 256><<<spmv_grid(c), 256, 0, c->stream>>>((int)c->n_own, c->d_nptr.p, c->d_nadj.p, c->d_vals.p, d_in,
+    k_spmv<false, SPMV_BLOCK><<<spmv_grid(c), SPMV_BLOCK, 0, c->stream>>>((int)c->n_own, c->d_nptr.p, c->d_nadj.p, c->d_vals.p, d_in,
                                                            d_out + 6 * c->own_lo, nullptr, nullptr, nullptr, nullptr,
                                                            nullptr, 0);
     FS_CUDA(c, cudaGetLastError());
@@ -500,7 +508,7 @@ static int enqueue_iteration(fs_context *c, double *red, int sg, int vg)
     const int64_t o6 = 6 * c->own_lo;
     int rc = halo_exchange(c, c->d_p.p);
     if (rc) return rc;
-    k_spmv<true, 256><<<sg, 256, 0, c->stream>>>((int)c->n_own, c->d_nptr.p, c->d_nadj.p, c->d_vals.p, c->d_p.p,
+    k_spmv<true, SPMV_BLOCK><<<sg, SPMV_BLOCK, 0, c->stream>>>((int)c->n_own, c->d_nptr.p, c->d_nadj.p, c->d_vals.p, c->d_p.p,
                                                  c->d_q.p + o6, c->d_p.p + o6, c->d_partials.p, c->d_counter.p,
                                                  c->d_state.p, red, single);
     if (!single) {
@@ -549,17 +557,36 @@ static int run_pcg(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
         FS_NCCL(c, nccl().AllReduce(red + 8, red + 8, 3, ncclDouble, ncclSum, (ncclComm_t)c->comm, st));
         k_finalize<<<1, 1, 0, st>>>(c->d_state.p, red + 8, 0);
     }
+    // The iteration is captured once into a CUDA graph of GRAPH_ITERS iterations and replayed; kernels
+    // past convergence (or past max_its) see done != 0 and return, so replaying whole graphs is exact.
+    constexpr int GRAPH_ITERS = 8;
+    const int key = PC * 2 + NORM;
+    if (!c->cg_graph_exec || c->cg_graph_key != key || c->cg_graph_red != red) {
+        if (c->cg_graph_exec) cudaGraphExecDestroy(c->cg_graph_exec);
+        c->cg_graph_exec = nullptr;
+        cudaGraph_t graph = nullptr;
+        FS_CUDA(c, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        rc = FS_OK;
+        for (int k = 0; k < GRAPH_ITERS && rc == FS_OK; k++) rc = enqueue_iteration<PC, NORM>(c, red, sg, vg);
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        FS_CUDA(c, ce);
+        FS_CUDA(c, cudaGraphInstantiate(&c->cg_graph_exec, graph, 0));
+        FS_CUDA(c, cudaGraphDestroy(graph));
+        c->cg_graph_key = key;
+        c->cg_graph_red = red;
+    }
     const int batch = o->check_every > 0 ? o->check_every : 64;
     for (;;) {
         FS_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state.p, sizeof(CgState), cudaMemcpyDeviceToHost, st));
         FS_CUDA(c, cudaStreamSynchronize(st));
         if (c->h_state->done) break;
         int64_t left = c->h_state->max_its - c->h_state->iter;
-        int n = (int)std::min<int64_t>(batch, std::max<int64_t>(left, 1));
-        for (int k = 0; k < n; k++) {
-            rc = enqueue_iteration<PC, NORM>(c, red, sg, vg);
-            if (rc) return rc;
-        }
+        int64_t n = std::min<int64_t>(batch, std::max<int64_t>(left, 1));
+        for (int64_t k = 0; k < n; k += GRAPH_ITERS) FS_CUDA(c, cudaGraphLaunch(c->cg_graph_exec, st));
         FS_CUDA(c, cudaGetLastError());
     }
     FS_CUDA(c, cudaEventRecord(c->ev1, st));
