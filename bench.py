@@ -222,6 +222,18 @@ def run_ours(args):
     peak, peak_src = peaks()
     achieved = actual_b / (spmv_ms * 1e-3) / 1e9
 
+    # ---- element kernel rooflines: algorithmic work per element from SURVEY.md section 8d ----
+    fp64_peak = s.bench_fp64_peak()
+    kflop_el, bytes_el = 15.7e3, 2630.0          # Quad-4: flops and minimum HBM bytes per element
+    asm_rate = n_elem / world / (asm_ms * 1e-3)  # per GPU
+    assembly_roofline = {
+        "kernel": "k_assemble_gather" if args.asm == "gather" else "k_assemble_colored",
+        "fp64": {"achieved": asm_rate * kflop_el / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": asm_rate * kflop_el / 1e12 / fp64_peak,
+                 "peak_source": "measured here (fs_bench_fp64_peak, dependent-FMA chains)"},
+        "hbm": {"achieved": asm_rate * bytes_el / 1e9, "peak": peak, "unit": "GB/s", "frac": asm_rate * bytes_el / 1e9 / peak},
+        "per_element": {"flop": kflop_el, "bytes": bytes_el},
+    }
+
     # ---- end to end through the host-buffer plugin call (loads in, displacements out) ----
     F_host = torch.empty((n_nodes, 6), dtype=torch.float64).pin_memory()
     F_host.copy_(torch.from_numpy(m["forces"]))
@@ -302,6 +314,7 @@ def run_ours(args):
                      "peak_source": peak_src, "bytes_per_launch": actual_b, "csr_equiv_bytes_per_launch": csr_b,
                      "csr_equiv_gbs": csr_b / (spmv_ms * 1e-3) / 1e9, "ms_per_launch": spmv_ms,
                      "share_of_step": spmv_ms * (iters + 1) / ms_per_step, "traffic": args.traffic},
+        "assembly_roofline": assembly_roofline,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(Fh.nbytes if world == 1 else 48 * n_own),
                 "d2h_bytes_per_step": int(Sh.nbytes), "includes": "loads H2D, values re-assembly, %d PCG iterations, displacements D2H" % iters},

@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "fs_set_nodal_loads", "fs_set_interface_loads", "fs_build_rhs", "fs_assemble", "fs_solve",
     "fs_get_solution", "fs_solve_host", "fs_interface_nodes", "fs_step", "fs_commit_step", "fs_get_sizes",
     "fs_export_dof_order", "fs_export_csr", "fs_export_rhs", "fs_debug_element_matrices", "fs_spmv_host",
-    "fs_bench_spmv", "fs_partition_plan", "fs_meshgen", "fs_read_xda", "fs_read_forces", "fs_write_xda",
+    "fs_bench_spmv", "fs_bench_fp64_peak", "fs_partition_plan", "fs_meshgen", "fs_read_xda", "fs_read_forces", "fs_write_xda",
 ]
 
 
@@ -327,6 +327,11 @@ class FemShell:
         y = np.empty_like(x)
         self._ck(self.lib.fs_spmv_host(self.ctx, _p(x), _p(y)))
         return y
+
+    def bench_fp64_peak(self) -> float:
+        t = C.c_double()
+        self._ck(self.lib.fs_bench_fp64_peak(self.ctx, C.byref(t)))
+        return t.value
 
     def bench_spmv(self, reps=20) -> float:
         i = _Info()

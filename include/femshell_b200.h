@@ -167,6 +167,10 @@ int fs_spmv_host(fs_context *ctx, const double *x, double *y);
 /* times `reps` SpMV launches with CUDA events on the context stream (info->spmv_ms = mean) */
 int fs_bench_spmv(fs_context *ctx, int reps, fs_solve_info *info);
 
+/* measured FP64 FMA peak of the device in TFLOP/s (dependent-FMA micro-benchmark): the roofline of the
+ * element kernels, which MEASURED_PEAKS.json does not carry */
+int fs_bench_fp64_peak(fs_context *ctx, double *tflops);
+
 /* host-only (no GPU): the node-block partition plan rank `rank` of `world` derives from the replicated
  * mesh -- owned range, local nodes, local elements, halo send lists and recv segments.  Two-call
  * protocol (NULL arrays -> sizes only).  sizes = {n_dofnodes, own_begin, own_end, own_lo, n_local,
