@@ -89,10 +89,12 @@ def make_workload(fsb, nodes_x, nodes_y):
                        (1, 1, 1, 1), QLOAD, 2, 1)
 
 
-def spmv_bytes(n_dof, n_blocks):
-    nnz = 36 * n_blocks
-    actual = 8 * nnz + 4 * n_blocks + 4 * (n_dof // 6 + 1) + 8 * n_dof + 8 * n_dof   # vals + block cols + row ptr + x + y
-    csr_equiv = 12 * nnz + 20 * n_dof                                                 # SURVEY.md section 8d figure
+def spmv_bytes(n_dof, n_blocks, matrix_bytes):
+    """bytes one SpMV launch must move: the matrix in the format actually streamed (fs_get_spmv_format:
+    values + column ids + row/slice pointers) + x read once + y written once; and the SURVEY.md section 8d
+    figure for the same matrix as a scalar CSR with 32-bit column ids (explicit zeros of the 6x6 blocks included)"""
+    actual = matrix_bytes + 8 * n_dof + 8 * n_dof
+    csr_equiv = 12 * 36 * n_blocks + 20 * n_dof
     return actual, csr_equiv
 
 
@@ -163,6 +165,7 @@ def run_ours(args):
     s = fsb.FemShell(device=local_rank, rank=rank, world=world, nccl_id=nccl_id)
     s.set_material(NU, EM, THICK)
     s.set_assembly_mode(fsb.ASM_GATHER if args.asm == "gather" else fsb.ASM_COLORED)
+    s.set_spmv_format(fsb.SPMV_FULL if args.spmv == "full" else fsb.SPMV_AUTO)
     t0 = time.perf_counter()
     s.set_mesh(m["xyz"], m["etype"], m["eptr"], m["enodes"], m["bc"])
     t_setup = time.perf_counter() - t0
@@ -218,7 +221,9 @@ def run_ours(args):
 
     # ---- dominant kernel: SpMV, timed alone on the same stream right after the timed region ----
     spmv_ms = max_over_ranks(s.bench_spmv(50))
-    actual_b, csr_b = spmv_bytes(6 * n_own, sz["n_blocks"])
+    fmt = s.spmv_format()
+    actual_b, csr_b = spmv_bytes(6 * n_own, sz["n_blocks"], fmt["matrix_bytes"])
+    spmv_kernel = "k_spmv_sell" if fmt["nz_per_block"] < 36 else "k_spmv"
     peak, peak_src = peaks()
     achieved = actual_b / (spmv_ms * 1e-3) / 1e9
 
@@ -305,12 +310,13 @@ def run_ours(args):
         "config": {"workload": "BASELINE configs[1]: meshGen %dx%d nodes DKQ+PLANE Quad-4 (%d elements, %d DOF), clamped, uniform pressure%s"
                    % (nx, ny, n_elem, n_dof, "" if world == 1 else " = one 1000x1000-node strip per GPU"),
                    "iters_per_step": iters, "pc": "jacobi", "dof_order": "first_encounter",
-                   "l2_policy": "inputs larger than L2 (matrix %.2f GB per GPU streamed every iteration)" % (8e-9 * 36 * sz["n_blocks"]),
+                   "spmv_format": "%d of 36 entries per 6x6 block streamed (%s)" % (fmt["nz_per_block"], "zero-compacted sliced ELL" if fmt["nz_per_block"] < 36 else "parity block-CSR"),
+                   "l2_policy": "inputs larger than L2 (matrix %.2f GB per GPU streamed every iteration)" % (1e-9 * fmt["matrix_bytes"]),
                    "parallelism": "node-block strips x%d" % world},
         "metrics": {"cg_dof_iterations_per_s": value, "elements_assembled_per_s": n_elem / (asm_ms * 1e-3),
                     "assemble_ms": asm_ms, "time_to_solution": tts, "setup_s_pattern_colouring_upload": t_setup,
                     "colors": sz["n_colors"], "assembly_mode": args.asm},
-        "roofline": {"bound": "hbm", "kernel": "k_spmv", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "roofline": {"bound": "hbm", "kernel": spmv_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "bytes_per_launch": actual_b, "csr_equiv_bytes_per_launch": csr_b,
                      "csr_equiv_gbs": csr_b / (spmv_ms * 1e-3) / 1e9, "ms_per_launch": spmv_ms,
                      "share_of_step": spmv_ms * (iters + 1) / ms_per_step, "traffic": args.traffic},
@@ -341,6 +347,7 @@ def main():
     ap.add_argument("--ref-nodes", type=int, default=1000)
     ap.add_argument("--ref-iters", type=int, default=10)
     ap.add_argument("--asm", default="gather", choices=["colored", "gather"])
+    ap.add_argument("--spmv", default="auto", choices=["auto", "full"], help="full = always stream the parity block-CSR (explicit zeros included)")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes/launch of k_spmv from an ncu --set full capture")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

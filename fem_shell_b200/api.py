@@ -22,13 +22,14 @@ DOF_FIRST_ENCOUNTER, DOF_NODE_ID = 0, 1
 PC_NONE, PC_JACOBI, PC_BJACOBI6 = 0, 1, 2
 NORM_UNPRECONDITIONED, NORM_PRECONDITIONED = 0, 1
 QUIRKS_REFERENCE = 3
+SPMV_AUTO, SPMV_FULL = 0, 1       # AUTO: iterate on the zero-compacted copy when the blocks share a planar pattern
 ASM_COLORED, ASM_GATHER = 0, 1   # gather is the default; it falls back to coloured if a row is too dense
 FS_OK, FS_ERR_ARG, FS_ERR_CUDA, FS_ERR_STATE, FS_ERR_NOT_CONVERGED, FS_ERR_BREAKDOWN, FS_ERR_COMM, FS_ERR_IO = 0, -1, -2, -3, -4, -5, -6, -7
 
 # every symbol include/femshell_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
     "fs_create", "fs_destroy", "fs_last_error", "fs_get_stream", "fs_dist_unique_id", "fs_dist_init",
-    "fs_set_material", "fs_set_quirks", "fs_set_dof_order", "fs_set_assembly_mode", "fs_set_mesh",
+    "fs_set_material", "fs_set_quirks", "fs_set_dof_order", "fs_set_assembly_mode", "fs_set_spmv_format", "fs_get_spmv_format", "fs_set_mesh",
     "fs_set_nodal_loads", "fs_set_interface_loads", "fs_build_rhs", "fs_assemble", "fs_solve",
     "fs_get_solution", "fs_solve_host", "fs_interface_nodes", "fs_step", "fs_commit_step", "fs_get_sizes",
     "fs_export_dof_order", "fs_export_csr", "fs_export_rhs", "fs_debug_element_matrices", "fs_spmv_host",
@@ -221,6 +222,16 @@ class FemShell:
 
     def set_assembly_mode(self, mode):
         self._ck(self.lib.fs_set_assembly_mode(self.ctx, C.c_int(mode)))
+
+    def set_spmv_format(self, mode):
+        self._ck(self.lib.fs_set_spmv_format(self.ctx, C.c_int(mode)))
+
+    def spmv_format(self):
+        """{'nz_per_block': 36 | 14, 'matrix_bytes': streamed per SpMV, 'block_slots': .., 'pattern': 6x6 0/1 array}"""
+        v = (C.c_int64 * 4)()
+        self._ck(self.lib.fs_get_spmv_format(self.ctx, v))
+        pat = np.array([[(v[3] >> (6 * a + b)) & 1 for b in range(6)] for a in range(6)], dtype=np.int32)
+        return {"nz_per_block": int(v[0]), "matrix_bytes": int(v[1]), "block_slots": int(v[2]), "pattern": pat}
 
     def set_mesh(self, xyz, etype, eptr, enodes, bc):
         xyz, etype, eptr, enodes = _f64(xyz), _i32(etype), _i64(eptr), _i32(enodes)

@@ -132,6 +132,34 @@ int fs_set_dof_order(fs_context *c, int mode)
     return FS_OK;
 }
 
+int fs_set_spmv_format(fs_context *c, int mode)
+{
+    FS_CHECK_CTX(c);
+    if (mode != FS_SPMV_AUTO && mode != FS_SPMV_FULL) return fail(c, FS_ERR_ARG, "unknown SpMV format");
+    if (mode != c->spmv_format_pref) c->sell_checked = c->sell_active = false;
+    c->spmv_format_pref = mode;
+    return FS_OK;
+}
+
+int fs_get_spmv_format(fs_context *c, int64_t info[4])
+{
+    FS_CHECK_CTX(c);
+    if (!c->assembled || !info) return fail(c, FS_ERR_STATE, "not assembled / null output");
+    FS_CUDA(c, cudaSetDevice(c->device));
+    FS_TRY(spmv_format_prepare(c));
+    if (c->sell_active) {
+        info[0] = c->sell_nz;
+        info[1] = 8 * (int64_t)c->sell_nz * 32 * c->sell_slots + 4 * 32 * c->sell_slots + 4 * (c->sell_slices + 1);
+        info[2] = 32 * c->sell_slots;
+    } else {
+        info[0] = 36;
+        info[1] = 8 * 36 * c->n_blocks + 4 * c->n_blocks + 4 * (c->n_own + 1);
+        info[2] = c->n_blocks;
+    }
+    info[3] = (int64_t)c->sell_detected;
+    return FS_OK;
+}
+
 int fs_set_assembly_mode(fs_context *c, int mode)
 {
     FS_CHECK_CTX(c);
@@ -163,6 +191,7 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
     c->n_elem = n_elem;
     c->pattern_ready = c->assembled = c->loads_set = c->rhs_ready = c->have_solution = false;
     c->gather_ready = c->gather_unavailable = false;
+    c->sell_checked = c->sell_active = c->sell_layout_ready = false;
     if (c->cg_graph_exec) { cudaGraphExecDestroy(c->cg_graph_exec); c->cg_graph_exec = nullptr; }
 
     // ---- DOF order (a12) ----

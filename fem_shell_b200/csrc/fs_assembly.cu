@@ -708,6 +708,7 @@ int assemble_values(fs_context *c, float *ms)
         if (ms) FS_CUDA(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
         c->assembled = true;
         c->minv_kind = -1;
+        c->sell_checked = false;
         return FS_OK;
     }
     FS_CUDA(c, cudaMemsetAsync(c->d_vals.p, 0, sizeof(double) * 36 * (size_t)c->n_blocks, st));
@@ -728,6 +729,7 @@ int assemble_values(fs_context *c, float *ms)
     if (ms) FS_CUDA(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
     c->assembled = true;
     c->minv_kind = -1;
+    c->sell_checked = false;
     return FS_OK;
 }
 

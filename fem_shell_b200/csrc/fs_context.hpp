@@ -127,6 +127,20 @@ struct fs_context {
     int64_t n_blocks = 0;
     bool pattern_ready = false, assembled = false;
 
+    // zero-compacted SpMV copy of the matrix (fs_sell.cuh); rebuilt lazily after every values pass
+    int spmv_format_pref = FS_SPMV_AUTO;
+    bool sell_checked = false;             // the current d_vals have been inspected
+    bool sell_active = false;              // the SpMV runs on the compacted copy
+    bool sell_layout_ready = false;        // slice pointers / columns built for this mesh
+    unsigned long long sell_detected = 0;  // union pattern of all 6x6 blocks (bit 6a+b)
+    unsigned long long sell_mask = 0;      // the kernel mask in use (superset of sell_detected)
+    int sell_nz = 36, sell_kind = -1;
+    int64_t sell_slices = 0, sell_slots = 0;
+    fs::DevBuf<int32_t> d_sell_sptr, d_sell_adj;
+    fs::DevBuf<double> d_sell_vals;
+    fs::DevBuf<unsigned long long> d_sell_mask;
+    int sell_blocks_per_sm = 2;
+
     // loads / vectors (length 6*n_local unless noted)
     fs::DevBuf<double> d_F;                // 6*n_own loads in dof order (unconstrained values)
     fs::DevBuf<double> d_stage;            // 6*span_n node-ordered staging for loads / solution
@@ -186,5 +200,6 @@ int solver_prepare(fs_context *c, int pc);
 int solver_run(fs_context *c, const fs_solve_opts *o, fs_solve_info *info);
 int spmv_once(fs_context *c, const double *d_in, double *d_out);
 int halo_exchange(fs_context *c, double *d_vec);
+int spmv_format_prepare(fs_context *c);
 
 }  // namespace fs

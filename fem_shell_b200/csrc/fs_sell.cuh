@@ -1,0 +1,189 @@
+// fs_sell.cuh -- zero-compacted SpMV format for matrices whose 6x6 node blocks share a sparse pattern.
+//
+// libMesh pre-allocates (and the reference's add_matrix fills, fs.cpp:1230) a dense 6x6 block for every
+// node pair sharing an element, explicit zeros included.  For a flat shell lying in a coordinate plane
+// (every meshGen plate, src/meshgen/main_all.cpp:141-160) the local->global rotation (fs.cpp:1061-1110)
+// is a signed permutation, so membrane, bending and drilling DOFs never couple and 22 of the 36 entries
+// of EVERY block are exact zeros.  The parity format (d_vals, what fs_export_csr returns) keeps them; the
+// SpMV does not have to stream them.  After each values pass the 36-bit union pattern of all blocks is
+// measured on the device; when it fits one of the masks below, the non-zero positions are copied into a
+// sliced-ELL layout and the CG iteration runs on that (same products, same column order, exact zeros
+// skipped: results are those of a sequential CSR row sum).
+//
+// Layout ("SELL-32 by node"): a slice = 32 consecutive owned block rows, one per lane; dmax = largest
+// number of blocks of any row in the slice; sptr[s] = sum of dmax over earlier slices.
+//   adj [32*(sptr[s]+slot) + lane]                  local column node of the lane's slot-th block (padding: own node)
+//   vals[32*(NZ*(sptr[s]+slot) + item) + lane]      item = rank of (a,b) among the set bits of the mask (row-major)
+// so every load of a warp is one contiguous 256-byte (values) or 128-byte (columns) line, a lane owns a
+// whole block row, and no cross-lane reduction is needed.
+#pragma once
+#include "fs_cg_device.cuh"
+
+namespace fs {
+
+// launch shape of k_spmv_sell (tools/sell_lab.cu)
+constexpr int SELL_BLOCK = 128;
+constexpr int SELL_MINB = 4;
+
+__host__ __device__ constexpr unsigned long long sell_bit(int a, int b) { return 1ull << (6 * a + b); }
+__host__ __device__ constexpr unsigned long long sell_group(int i, int j, int k)  // rows/cols {i,j,k} fully coupled (k < 0: pair, j < 0: single)
+{
+    unsigned long long m = 0;
+    const int g[3] = {i, j, k};
+    for (int p = 0; p < 3; p++)
+        for (int q = 0; q < 3; q++)
+            if (g[p] >= 0 && g[q] >= 0) m |= sell_bit(g[p], g[q]);
+    return m;
+}
+// shell in the xy plane: membrane (u,v), bending (w,tx,ty), drilling tz -- and the two other coordinate planes
+constexpr unsigned long long SELL_MASK_XY = sell_group(0, 1, -1) | sell_group(2, 3, 4) | sell_group(5, -1, -1);
+constexpr unsigned long long SELL_MASK_XZ = sell_group(0, 2, -1) | sell_group(1, 3, 5) | sell_group(4, -1, -1);
+constexpr unsigned long long SELL_MASK_YZ = sell_group(1, 2, -1) | sell_group(0, 4, 5) | sell_group(3, -1, -1);
+constexpr unsigned long long SELL_MASK_FULL = (1ull << 36) - 1;
+
+__host__ __device__ constexpr int sell_popcount(unsigned long long m)
+{
+    int n = 0;
+    for (; m; m &= m - 1) n++;
+    return n;
+}
+__host__ __device__ constexpr int sell_item(unsigned long long mask, int a, int b) { return sell_popcount(mask & (sell_bit(a, b) - 1)); }
+__host__ __device__ constexpr bool sell_uses_col(unsigned long long mask, int b)
+{
+    for (int a = 0; a < 6; a++)
+        if (mask & sell_bit(a, b)) return true;
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// q = A p on the compacted matrix (+ partial p.q).  Lane = block row; slots of a slice are walked in
+// column order, two at a time so that 2*NZ value loads are in flight per lane.
+// ---------------------------------------------------------------------------------------------
+template <unsigned long long MASK, bool WITH_DOT, int BLOCK, int MINB, int UNROLL = 2>
+__global__ void __launch_bounds__(BLOCK, MINB)
+k_spmv_sell(int n_own, int n_slices, const int32_t *__restrict__ sptr, const int32_t *__restrict__ adj,
+            const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y_own,
+            const double *__restrict__ x_own, double *partials, unsigned int *counter, CgState *state,
+            double *red, int inline_finalize)
+{
+    constexpr int NZ = sell_popcount(MASK);
+    if (WITH_DOT && state->done) return;
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
+    const int nw = gridDim.x * (BLOCK / 32);
+    double dot = 0.0;
+    for (int s = gw; s < n_slices; s += nw) {
+        const int s0 = sptr[s], dmax = sptr[s + 1] - s0;
+        const int32_t *aj = adj + 32 * (size_t)s0 + lane;
+        const double *v = vals + 32 * (size_t)NZ * s0 + lane;
+        double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll UNROLL
+        for (int slot = 0; slot < dmax; slot++) {
+            const double2 *xp = reinterpret_cast<const double2 *>(x + 6 * (size_t)aj[32 * slot]);
+            double xv[6];
+#pragma unroll
+            for (int h = 0; h < 3; h++)
+                if (sell_uses_col(MASK, 2 * h) || sell_uses_col(MASK, 2 * h + 1)) {
+                    const double2 t = xp[h];
+                    xv[2 * h] = t.x;
+                    xv[2 * h + 1] = t.y;
+                }
+            const double *vs = v + 32 * (size_t)NZ * slot;
+#pragma unroll
+            for (int a = 0; a < 6; a++)
+#pragma unroll
+                for (int b = 0; b < 6; b++)
+                    if (MASK & sell_bit(a, b)) acc[a] += __ldcs(vs + 32 * sell_item(MASK, a, b)) * xv[b];
+        }
+        const int p = 32 * s + lane;
+        if (p < n_own) {
+            store6(y_own + 6 * (size_t)p, acc);
+            if (WITH_DOT) {
+                double pv[6];
+                load6(x_own + 6 * (size_t)p, pv);
+#pragma unroll
+                for (int a = 0; a < 6; a++) dot += acc[a] * pv[a];
+            }
+        }
+    }
+    if (WITH_DOT) {
+        double vv[1] = {dot}, out[1];
+        if (grid_reduce<1, BLOCK>(vv, partials, counter, out) && threadIdx.x == 0) {
+            red[0] = out[0];
+            if (inline_finalize) finalize_pq(state, out[0]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// format build
+// ---------------------------------------------------------------------------------------------
+// union pattern of all 6x6 blocks: bit 6a+b set when any block has a non-zero (a,b).  Same access
+// pattern as the full SpMV (warp = block row, lane = one double2 of each scalar row).
+__global__ void __launch_bounds__(256) k_sell_detect(int n_own, const int32_t *__restrict__ nptr,
+                                                     const double *__restrict__ vals, unsigned long long *mask_out)
+{
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nw = gridDim.x * (blockDim.x >> 5);
+    unsigned long long m = 0;
+    for (int p = gw; p < n_own; p += nw) {
+        const int b0 = nptr[p], L2 = 3 * (nptr[p + 1] - b0);
+        const double2 *base = reinterpret_cast<const double2 *>(vals + (size_t)36 * b0);
+        for (int l = lane; l < L2; l += 32) {
+            const int h = l % 3;
+#pragma unroll
+            for (int a = 0; a < 6; a++) {
+                const double2 t = __ldcs(base + (size_t)a * L2 + l);
+                if (t.x != 0.0) m |= sell_bit(a, 2 * h);
+                if (t.y != 0.0) m |= sell_bit(a, 2 * h + 1);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+    if (lane == 0 && m) atomicOr(mask_out, m);
+}
+
+__global__ void k_sell_dmax(int n_own, int n_slices, const int32_t *__restrict__ nptr, int32_t *dmax)
+{
+    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (s >= n_slices) return;
+    const int p = 32 * s + lane;
+    int d = p < n_own ? nptr[p + 1] - nptr[p] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, o));
+    if (lane == 0) dmax[s] = d;
+    if (s == 0 && lane == 0) dmax[n_slices] = 0;
+}
+
+// warp = slice, lane = block row: copies the masked entries of the parity format into the sliced layout
+__global__ void __launch_bounds__(256) k_sell_fill(int n_own, int n_slices, int own_lo, unsigned long long mask,
+                                                   const int32_t *__restrict__ nptr, const int32_t *__restrict__ nadj,
+                                                   const double *__restrict__ full, const int32_t *__restrict__ sptr,
+                                                   int32_t *__restrict__ adj, double *__restrict__ vals, int nz,
+                                                   int write_adj)
+{
+    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (s >= n_slices) return;
+    const int p = 32 * s + lane;
+    const bool live = p < n_own;
+    const int b0 = live ? nptr[p] : 0, deg = live ? nptr[p + 1] - b0 : 0;
+    const int s0 = sptr[s], dmax = sptr[s + 1] - s0;
+    const int self = own_lo + (live ? p : 0);
+    const double *row = full + (size_t)36 * b0;
+    for (int slot = 0; slot < dmax; slot++) {
+        const bool have = slot < deg;
+        if (write_adj) adj[32 * (size_t)(s0 + slot) + lane] = have ? nadj[b0 + slot] : self;
+        double *dst = vals + 32 * ((size_t)nz * (s0 + slot)) + lane;
+        int item = 0;
+        for (int a = 0; a < 6; a++)
+            for (int b = 0; b < 6; b++)
+                if (mask & sell_bit(a, b)) {
+                    dst[32 * (size_t)item] = have ? row[(size_t)a * 6 * deg + 6 * slot + b] : 0.0;
+                    item++;
+                }
+    }
+}
+
+}  // namespace fs

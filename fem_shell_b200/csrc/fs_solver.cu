@@ -12,8 +12,12 @@
 // Reductions are deterministic: per-block partials, the last block to arrive sums them in index
 // order.  Multi-GPU: halo exchange of p before k_spmv_dot (ncclSend/Recv), ncclAllReduce of the
 // partial sums, then a one-thread finalise kernel.
+#include <cub/cub.cuh>
+
 #include "fs_context.hpp"
+#include "fs_cg_device.cuh"
 #include "fs_nccl.hpp"
+#include "fs_sell.cuh"
 
 namespace fs {
 
@@ -25,108 +29,6 @@ namespace fs {
     } while (0)
 
 static inline unsigned int nblk(int64_t n, int bs) { return (unsigned int)((n + bs - 1) / bs); }
-
-// ---------------------------------------------------------------------------------------------
-// deterministic grid reduction of NV values; returns true in the block that arrives last, with
-// the totals in out[] (valid for thread 0 of that block)
-// ---------------------------------------------------------------------------------------------
-template <int NV, int BLOCK>
-__device__ __forceinline__ bool grid_reduce(double (&v)[NV], double *partials, unsigned int *counter,
-                                            double (&out)[NV])
-{
-    __shared__ double s_red[NV][BLOCK / 32];
-    __shared__ bool s_last;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < NV; k++) {
-        double x = v[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0) s_red[k][warp] = x;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; k++) {
-            double x = 0.0;
-            for (int w = 0; w < BLOCK / 32; w++) x += s_red[k][w];
-            partials[(size_t)blockIdx.x * NV + k] = x;
-        }
-        __threadfence();
-        unsigned int ticket = atomicInc(counter, gridDim.x - 1);  // wraps back to 0 for the next use
-        s_last = (ticket == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return false;
-    __threadfence();
-    // fixed-order sum of the per-block partials
-#pragma unroll
-    for (int k = 0; k < NV; k++) {
-        double x = 0.0;
-        for (unsigned int b = threadIdx.x; b < gridDim.x; b += BLOCK) x += partials[(size_t)b * NV + k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        __syncthreads();
-        if (lane == 0) s_red[k][warp] = x;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; k++) {
-            double x = 0.0;
-            for (int w = 0; w < BLOCK / 32; w++) x += s_red[k][w];
-            out[k] = x;
-        }
-    }
-    return true;
-}
-
-// ---- scalar recurrences (run by one thread) --------------------------------------------------
-__device__ __forceinline__ void finalize_pq(CgState *s, double pq)
-{
-    s->pq = pq;
-    s->alpha = s->rz / pq;
-    if (!(pq > 0.0)) {  // not SPD (SURVEY.md section 7 "SPD is empirical")
-        s->status = FS_ERR_BREAKDOWN;
-        s->done = 1;
-    }
-}
-
-__device__ __forceinline__ void finalize_update(CgState *s, double rz_new, double nrm2)
-{
-    s->beta = rz_new / s->rz;
-    s->rz = rz_new;
-    s->nrm2 = nrm2;
-    s->iter += 1;
-    if (nrm2 <= s->tol2 * s->bnorm2) {
-        s->status = FS_OK;
-        s->done = 1;
-    } else if (s->iter >= s->max_its) {
-        s->status = FS_ERR_NOT_CONVERGED;
-        s->done = 1;
-    }
-}
-
-__device__ __forceinline__ void finalize_init(CgState *s, double rz, double nrm2, double bnorm2)
-{
-    s->rz = rz;
-    s->nrm2 = nrm2;
-    s->bnorm2 = bnorm2;
-    s->iter = 0;
-    s->status = FS_ERR_NOT_CONVERGED;
-    s->done = 0;
-    if (bnorm2 == 0.0) {  // b = 0 -> x = 0 (host zeroes x when it sees nrm2 < 0)
-        s->bnorm2 = 1.0;
-        s->nrm2 = -1.0;
-        s->status = FS_OK;
-        s->done = 1;
-    } else if (nrm2 <= s->tol2 * bnorm2) {
-        s->status = FS_OK;
-        s->done = 1;
-    } else if (s->max_its <= 0) {
-        s->done = 1;
-    }
-}
 
 // which: 0 init (red = rz, nrm2, bnorm2), 1 after spmv (red = pq), 2 after update (red = rz_new, nrm2)
 __global__ void k_finalize(CgState *s, const double *red, int which)
@@ -256,23 +158,6 @@ __device__ __forceinline__ void apply_pc_node(const double *__restrict__ minv, i
             z[a] = s;
         }
     }
-}
-
-__device__ __forceinline__ void load6(const double *p, double v[6])
-{
-    const double2 *q = reinterpret_cast<const double2 *>(p);
-#pragma unroll
-    for (int h = 0; h < 3; h++) {
-        double2 t = q[h];
-        v[2 * h] = t.x;
-        v[2 * h + 1] = t.y;
-    }
-}
-__device__ __forceinline__ void store6(double *p, const double v[6])
-{
-    double2 *q = reinterpret_cast<double2 *>(p);
-#pragma unroll
-    for (int h = 0; h < 3; h++) q[h] = make_double2(v[2 * h], v[2 * h + 1]);
 }
 
 template <int PC, int NORM, int BLOCK>
@@ -419,13 +304,102 @@ int solver_query_occupancy(fs_context *c)
     c->spmv_blocks_per_sm = std::max(1, nb);
     FS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_update<1, 0, 256>, 256, 0));
     c->vec_blocks_per_sm = std::max(1, nb);
+    FS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_spmv_sell<SELL_MASK_XY, true, SELL_BLOCK, SELL_MINB>, SELL_BLOCK, 0));
+    c->sell_blocks_per_sm = std::max(1, nb);
     return FS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// zero-compacted SpMV copy (fs_sell.cuh): measured and rebuilt lazily after every values pass
+// ---------------------------------------------------------------------------------------------
+static const unsigned long long SELL_MASKS[3] = {SELL_MASK_XY, SELL_MASK_XZ, SELL_MASK_YZ};
+
+static void drop_cg_graph(fs_context *c)
+{
+    if (c->cg_graph_exec) cudaGraphExecDestroy(c->cg_graph_exec);
+    c->cg_graph_exec = nullptr;
+}
+
+int spmv_format_prepare(fs_context *c)
+{
+    if (c->sell_checked) return FS_OK;
+    if (!c->assembled) return fail(c, FS_ERR_STATE, "matrix not assembled");
+    cudaStream_t st = c->stream;
+    const bool was = c->sell_active;
+    const unsigned long long old_mask = c->sell_mask;
+    c->sell_active = false;
+    c->sell_checked = true;
+    if (c->spmv_format_pref == FS_SPMV_FULL) {
+        if (was) drop_cg_graph(c);
+        return FS_OK;
+    }
+    const int n_own = (int)c->n_own;
+    if (c->d_sell_mask.n < 1) FS_CUDA(c, c->d_sell_mask.alloc(1));
+    FS_CUDA(c, cudaMemsetAsync(c->d_sell_mask.p, 0, sizeof(unsigned long long), st));
+    k_sell_detect<<<c->sm_count * 8, 256, 0, st>>>(n_own, c->d_nptr.p, c->d_vals.p, c->d_sell_mask.p);
+    unsigned long long m = 0;
+    FS_CUDA(c, cudaMemcpyAsync(&m, c->d_sell_mask.p, sizeof m, cudaMemcpyDeviceToHost, st));
+    FS_CUDA(c, cudaStreamSynchronize(st));
+    c->sell_detected = m;
+    unsigned long long mask = 0;
+    for (int k = 0; k < 3 && !mask; k++)
+        if ((m & ~SELL_MASKS[k]) == 0) { mask = SELL_MASKS[k]; c->sell_kind = k; }
+    if (!mask) {  // blocks are (nearly) dense: the parity format is the SpMV format
+        if (was) drop_cg_graph(c);
+        return FS_OK;
+    }
+    const int n_slices = (n_own + 31) / 32;
+    int write_adj = 0;
+    if (!c->sell_layout_ready) {
+        DevBuf<int32_t> dmax;
+        FS_CUDA(c, dmax.alloc((size_t)n_slices + 1));
+        FS_CUDA(c, c->d_sell_sptr.alloc((size_t)n_slices + 1));
+        k_sell_dmax<<<nblk(n_slices, 8), 256, 0, st>>>(n_own, n_slices, c->d_nptr.p, dmax.p);
+        size_t bytes = 0;
+        FS_CUDA(c, cub::DeviceScan::ExclusiveSum(nullptr, bytes, dmax.p, c->d_sell_sptr.p, n_slices + 1, st));
+        DevBuf<char> tmp;
+        FS_CUDA(c, tmp.alloc(bytes));
+        FS_CUDA(c, cub::DeviceScan::ExclusiveSum(tmp.p, bytes, dmax.p, c->d_sell_sptr.p, n_slices + 1, st));
+        int32_t total = 0;
+        FS_CUDA(c, cudaMemcpyAsync(&total, c->d_sell_sptr.p + n_slices, sizeof total, cudaMemcpyDeviceToHost, st));
+        FS_CUDA(c, cudaStreamSynchronize(st));
+        c->sell_slices = n_slices;
+        c->sell_slots = total;
+        FS_CUDA(c, c->d_sell_adj.alloc((size_t)32 * total));
+        c->sell_layout_ready = true;
+        write_adj = 1;
+    }
+    const int nz = sell_popcount(mask);
+    const size_t need = (size_t)32 * nz * c->sell_slots;
+    if (c->d_sell_vals.n < need) FS_CUDA(c, c->d_sell_vals.alloc(need));
+    k_sell_fill<<<nblk(n_slices, 8), 256, 0, st>>>(n_own, n_slices, (int)c->own_lo, mask, c->d_nptr.p, c->d_nadj.p, c->d_vals.p,
+                                                   c->d_sell_sptr.p, c->d_sell_adj.p, c->d_sell_vals.p, nz, write_adj);
+    FS_CUDA(c, cudaGetLastError());
+    c->sell_active = true;
+    c->sell_mask = mask;
+    c->sell_nz = nz;
+    if (!was || old_mask != mask) drop_cg_graph(c);
+    return FS_OK;
+}
+
+template <unsigned long long MASK, bool WITH_DOT>
+static void launch_sell(fs_context *c, const double *x, double *y_own, const double *x_own, double *red, int single)
+{
+    const int64_t want = (c->sell_slices + SELL_BLOCK / 32 - 1) / (SELL_BLOCK / 32);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->sm_count * c->sell_blocks_per_sm));
+    k_spmv_sell<MASK, WITH_DOT, SELL_BLOCK, SELL_MINB><<<grid, SELL_BLOCK, 0, c->stream>>>(
+        (int)c->n_own, (int)c->sell_slices, c->d_sell_sptr.p, c->d_sell_adj.p, c->d_sell_vals.p, x, y_own, x_own,
+        c->d_partials.p, c->d_counter.p, c->d_state.p, red, single);
 }
 
 int solver_prepare(fs_context *c, int pc)
 {
     if (!c->assembled) return fail(c, FS_ERR_STATE, "fs_solve before fs_assemble");
     if (pc < 0 || pc > 2) return fail(c, FS_ERR_ARG, "unknown preconditioner");
+    {
+        int rc = spmv_format_prepare(c);
+        if (rc) return rc;
+    }
     if (c->minv_kind == pc) return FS_OK;
     if (pc != FS_PC_NONE) {
         const size_t need = (size_t)(pc == 1 ? 6 : 36) * c->n_own;
@@ -490,13 +464,28 @@ static int vec_grid(fs_context *c)
     return (int)std::max<int64_t>(1, std::min(want, cap));
 }
 
+// y_own = A x (+ partial x_own.y_own) on whichever copy of the matrix is current
+template <bool WITH_DOT>
+static void launch_spmv(fs_context *c, const double *x, double *y_own, const double *x_own, double *red, int single)
+{
+    if (c->sell_active) {
+        if (c->sell_mask == SELL_MASK_XY) launch_sell<SELL_MASK_XY, WITH_DOT>(c, x, y_own, x_own, red, single);
+        else if (c->sell_mask == SELL_MASK_XZ) launch_sell<SELL_MASK_XZ, WITH_DOT>(c, x, y_own, x_own, red, single);
+        else launch_sell<SELL_MASK_YZ, WITH_DOT>(c, x, y_own, x_own, red, single);
+        return;
+    }
+    k_spmv<WITH_DOT, SPMV_BLOCK><<<spmv_grid(c), SPMV_BLOCK, 0, c->stream>>>(
+        (int)c->n_own, c->d_nptr.p, c->d_nadj.p, c->d_vals.p, x, y_own, x_own, c->d_partials.p, c->d_counter.p,
+        c->d_state.p, red, single);
+}
+
 int spmv_once(fs_context *c, const double *d_in, double *d_out)
 {
-    int rc = halo_exchange(c, const_cast<double *>(d_in));
+    int rc = spmv_format_prepare(c);
     if (rc) return rc;
-    k_spmv<false, SPMV_BLOCK><<<spmv_grid(c), SPMV_BLOCK, 0, c->stream>>>((int)c->n_own, c->d_nptr.p, c->d_nadj.p, c->d_vals.p, d_in,
-                                                           d_out + 6 * c->own_lo, nullptr, nullptr, nullptr, nullptr,
-                                                           nullptr, 0);
+    rc = halo_exchange(c, const_cast<double *>(d_in));
+    if (rc) return rc;
+    launch_spmv<false>(c, d_in, d_out + 6 * c->own_lo, nullptr, nullptr, 0);
     FS_CUDA(c, cudaGetLastError());
     return FS_OK;
 }
@@ -508,9 +497,7 @@ static int enqueue_iteration(fs_context *c, double *red, int sg, int vg)
     const int64_t o6 = 6 * c->own_lo;
     int rc = halo_exchange(c, c->d_p.p);
     if (rc) return rc;
-    k_spmv<true, SPMV_BLOCK><<<sg, SPMV_BLOCK, 0, c->stream>>>((int)c->n_own, c->d_nptr.p, c->d_nadj.p, c->d_vals.p, c->d_p.p,
-                                                 c->d_q.p + o6, c->d_p.p + o6, c->d_partials.p, c->d_counter.p,
-                                                 c->d_state.p, red, single);
+    launch_spmv<true>(c, c->d_p.p, c->d_q.p + o6, c->d_p.p + o6, red, single);
     if (!single) {
         FS_NCCL(c, nccl().AllReduce(red, red, 1, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
         k_finalize<<<1, 1, 0, c->stream>>>(c->d_state.p, red, 1);
@@ -533,7 +520,7 @@ static int run_pcg(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
     const int single = (c->world == 1);
     const int64_t o6 = 6 * c->own_lo;
     const int sg = spmv_grid(c), vg = vec_grid(c);
-    const int maxgrid = std::max(sg, vg);
+    const int maxgrid = std::max(std::max(sg, vg), c->sm_count * c->sell_blocks_per_sm);
     if (c->d_partials.n < (size_t)maxgrid * 4) FS_CUDA(c, c->d_partials.alloc((size_t)maxgrid * 4 + 16));
     double *red = c->d_partials.p + (size_t)maxgrid * 4;  // 16 spare doubles behind the partials
 
@@ -560,7 +547,7 @@ static int run_pcg(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
     // The iteration is captured once into a CUDA graph of GRAPH_ITERS iterations and replayed; kernels
     // past convergence (or past max_its) see done != 0 and return, so replaying whole graphs is exact.
     constexpr int GRAPH_ITERS = 8;
-    const int key = PC * 2 + NORM;
+    const int key = PC * 2 + NORM + (c->sell_active ? 8 * (1 + c->sell_kind) : 0);
     if (!c->cg_graph_exec || c->cg_graph_key != key || c->cg_graph_red != red) {
         if (c->cg_graph_exec) cudaGraphExecDestroy(c->cg_graph_exec);
         c->cg_graph_exec = nullptr;

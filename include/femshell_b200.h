@@ -63,6 +63,12 @@ enum { FS_QUIRK_Y21 = 1 /* fs.cpp:586 */, FS_QUIRK_DET_LU = 2 /* fs.cpp:512,652 
  * graph-coloured scatter-add (one launch per colour, atomics-free read-modify-write) */
 enum { FS_ASM_COLORED = 0, FS_ASM_GATHER = 1 };
 
+/* storage the SpMV streams: AUTO = after each values pass measure the union pattern of all 6x6 blocks and,
+ * when it is one of the planar-shell patterns (membrane / bending / drilling decoupled: 14 of 36 entries),
+ * iterate on a zero-compacted sliced-ELL copy; FULL = always the parity format (explicit zeros included).
+ * fs_export_csr returns the parity format either way. */
+enum { FS_SPMV_AUTO = 0, FS_SPMV_FULL = 1 };
+
 typedef struct fs_solve_opts {
     double rtol;        /* relative tolerance (reference default 1e-12 = TOLERANCE^2, fs.cpp:130-133) */
     int64_t max_its;    /* reference default 5000 */
@@ -101,6 +107,7 @@ int fs_set_material(fs_context *ctx, double nu, double E, double thickness);
 int fs_set_quirks(fs_context *ctx, int quirk_flags);
 int fs_set_dof_order(fs_context *ctx, int mode);
 int fs_set_assembly_mode(fs_context *ctx, int mode);
+int fs_set_spmv_format(fs_context *ctx, int mode);
 
 /* replaces mesh.read + the DirichletBoundary setup (fs.cpp:35-37, 90-120) + equation_systems.init
  * (fs.cpp:125: DOF numbering, sparsity, constraints).  The whole (replicated) mesh is passed on
@@ -164,6 +171,10 @@ int fs_export_rhs(fs_context *ctx, double *rhs /* 6*n_own */);
 int fs_debug_element_matrices(fs_context *ctx, double *out);
 /* y = A x on the device matrix; x, y in DOF order, length 6*n_dofnodes (single rank only) */
 int fs_spmv_host(fs_context *ctx, const double *x, double *y);
+/* format the SpMV of the assembled matrix runs on: info = {values streamed per 6x6 block (36 parity
+ * format, 14 compacted), matrix bytes streamed per SpMV (values + column ids + row/slice pointers),
+ * block slots incl. padding, 36-bit union pattern of the blocks (bit 6a+b)} */
+int fs_get_spmv_format(fs_context *ctx, int64_t info[4]);
 /* times `reps` SpMV launches with CUDA events on the context stream (info->spmv_ms = mean) */
 int fs_bench_spmv(fs_context *ctx, int reps, fs_solve_info *info);
 

@@ -144,6 +144,61 @@ def test_spmv_matches_oracle(fso, fsb):
     assert np.abs(y - yr).max() <= 1e-12 * np.abs(yr).max()
 
 
+def _rotate_mesh(m, R):
+    m = dict(m)
+    m["xyz"] = np.ascontiguousarray(np.asarray(m["xyz"], float) @ R.T)
+    m["forces"] = np.ascontiguousarray(np.hstack([m["forces"][:, :3] @ R.T, m["forces"][:, 3:] @ R.T]))
+    return m
+
+
+@pytest.mark.parametrize("plane", ["xy", "xz", "yz"])
+@pytest.mark.parametrize("kind", ["q", "t"])
+def test_compacted_spmv_format_on_planar_shells(fso, fsb, kind, plane):
+    """plates in a coordinate plane: the union pattern of the 6x6 blocks has 14 entries, the SpMV runs on the
+    sliced-ELL copy and agrees with the oracle's CSR product and with the parity-format kernel"""
+    m = fsb.meshgen(kind, 37, 21, 0, 0, 10, 6, (1, 0, 1, 20), 300.0, 2, 1)
+    R = {"xy": np.eye(3), "xz": np.array([[1., 0, 0], [0, 0, -1], [0, 1, 0]]), "yz": np.array([[0., 0, 1], [1, 0, 0], [0, 1, 0]])}[plane]
+    m = _rotate_mesh(m, R)
+    ref = fso.assemble(as_fso_mesh(fso, m), m["forces"], 0.3, 1e7, 0.5)
+    s = gpu_system(fsb, m, 0.3, 1e7, 0.5, loads=m["forces"])
+    fmt = s.spmv_format()
+    assert fmt["nz_per_block"] == 14 and fmt["pattern"].sum() == 14, fmt
+    rp, ci, v = ref.csr()
+    rows = np.repeat(np.arange(rp.size - 1), np.diff(rp))
+    pat = np.zeros((6, 6), int)
+    np.add.at(pat, (rows[v != 0] % 6, ci[v != 0] % 6), 1)
+    assert np.array_equal(fmt["pattern"] > 0, pat > 0)
+    x = np.random.default_rng(11).standard_normal(6 * ref.n_dofnodes)
+    y, yr = s.spmv(x), fso.spmv(ref, x)
+    assert np.abs(y - yr).max() <= 1e-13 * np.abs(yr).max()
+    s.set_spmv_format(fsb.SPMV_FULL)
+    assert s.spmv_format()["nz_per_block"] == 36
+    y36 = s.spmv(x)
+    assert np.abs(y - y36).max() <= 1e-13 * np.abs(yr).max()
+    # the solve is the same on either copy
+    i36 = s.solve(rtol=1e-10, max_its=200000, warm_start=False)
+    u36 = s.solution()
+    s.set_spmv_format(fsb.SPMV_AUTO)
+    i14 = s.solve(rtol=1e-10, max_its=200000, warm_start=False)
+    u14 = s.solution()
+    assert abs(i14.iterations - i36.iterations) <= max(3, i36.iterations // 50)
+    assert np.linalg.norm(u14 - u36) <= 1e-8 * np.linalg.norm(u36)
+    # re-assembly with another material keeps the layout and refreshes the values
+    s.set_material(0.2, 2e7, 0.4)
+    s.assemble()
+    ref2 = fso.assemble(as_fso_mesh(fso, m), m["forces"], 0.2, 2e7, 0.4)
+    y2, y2r = s.spmv(x), fso.spmv(ref2, x)
+    assert s.spmv_format()["nz_per_block"] == 14
+    assert np.abs(y2 - y2r).max() <= 1e-13 * np.abs(y2r).max()
+
+
+def test_dense_blocks_keep_the_parity_format(fso, fsb):
+    m = meshes.folded_cantilever(skew=0.35)
+    s = gpu_system(fsb, m, 0.3, 1e4, 0.25, loads=m["forces"])
+    fmt = s.spmv_format()
+    assert fmt["nz_per_block"] == 36 and fmt["pattern"].sum() == 36
+
+
 # ---- solves ---------------------------------------------------------------------------------
 def agree6(value, gold):
     import math
