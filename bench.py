@@ -162,7 +162,8 @@ def run_ours(args):
     ny = args.nodes * world                      # weak scaling: one 1000 x 1000-node strip per GPU
     m = make_workload(fsb, nx, ny)
     n_nodes, n_elem = m["xyz"].shape[0], m["etype"].size
-    s = fsb.FemShell(device=local_rank, rank=rank, world=world, nccl_id=nccl_id)
+    comm = {"auto": fsb.COMM_AUTO, "nccl": fsb.COMM_NCCL, "peer": fsb.COMM_PEER}[args.comm]
+    s = fsb.FemShell(device=local_rank, rank=rank, world=world, nccl_id=nccl_id, comm=comm)
     s.set_material(NU, EM, THICK)
     s.set_assembly_mode(fsb.ASM_GATHER if args.asm == "gather" else fsb.ASM_COLORED)
     s.set_spmv_format(fsb.SPMV_FULL if args.spmv == "full" else fsb.SPMV_AUTO)
@@ -222,6 +223,8 @@ def run_ours(args):
     # ---- dominant kernel: SpMV, timed alone on the same stream right after the timed region ----
     spmv_ms = max_over_ranks(s.bench_spmv(50))
     fmt = s.spmv_format()
+    comm_used = "none (single rank)" if world == 1 else ("NVLink peer windows: halo push + mailbox all-reduce inside the CG kernels"
+                                                          if s.comm_mode() == fsb.COMM_PEER else "NCCL send/recv + all-reduce per iteration")
     actual_b, csr_b = spmv_bytes(6 * n_own, sz["n_blocks"], fmt["matrix_bytes"])
     spmv_kernel = "k_spmv_sell" if fmt["nz_per_block"] < 36 else "k_spmv"
     peak, peak_src = peaks()
@@ -301,7 +304,9 @@ def run_ours(args):
                "elements_per_s": n_elem / t_asm}
 
     launches_per_step = 3 + 3 * iters           # rhs, spmv(x0), init, then (spmv+dot, update, direction) per iteration
-    if world > 1:
+    if world > 1 and s.comm_mode() == fsb.COMM_PEER:
+        launches_per_step += 2 + iters          # pack + init finalise, then one halo-push kernel per iteration
+    elif world > 1:
         launches_per_step += 2 + 3 * iters      # pack + finalise kernels around the NCCL calls
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -312,7 +317,7 @@ def run_ours(args):
                    "iters_per_step": iters, "pc": "jacobi", "dof_order": "first_encounter",
                    "spmv_format": "%d of 36 entries per 6x6 block streamed (%s)" % (fmt["nz_per_block"], "zero-compacted sliced ELL" if fmt["nz_per_block"] < 36 else "parity block-CSR"),
                    "l2_policy": "inputs larger than L2 (matrix %.2f GB per GPU streamed every iteration)" % (1e-9 * fmt["matrix_bytes"]),
-                   "parallelism": "node-block strips x%d" % world},
+                   "parallelism": "node-block strips x%d" % world, "comm": comm_used},
         "metrics": {"cg_dof_iterations_per_s": value, "elements_assembled_per_s": n_elem / (asm_ms * 1e-3),
                     "assemble_ms": asm_ms, "time_to_solution": tts, "setup_s_pattern_colouring_upload": t_setup,
                     "colors": sz["n_colors"], "assembly_mode": args.asm},
@@ -347,6 +352,7 @@ def main():
     ap.add_argument("--ref-nodes", type=int, default=1000)
     ap.add_argument("--ref-iters", type=int, default=10)
     ap.add_argument("--asm", default="gather", choices=["colored", "gather"])
+    ap.add_argument("--comm", default="auto", choices=["auto", "nccl", "peer"], help="multi-GPU exchange inside the CG iteration")
     ap.add_argument("--spmv", default="auto", choices=["auto", "full"], help="full = always stream the parity block-CSR (explicit zeros included)")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes/launch of k_spmv from an ncu --set full capture")
     args = ap.parse_args()

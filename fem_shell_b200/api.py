@@ -22,13 +22,14 @@ DOF_FIRST_ENCOUNTER, DOF_NODE_ID = 0, 1
 PC_NONE, PC_JACOBI, PC_BJACOBI6 = 0, 1, 2
 NORM_UNPRECONDITIONED, NORM_PRECONDITIONED = 0, 1
 QUIRKS_REFERENCE = 3
+COMM_AUTO, COMM_NCCL, COMM_PEER = 0, 1, 2   # how the CG iteration talks between GPUs (fs_peer.cuh)
 SPMV_AUTO, SPMV_FULL = 0, 1       # AUTO: iterate on the zero-compacted copy when the blocks share a planar pattern
 ASM_COLORED, ASM_GATHER = 0, 1   # gather is the default; it falls back to coloured if a row is too dense
 FS_OK, FS_ERR_ARG, FS_ERR_CUDA, FS_ERR_STATE, FS_ERR_NOT_CONVERGED, FS_ERR_BREAKDOWN, FS_ERR_COMM, FS_ERR_IO = 0, -1, -2, -3, -4, -5, -6, -7
 
 # every symbol include/femshell_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
-    "fs_create", "fs_destroy", "fs_last_error", "fs_get_stream", "fs_dist_unique_id", "fs_dist_init",
+    "fs_create", "fs_destroy", "fs_last_error", "fs_get_stream", "fs_dist_unique_id", "fs_dist_init", "fs_set_comm_mode", "fs_get_comm_mode",
     "fs_set_material", "fs_set_quirks", "fs_set_dof_order", "fs_set_assembly_mode", "fs_set_spmv_format", "fs_get_spmv_format", "fs_set_mesh",
     "fs_set_nodal_loads", "fs_set_interface_loads", "fs_build_rhs", "fs_assemble", "fs_solve",
     "fs_get_solution", "fs_solve_host", "fs_interface_nodes", "fs_step", "fs_commit_step", "fs_get_sizes",
@@ -170,7 +171,7 @@ def write_xda(path, xyz, etype, eptr, enodes, bc):
 class FemShell:
     """One GPU, one stream.  Method names follow the C ABI one to one."""
 
-    def __init__(self, device=0, rank=0, world=1, nccl_id=None):
+    def __init__(self, device=0, rank=0, world=1, nccl_id=None, comm=COMM_AUTO):
         self.lib = load_library()
         self.ctx = C.c_void_p()
         rc = self.lib.fs_create(C.byref(self.ctx), C.c_int(device))
@@ -181,6 +182,12 @@ class FemShell:
         if world > 1:
             buf = (C.c_uint8 * 128).from_buffer_copy(bytes(nccl_id))
             self._ck(self.lib.fs_dist_init(self.ctx, C.c_int(rank), C.c_int(world), buf))
+            self._ck(self.lib.fs_set_comm_mode(self.ctx, C.c_int(comm)))
+
+    def comm_mode(self) -> int:
+        m = C.c_int()
+        self._ck(self.lib.fs_get_comm_mode(self.ctx, C.byref(m)))
+        return m.value
 
     @staticmethod
     def unique_id() -> bytes:

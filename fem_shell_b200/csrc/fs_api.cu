@@ -62,6 +62,7 @@ int fs_destroy(fs_context *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->cg_graph_exec) cudaGraphExecDestroy(c->cg_graph_exec);
+    peer_window_teardown(c);
     if (c->comm && nccl().ok) nccl().CommDestroy((ncclComm_t)c->comm);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -102,6 +103,23 @@ int fs_dist_init(fs_context *c, int rank, int world, const uint8_t id_bytes[128]
         if (r != ncclSuccess) return fail(c, FS_ERR_COMM, std::string("ncclCommInitRank: ") + nccl().GetErrorString(r));
         c->comm = (ncclComm *)comm;
     }
+    return FS_OK;
+}
+
+int fs_set_comm_mode(fs_context *c, int mode)
+{
+    FS_CHECK_CTX(c);
+    if (mode != FS_COMM_AUTO && mode != FS_COMM_NCCL && mode != FS_COMM_PEER) return fail(c, FS_ERR_ARG, "unknown comm mode");
+    if (c->n_nodes) return fail(c, FS_ERR_STATE, "fs_set_comm_mode must precede fs_set_mesh");
+    c->comm_pref = mode;
+    return FS_OK;
+}
+
+int fs_get_comm_mode(fs_context *c, int *mode)
+{
+    FS_CHECK_CTX(c);
+    if (!mode) return fail(c, FS_ERR_ARG, "null output");
+    *mode = c->peer_ready ? FS_COMM_PEER : FS_COMM_NCCL;
     return FS_OK;
 }
 
@@ -179,6 +197,7 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
         return fail(c, FS_ERR_ARG, "empty mesh or null array");
     if (n_nodes >= (int64_t)1 << 31 || n_elem >= (int64_t)1 << 31) return fail(c, FS_ERR_ARG, "mesh too large for 32-bit ids");
     FS_CUDA(c, cudaSetDevice(c->device));
+    FS_TRY(peer_window_teardown(c));
     for (int64_t e = 0; e < n_elem; e++) {
         int nen = (int)(eptr[e + 1] - eptr[e]);
         if ((etype[e] == FS_TRI3 && nen != 3) || (etype[e] == FS_QUAD4 && nen != 4) ||
@@ -297,6 +316,7 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
         FS_CUDA(c, cudaMemset(v->p, 0, sizeof(double) * 6 * c->n_local));
     }
     c->d_full.release();
+    FS_TRY(peer_window_setup(c));
     return build_pattern(c, tri, quad, tri_gid, quad_gid);
 }
 

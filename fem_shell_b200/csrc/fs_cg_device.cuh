@@ -2,6 +2,7 @@
 // (fs_sell.cuh): the deterministic grid reduction and the scalar recurrences of the iteration.
 #pragma once
 #include "fs_context.hpp"
+#include "fs_peer.cuh"
 
 namespace fs {
 
@@ -104,6 +105,23 @@ __device__ __forceinline__ void finalize_init(CgState *s, double rz, double nrm2
         s->done = 1;
     } else if (s->max_its <= 0) {
         s->done = 1;
+    }
+}
+
+// what the block that finished a grid reduction does with the totals.  fin_mode: 0 leave them in red[] (an
+// ncclAllReduce + k_finalize follow), 1 single rank: advance the recurrence here, 2 push them to every
+// rank's mailbox (fs_peer.cuh); the consuming kernel completes the sum
+enum { FIN_RED = 0, FIN_INLINE = 1, FIN_PEER = 2 };
+template <int NV>
+__device__ __forceinline__ void finish_dot(const double (&out)[NV], double *red, int fin_mode, CgState *state, PeerWin *pw)
+{
+#pragma unroll
+    for (int k = 0; k < NV; k++) red[k] = out[k];
+    if (fin_mode == FIN_PEER) peer_red_push<NV>(pw, out);
+    else if (fin_mode == FIN_INLINE) {
+        if (NV == 1) finalize_pq(state, out[0]);
+        else if (NV == 2) finalize_update(state, out[0], out[NV > 1 ? 1 : 0]);
+        else finalize_init(state, out[0], out[NV > 1 ? 1 : 0], out[NV > 2 ? 2 : 0]);
     }
 }
 

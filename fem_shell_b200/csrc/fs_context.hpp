@@ -10,6 +10,7 @@
 #include "../../include/femshell_b200.h"
 
 struct ncclComm;
+namespace fs { struct PeerWin; }
 
 namespace fs {
 
@@ -17,15 +18,24 @@ template <class T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    bool owned = true;
     ~DevBuf() { release(); }
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     void release()
     {
-        if (p) cudaFree(p);
+        if (p && owned) cudaFree(p);
         p = nullptr;
         n = 0;
+        owned = true;
+    }
+    void view(T *ptr, size_t count)  // non-owning window into another allocation
+    {
+        release();
+        p = ptr;
+        n = count;
+        owned = false;
     }
     cudaError_t alloc(size_t count)
     {
@@ -80,6 +90,14 @@ struct fs_context {
     // distributed
     int rank = 0, world = 1;
     ncclComm *comm = nullptr;
+
+    // NVLink peer window (fs_peer.cuh): [mailbox | p] mapped into every rank of the box
+    int comm_pref = FS_COMM_AUTO;
+    bool peer_ready = false;
+    void *win_base = nullptr;                  // this rank's window (cudaMalloc)
+    void *peer_base[8] = {};                   // the other ranks' windows (cudaIpcOpenMemHandle)
+    fs::DevBuf<fs::PeerWin> d_pw;
+    fs::DevBuf<int32_t> d_push_peer, d_push_dst;
 
     // material / switches
     double nu = 0.3, E = 1e7, thickness = 1.0;
@@ -201,5 +219,9 @@ int solver_run(fs_context *c, const fs_solve_opts *o, fs_solve_info *info);
 int spmv_once(fs_context *c, const double *d_in, double *d_out);
 int halo_exchange(fs_context *c, double *d_vec);
 int spmv_format_prepare(fs_context *c);
+
+// peer.cu
+int peer_window_setup(fs_context *c);     // collective; call after the vectors are sized
+int peer_window_teardown(fs_context *c);  // collective
 
 }  // namespace fs

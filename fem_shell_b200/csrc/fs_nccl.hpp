@@ -21,6 +21,7 @@ struct NcclApi {
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     bool ok = false;
 };
 
@@ -41,9 +42,10 @@ inline NcclApi &nccl()
         FS_SYM(Send, "ncclSend");
         FS_SYM(Recv, "ncclRecv");
         FS_SYM(AllReduce, "ncclAllReduce");
+        FS_SYM(AllGather, "ncclAllGather");
 #undef FS_SYM
         a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.GetErrorString && a.GroupStart && a.GroupEnd &&
-               a.Send && a.Recv && a.AllReduce;
+               a.Send && a.Recv && a.AllReduce && a.AllGather;
         return a;
     }();
     return api;

@@ -1,0 +1,167 @@
+// fs_peer.cuh -- the CG iteration's two exchanges done by the kernels themselves over NVLink peer memory.
+//
+// The reference's Krylov loop (KSPSolve, fs.cpp:138) costs PETSc one VecScatter (halo of p) and two
+// MPI_Allreduce per iteration.  With one process per GPU on an NVSwitch box every rank maps a small
+// "window" of every other rank (cudaIpc): [mailbox | direction vector p].  Then
+//   * the halo of p is PUSHED by its owner straight into the neighbours' halo segments of p (k_halo_push,
+//     remote 128-bit stores) and stamped; the neighbour's SpMV waits for the stamp at its first instruction;
+//   * a dot product is finished by the producing kernel: its last block stores the rank's partial sums into
+//     every rank's mailbox and stamps them; the consuming kernel (k_update for p.Ap, k_direction for r.z and
+//     the norm) waits for all stamps and adds the partials in rank order -- every rank gets bit-identical
+//     alpha/beta, deterministic, no reduction kernel, no NCCL launch in the loop.
+// Stamps are monotonic per rank; slots are double-buffered by stamp parity (a rank cannot run two
+// reductions ahead of a peer, because the next reduction needs the peer's contribution to this one).
+// A wait that exceeds spin_limit cycles marks the solve as FS_ERR_COMM instead of hanging the GPU.
+#pragma once
+#include "fs_context.hpp"
+
+namespace fs {
+
+constexpr int PEER_MAX = 8;                       // ranks of one NVSwitch box
+constexpr int MBOX_RED_SEQ = 0;                   // [2][PEER_MAX] stamps
+constexpr int MBOX_RED_VAL = 2 * PEER_MAX;        // [2][PEER_MAX][4] doubles
+constexpr int MBOX_HALO = MBOX_RED_VAL + 2 * PEER_MAX * 4;  // [PEER_MAX] stamps
+constexpr int MBOX_WORDS = 128;                   // 1 KB header in front of p
+
+struct PeerWin {
+    int rank, world;
+    unsigned long long seq_red;                   // stamp of this rank's latest reduction contribution
+    unsigned long long seq_halo;                  // stamp of this rank's latest halo push
+    unsigned long long *mbox[PEER_MAX];           // mailbox of every rank (mbox[rank] = own, local memory)
+    double *peer_p[PEER_MAX];                     // p vector of every rank in ITS local layout
+    int n_recv, recv_rank[PEER_MAX];              // ranks this rank receives halo values from
+    int n_send, send_rank[PEER_MAX];
+    long long spin_limit;                         // clock64 ticks
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_volatile_f64(const double *p)
+{
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_f64(double *p, double v)
+{
+    asm volatile("st.volatile.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+// spin until *flag >= stamp; false on timeout
+__device__ __forceinline__ bool peer_spin(const unsigned long long *flag, unsigned long long stamp, long long limit)
+{
+    if (ld_acquire_sys(flag) >= stamp) return true;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < stamp) {
+        __nanosleep(64);
+        if (clock64() - t0 > limit) return false;
+    }
+    return true;
+}
+
+// one thread: this rank's NV partial sums -> every rank's mailbox, then the stamps
+template <int NV>
+__device__ __forceinline__ void peer_red_push(PeerWin *pw, const double (&v)[NV])
+{
+    const unsigned long long stamp = pw->seq_red + 1;
+    const int par = (int)(stamp & 1), me = pw->rank;
+    for (int r = 0; r < pw->world; r++) {
+        double *val = reinterpret_cast<double *>(pw->mbox[r] + MBOX_RED_VAL) + (par * PEER_MAX + me) * 4;
+#pragma unroll
+        for (int k = 0; k < NV; k++) st_volatile_f64(val + k, v[k]);
+    }
+    __threadfence_system();
+    for (int r = 0; r < pw->world; r++) st_release_sys(pw->mbox[r] + MBOX_RED_SEQ + par * PEER_MAX + me, stamp);
+    pw->seq_red = stamp;
+}
+
+// whole block: wait for every rank's contribution to the reduction this rank produced last, add in rank
+// order.  Returns false on timeout (state marked FS_ERR_COMM by the caller).
+template <int NV>
+__device__ __forceinline__ bool peer_red_wait(PeerWin *pw, double (&out)[NV])
+{
+    __shared__ double s_sum[4];
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) {
+        const unsigned long long stamp = *reinterpret_cast<volatile unsigned long long *>(&pw->seq_red);
+        const int par = (int)(stamp & 1);
+        const unsigned long long *mb = pw->mbox[pw->rank];
+        bool ok = true;
+        for (int r = 0; r < pw->world && ok; r++) ok = peer_spin(mb + MBOX_RED_SEQ + par * PEER_MAX + r, stamp, pw->spin_limit);
+        double acc[NV];
+#pragma unroll
+        for (int k = 0; k < NV; k++) acc[k] = 0.0;
+        const double *val = reinterpret_cast<const double *>(mb + MBOX_RED_VAL) + par * PEER_MAX * 4;
+        for (int r = 0; r < pw->world; r++)
+#pragma unroll
+            for (int k = 0; k < NV; k++) acc[k] += ld_volatile_f64(val + 4 * r + k);
+#pragma unroll
+        for (int k = 0; k < NV; k++) s_sum[k] = acc[k];
+        s_ok = ok ? 1 : 0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; k++) out[k] = s_sum[k];
+    const bool ok = s_ok != 0;
+    __syncthreads();
+    return ok;
+}
+
+// whole block: wait until every neighbour has pushed as many halos as this rank has
+__device__ __forceinline__ bool peer_halo_wait(PeerWin *pw)
+{
+    __shared__ int s_hok;
+    if (threadIdx.x == 0) {
+        const unsigned long long stamp = *reinterpret_cast<volatile unsigned long long *>(&pw->seq_halo);
+        const unsigned long long *mb = pw->mbox[pw->rank];
+        bool ok = true;
+        for (int k = 0; k < pw->n_recv && ok; k++) ok = peer_spin(mb + MBOX_HALO + pw->recv_rank[k], stamp, pw->spin_limit);
+        s_hok = ok ? 1 : 0;
+    }
+    __syncthreads();
+    return s_hok != 0;
+}
+
+__device__ __forceinline__ void peer_fail(CgState *s)
+{
+    s->status = FS_ERR_COMM;
+    s->done = 1;
+}
+
+// owned boundary values of p -> the neighbours' halo segments (remote stores), then one stamp per neighbour.
+// push_peer[s] / push_dst[s]: destination rank and LOCAL node index there of send-list entry s.
+static __global__ void __launch_bounds__(256)
+k_halo_push(PeerWin *pw, int64_t n_send, const int32_t *__restrict__ idx, const int32_t *__restrict__ push_peer,
+            const int32_t *__restrict__ push_dst, const double *__restrict__ vec, CgState *state, unsigned int *counter)
+{
+    if (state->done) return;
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < 3 * n_send) {
+        const int64_t s = t / 3;
+        const int h = (int)(t - 3 * s);
+        const double2 v = reinterpret_cast<const double2 *>(vec + 6 * (size_t)idx[s])[h];
+        double2 *dst = reinterpret_cast<double2 *>(pw->peer_p[push_peer[s]] + 6 * (size_t)push_dst[s]) + h;
+        *dst = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicInc(counter, gridDim.x - 1);
+        if (ticket == gridDim.x - 1) {
+            __threadfence_system();
+            const unsigned long long stamp = pw->seq_halo + 1;
+            for (int k = 0; k < pw->n_send; k++) st_release_sys(pw->mbox[pw->send_rank[k]] + MBOX_HALO + pw->rank, stamp);
+            pw->seq_halo = stamp;
+        }
+    }
+}
+
+}  // namespace fs

@@ -18,6 +18,7 @@
 // whole block row, and no cross-lane reduction is needed.
 #pragma once
 #include "fs_cg_device.cuh"
+#include "fs_peer.cuh"
 
 namespace fs {
 
@@ -64,10 +65,14 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 k_spmv_sell(int n_own, int n_slices, const int32_t *__restrict__ sptr, const int32_t *__restrict__ adj,
             const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y_own,
             const double *__restrict__ x_own, double *partials, unsigned int *counter, CgState *state,
-            double *red, int inline_finalize)
+            double *red, int fin_mode, PeerWin *pw)
 {
     constexpr int NZ = sell_popcount(MASK);
     if (WITH_DOT && state->done) return;
+    if (WITH_DOT && pw && !peer_halo_wait(pw)) {  // the neighbours' boundary values of x must have landed
+        if (blockIdx.x == 0 && threadIdx.x == 0) peer_fail(state);
+        return;
+    }
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
     const int nw = gridDim.x * (BLOCK / 32);
@@ -108,10 +113,7 @@ k_spmv_sell(int n_own, int n_slices, const int32_t *__restrict__ sptr, const int
     }
     if (WITH_DOT) {
         double vv[1] = {dot}, out[1];
-        if (grid_reduce<1, BLOCK>(vv, partials, counter, out) && threadIdx.x == 0) {
-            red[0] = out[0];
-            if (inline_finalize) finalize_pq(state, out[0]);
-        }
+        if (grid_reduce<1, BLOCK>(vv, partials, counter, out) && threadIdx.x == 0) finish_dot<1>(out, red, fin_mode, state, pw);
     }
 }
 
@@ -120,7 +122,7 @@ k_spmv_sell(int n_own, int n_slices, const int32_t *__restrict__ sptr, const int
 // ---------------------------------------------------------------------------------------------
 // union pattern of all 6x6 blocks: bit 6a+b set when any block has a non-zero (a,b).  Same access
 // pattern as the full SpMV (warp = block row, lane = one double2 of each scalar row).
-__global__ void __launch_bounds__(256) k_sell_detect(int n_own, const int32_t *__restrict__ nptr,
+static __global__ void __launch_bounds__(256) k_sell_detect(int n_own, const int32_t *__restrict__ nptr,
                                                      const double *__restrict__ vals, unsigned long long *mask_out)
 {
     const int lane = threadIdx.x & 31;
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(256) k_sell_detect(int n_own, const int32_t *_
     if (lane == 0 && m) atomicOr(mask_out, m);
 }
 
-__global__ void k_sell_dmax(int n_own, int n_slices, const int32_t *__restrict__ nptr, int32_t *dmax)
+static __global__ void k_sell_dmax(int n_own, int n_slices, const int32_t *__restrict__ nptr, int32_t *dmax)
 {
     const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (s >= n_slices) return;
@@ -158,7 +160,7 @@ __global__ void k_sell_dmax(int n_own, int n_slices, const int32_t *__restrict__
 }
 
 // warp = slice, lane = block row: copies the masked entries of the parity format into the sliced layout
-__global__ void __launch_bounds__(256) k_sell_fill(int n_own, int n_slices, int own_lo, unsigned long long mask,
+static __global__ void __launch_bounds__(256) k_sell_fill(int n_own, int n_slices, int own_lo, unsigned long long mask,
                                                    const int32_t *__restrict__ nptr, const int32_t *__restrict__ nadj,
                                                    const double *__restrict__ full, const int32_t *__restrict__ sptr,
                                                    int32_t *__restrict__ adj, double *__restrict__ vals, int nz,

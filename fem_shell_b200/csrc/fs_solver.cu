@@ -54,9 +54,13 @@ __global__ void __launch_bounds__(BLOCK, SPMV_MIN_BLOCKS)
 k_spmv(int n_own, const int32_t *__restrict__ nptr, const int32_t *__restrict__ nadj,
        const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y_own,
        const double *__restrict__ x_own, double *partials, unsigned int *counter, CgState *state,
-       double *red, int inline_finalize)
+       double *red, int fin_mode, PeerWin *pw)
 {
     if (WITH_DOT && state->done) return;
+    if (WITH_DOT && pw && !peer_halo_wait(pw)) {  // the neighbours' boundary values of x must have landed
+        if (blockIdx.x == 0 && threadIdx.x == 0) peer_fail(state);
+        return;
+    }
     const int lane = threadIdx.x & 31;
     const int warps_per_block = BLOCK / 32;
     const int gw = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
@@ -118,10 +122,7 @@ k_spmv(int n_own, const int32_t *__restrict__ nptr, const int32_t *__restrict__ 
     }
     if (WITH_DOT) {
         double v[1] = {dot}, out[1];
-        if (grid_reduce<1, BLOCK>(v, partials, counter, out) && threadIdx.x == 0) {
-            red[0] = out[0];
-            if (inline_finalize) finalize_pq(state, out[0]);
-        }
+        if (grid_reduce<1, BLOCK>(v, partials, counter, out) && threadIdx.x == 0) finish_dot<1>(out, red, fin_mode, state, pw);
     }
 }
 
@@ -164,10 +165,21 @@ template <int PC, int NORM, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 k_update(int64_t n_own, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
          const double *__restrict__ q, double *__restrict__ z, const double *__restrict__ minv,
-         double *partials, unsigned int *counter, CgState *state, double *red, int inline_finalize)
+         double *partials, unsigned int *counter, CgState *state, double *red, int fin_mode, PeerWin *pw)
 {
     if (state->done) return;
-    const double alpha = state->alpha;
+    double alpha;
+    if (pw) {  // p.Ap arrives as one partial per rank in the mailbox: finish the sum here (fs_peer.cuh)
+        double t[1];
+        const bool ok = peer_red_wait<1>(pw, t);
+        const bool spd = t[0] > 0.0;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            if (!ok) peer_fail(state);
+            else finalize_pq(state, t[0]);
+        }
+        if (!ok || !spd) return;
+        alpha = state->rz / t[0];
+    } else alpha = state->alpha;
     double rz = 0.0, nn = 0.0;
     for (int64_t n = blockIdx.x * (int64_t)BLOCK + threadIdx.x; n < n_own; n += (int64_t)gridDim.x * BLOCK) {
         double xv[6], rv[6], pv[6], qv[6], zv[6];
@@ -191,21 +203,25 @@ k_update(int64_t n_own, double *__restrict__ x, double *__restrict__ r, const do
         }
     }
     double v[2] = {rz, nn}, out[2];
-    if (grid_reduce<2, BLOCK>(v, partials, counter, out) && threadIdx.x == 0) {
-        red[0] = out[0];
-        red[1] = out[1];
-        if (inline_finalize) finalize_update(state, out[0], out[1]);
-    }
+    if (grid_reduce<2, BLOCK>(v, partials, counter, out) && threadIdx.x == 0) finish_dot<2>(out, red, fin_mode, state, pw);
 }
 
 // p = z + beta p
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
-k_direction(int64_t n_own, const double *__restrict__ z, double *__restrict__ p, CgState *state)
+k_direction(int64_t n_own, const double *__restrict__ z, double *__restrict__ p, CgState *state, PeerWin *pw,
+            unsigned int *counter)
 {
     // after convergence x is final; p is not needed any more
     if (state->done) return;
-    const double beta = state->beta;
+    double beta, t[2] = {0.0, 0.0};
+    if (pw) {  // r.z and the norm arrive as per-rank partials: finish the sums, beta from the OLD r.z
+        if (!peer_red_wait<2>(pw, t)) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) peer_fail(state);
+            return;
+        }
+        beta = t[0] / state->rz;
+    } else beta = state->beta;
     const int64_t n2 = 3 * n_own;
     const double2 *z2 = reinterpret_cast<const double2 *>(z);
     double2 *p2 = reinterpret_cast<double2 *>(p);
@@ -215,6 +231,10 @@ k_direction(int64_t n_own, const double *__restrict__ z, double *__restrict__ p,
         pp.y = zz.y + beta * pp.y;
         p2[i] = pp;
     }
+    if (pw) {  // the block that finishes last advances the recurrence (every block has read the old state)
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicInc(counter, gridDim.x - 1) == gridDim.x - 1) finalize_update(state, t[0], t[1]);
+    }
 }
 
 // r = b - q ; z = M^-1 r ; p = z ; sums r.z, norm(r|z), norm(b|M^-1 b)
@@ -222,7 +242,7 @@ template <int PC, int NORM, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 k_init(int64_t n_own, const double *__restrict__ b, const double *__restrict__ q, double *__restrict__ r,
        double *__restrict__ z, double *__restrict__ p, const double *__restrict__ minv, double *partials,
-       unsigned int *counter, CgState *state, double *red, int inline_finalize)
+       unsigned int *counter, CgState *state, double *red, int fin_mode, PeerWin *pw)
 {
     double rz = 0.0, nn = 0.0, bb = 0.0;
     for (int64_t n = blockIdx.x * (int64_t)BLOCK + threadIdx.x; n < n_own; n += (int64_t)gridDim.x * BLOCK) {
@@ -244,11 +264,17 @@ k_init(int64_t n_own, const double *__restrict__ b, const double *__restrict__ q
         }
     }
     double v[3] = {rz, nn, bb}, out[3];
-    if (grid_reduce<3, BLOCK>(v, partials, counter, out) && threadIdx.x == 0) {
-        red[0] = out[0];
-        red[1] = out[1];
-        red[2] = out[2];
-        if (inline_finalize) finalize_init(state, out[0], out[1], out[2]);
+    if (grid_reduce<3, BLOCK>(v, partials, counter, out) && threadIdx.x == 0) finish_dot<3>(out, red, fin_mode, state, pw);
+}
+
+// peer mode: the three sums of k_init, one partial per rank -> start of the recurrence
+__global__ void k_finalize_init_peer(CgState *s, PeerWin *pw)
+{
+    double t[3];
+    const bool ok = peer_red_wait<3>(pw, t);
+    if (threadIdx.x == 0) {
+        finalize_init(s, t[0], t[1], t[2]);
+        if (!ok) peer_fail(s);
     }
 }
 
@@ -383,13 +409,13 @@ int spmv_format_prepare(fs_context *c)
 }
 
 template <unsigned long long MASK, bool WITH_DOT>
-static void launch_sell(fs_context *c, const double *x, double *y_own, const double *x_own, double *red, int single)
+static void launch_sell(fs_context *c, const double *x, double *y_own, const double *x_own, double *red, int fin_mode, PeerWin *pw)
 {
     const int64_t want = (c->sell_slices + SELL_BLOCK / 32 - 1) / (SELL_BLOCK / 32);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->sm_count * c->sell_blocks_per_sm));
     k_spmv_sell<MASK, WITH_DOT, SELL_BLOCK, SELL_MINB><<<grid, SELL_BLOCK, 0, c->stream>>>(
         (int)c->n_own, (int)c->sell_slices, c->d_sell_sptr.p, c->d_sell_adj.p, c->d_sell_vals.p, x, y_own, x_own,
-        c->d_partials.p, c->d_counter.p, c->d_state.p, red, single);
+        c->d_partials.p, c->d_counter.p, c->d_state.p, red, fin_mode, pw);
 }
 
 int solver_prepare(fs_context *c, int pc)
@@ -466,17 +492,17 @@ static int vec_grid(fs_context *c)
 
 // y_own = A x (+ partial x_own.y_own) on whichever copy of the matrix is current
 template <bool WITH_DOT>
-static void launch_spmv(fs_context *c, const double *x, double *y_own, const double *x_own, double *red, int single)
+static void launch_spmv(fs_context *c, const double *x, double *y_own, const double *x_own, double *red, int fin_mode, PeerWin *pw)
 {
     if (c->sell_active) {
-        if (c->sell_mask == SELL_MASK_XY) launch_sell<SELL_MASK_XY, WITH_DOT>(c, x, y_own, x_own, red, single);
-        else if (c->sell_mask == SELL_MASK_XZ) launch_sell<SELL_MASK_XZ, WITH_DOT>(c, x, y_own, x_own, red, single);
-        else launch_sell<SELL_MASK_YZ, WITH_DOT>(c, x, y_own, x_own, red, single);
+        if (c->sell_mask == SELL_MASK_XY) launch_sell<SELL_MASK_XY, WITH_DOT>(c, x, y_own, x_own, red, fin_mode, pw);
+        else if (c->sell_mask == SELL_MASK_XZ) launch_sell<SELL_MASK_XZ, WITH_DOT>(c, x, y_own, x_own, red, fin_mode, pw);
+        else launch_sell<SELL_MASK_YZ, WITH_DOT>(c, x, y_own, x_own, red, fin_mode, pw);
         return;
     }
     k_spmv<WITH_DOT, SPMV_BLOCK><<<spmv_grid(c), SPMV_BLOCK, 0, c->stream>>>(
         (int)c->n_own, c->d_nptr.p, c->d_nadj.p, c->d_vals.p, x, y_own, x_own, c->d_partials.p, c->d_counter.p,
-        c->d_state.p, red, single);
+        c->d_state.p, red, fin_mode, pw);
 }
 
 int spmv_once(fs_context *c, const double *d_in, double *d_out)
@@ -485,7 +511,7 @@ int spmv_once(fs_context *c, const double *d_in, double *d_out)
     if (rc) return rc;
     rc = halo_exchange(c, const_cast<double *>(d_in));
     if (rc) return rc;
-    launch_spmv<false>(c, d_in, d_out + 6 * c->own_lo, nullptr, nullptr, 0);
+    launch_spmv<false>(c, d_in, d_out + 6 * c->own_lo, nullptr, nullptr, FIN_RED, nullptr);
     FS_CUDA(c, cudaGetLastError());
     return FS_OK;
 }
@@ -493,23 +519,30 @@ int spmv_once(fs_context *c, const double *d_in, double *d_out)
 template <int PC, int NORM>
 static int enqueue_iteration(fs_context *c, double *red, int sg, int vg)
 {
-    const int single = (c->world == 1);
+    const bool single = (c->world == 1), peer = !single && c->peer_ready;
+    const int fin = single ? FIN_INLINE : (peer ? FIN_PEER : FIN_RED);
+    PeerWin *pw = peer ? c->d_pw.p : nullptr;
     const int64_t o6 = 6 * c->own_lo;
-    int rc = halo_exchange(c, c->d_p.p);
-    if (rc) return rc;
-    launch_spmv<true>(c, c->d_p.p, c->d_q.p + o6, c->d_p.p + o6, red, single);
-    if (!single) {
+    if (peer) {  // halo of p pushed into the neighbours' memory; their SpMV waits for the stamp
+        k_halo_push<<<std::max(1u, nblk(3 * c->send_total, 256)), 256, 0, c->stream>>>(
+            pw, c->send_total, c->d_send_idx.p, c->d_push_peer.p, c->d_push_dst.p, c->d_p.p, c->d_state.p, c->d_counter.p);
+    } else {
+        int rc = halo_exchange(c, c->d_p.p);
+        if (rc) return rc;
+    }
+    launch_spmv<true>(c, c->d_p.p, c->d_q.p + o6, c->d_p.p + o6, red, fin, pw);
+    if (fin == FIN_RED) {
         FS_NCCL(c, nccl().AllReduce(red, red, 1, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
         k_finalize<<<1, 1, 0, c->stream>>>(c->d_state.p, red, 1);
     }
     k_update<PC, NORM, 256><<<vg, 256, 0, c->stream>>>(c->n_own, c->d_x.p + o6, c->d_r.p + o6, c->d_p.p + o6,
                                                        c->d_q.p + o6, c->d_z.p + o6, c->d_minv.p, c->d_partials.p,
-                                                       c->d_counter.p, c->d_state.p, red + 4, single);
-    if (!single) {
+                                                       c->d_counter.p, c->d_state.p, red + 4, fin, pw);
+    if (fin == FIN_RED) {
         FS_NCCL(c, nccl().AllReduce(red + 4, red + 4, 2, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
         k_finalize<<<1, 1, 0, c->stream>>>(c->d_state.p, red + 4, 2);
     }
-    k_direction<256><<<vg, 256, 0, c->stream>>>(c->n_own, c->d_z.p + o6, c->d_p.p + o6, c->d_state.p);
+    k_direction<256><<<vg, 256, 0, c->stream>>>(c->n_own, c->d_z.p + o6, c->d_p.p + o6, c->d_state.p, pw, c->d_counter.p);
     return FS_OK;
 }
 
@@ -517,7 +550,9 @@ template <int PC, int NORM>
 static int run_pcg(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
 {
     cudaStream_t st = c->stream;
-    const int single = (c->world == 1);
+    const bool single = (c->world == 1), peer = !single && c->peer_ready;
+    const int fin = single ? FIN_INLINE : (peer ? FIN_PEER : FIN_RED);
+    PeerWin *pw = peer ? c->d_pw.p : nullptr;
     const int64_t o6 = 6 * c->own_lo;
     const int sg = spmv_grid(c), vg = vec_grid(c);
     const int maxgrid = std::max(std::max(sg, vg), c->sm_count * c->sell_blocks_per_sm);
@@ -539,15 +574,17 @@ static int run_pcg(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
     if (rc) return rc;
     k_init<PC, NORM, 256><<<vg, 256, 0, st>>>(c->n_own, c->d_b.p + o6, c->d_q.p + o6, c->d_r.p + o6, c->d_z.p + o6,
                                               c->d_p.p + o6, c->d_minv.p, c->d_partials.p, c->d_counter.p,
-                                              c->d_state.p, red + 8, single);
-    if (!single) {
+                                              c->d_state.p, red + 8, fin, pw);
+    if (fin == FIN_RED) {
         FS_NCCL(c, nccl().AllReduce(red + 8, red + 8, 3, ncclDouble, ncclSum, (ncclComm_t)c->comm, st));
         k_finalize<<<1, 1, 0, st>>>(c->d_state.p, red + 8, 0);
+    } else if (fin == FIN_PEER) {
+        k_finalize_init_peer<<<1, 32, 0, st>>>(c->d_state.p, pw);
     }
     // The iteration is captured once into a CUDA graph of GRAPH_ITERS iterations and replayed; kernels
     // past convergence (or past max_its) see done != 0 and return, so replaying whole graphs is exact.
     constexpr int GRAPH_ITERS = 8;
-    const int key = PC * 2 + NORM + (c->sell_active ? 8 * (1 + c->sell_kind) : 0);
+    const int key = PC * 2 + NORM + (c->sell_active ? 8 * (1 + c->sell_kind) : 0) + (peer ? 64 : 0);
     if (!c->cg_graph_exec || c->cg_graph_key != key || c->cg_graph_red != red) {
         if (c->cg_graph_exec) cudaGraphExecDestroy(c->cg_graph_exec);
         c->cg_graph_exec = nullptr;

@@ -69,6 +69,12 @@ enum { FS_ASM_COLORED = 0, FS_ASM_GATHER = 1 };
  * fs_export_csr returns the parity format either way. */
 enum { FS_SPMV_AUTO = 0, FS_SPMV_FULL = 1 };
 
+/* how the CG iteration exchanges data between the GPUs of one box: PEER = the kernels push halos and
+ * partial dot products straight into the other ranks' memory over NVLink (cudaIpc windows, no NCCL call
+ * in the loop); NCCL = ncclSend/Recv + ncclAllReduce per iteration; AUTO = PEER when every rank could map
+ * every other rank's window, else NCCL.  Must be set identically on all ranks before fs_set_mesh. */
+enum { FS_COMM_AUTO = 0, FS_COMM_NCCL = 1, FS_COMM_PEER = 2 };
+
 typedef struct fs_solve_opts {
     double rtol;        /* relative tolerance (reference default 1e-12 = TOLERANCE^2, fs.cpp:130-133) */
     int64_t max_its;    /* reference default 5000 */
@@ -100,6 +106,11 @@ void *fs_get_stream(fs_context *ctx);
  * communicator libMesh/PETSc use (fs.cpp:28,35). */
 int fs_dist_unique_id(uint8_t id_out[128]);
 int fs_dist_init(fs_context *ctx, int rank, int world, const uint8_t nccl_unique_id[128]);
+int fs_set_comm_mode(fs_context *ctx, int mode);
+/* FS_COMM_NCCL or FS_COMM_PEER: what the iteration of the current mesh uses (single rank: FS_COMM_NCCL) */
+int fs_get_comm_mode(fs_context *ctx, int *mode);
+
+/* NOTE multi-rank: fs_set_mesh and fs_destroy are collective (every rank of the communicator calls them). */
 
 /* ---- inputs ------------------------------------------------------------ */
 /* replaces the globals nu, em, thickness + initMaterialMatrices (fs.cpp:273-294) */
