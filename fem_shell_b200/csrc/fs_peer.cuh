@@ -6,9 +6,11 @@
 //   * the halo of p is PUSHED by its owner straight into the neighbours' halo segments of p (k_halo_push,
 //     remote 128-bit stores) and stamped; the neighbour's SpMV waits for the stamp at its first instruction;
 //   * a dot product is finished by the producing kernel: its last block stores the rank's partial sums into
-//     every rank's mailbox and stamps them; the consuming kernel (k_update for p.Ap, k_direction for r.z and
-//     the norm) waits for all stamps and adds the partials in rank order -- every rank gets bit-identical
-//     alpha/beta, deterministic, no reduction kernel, no NCCL launch in the loop.
+//     every rank's mailbox; the consuming kernel (k_update for p.Ap, k_direction for r.z and the norm) waits
+//     for all of them and adds the partials in rank order -- every rank gets bit-identical alpha/beta,
+//     deterministic, no reduction kernel, no NCCL launch in the loop.  The partials travel as self-certifying
+//     8-byte words {32 bits of the double | 32-bit stamp} (the "LL" trick of NCCL's low-latency protocol): an
+//     8-byte store is single-copy atomic, so no fence and no separate flag are needed.
 // Stamps are monotonic per rank; slots are double-buffered by stamp parity (a rank cannot run two
 // reductions ahead of a peer, because the next reduction needs the peer's contribution to this one).
 // A wait that exceeds spin_limit cycles marks the solve as FS_ERR_COMM instead of hanging the GPU.
@@ -18,10 +20,9 @@
 namespace fs {
 
 constexpr int PEER_MAX = 8;                       // ranks of one NVSwitch box
-constexpr int MBOX_RED_SEQ = 0;                   // [2][PEER_MAX] stamps
-constexpr int MBOX_RED_VAL = 2 * PEER_MAX;        // [2][PEER_MAX][4] doubles
-constexpr int MBOX_HALO = MBOX_RED_VAL + 2 * PEER_MAX * 4;  // [PEER_MAX] stamps
-constexpr int MBOX_WORDS = 128;                   // 1 KB header in front of p
+constexpr int MBOX_RED = 0;                       // [2 parities][PEER_MAX ranks][4 values][2 words] LL words
+constexpr int MBOX_HALO = 2 * PEER_MAX * 8;       // [PEER_MAX] halo stamps
+constexpr int MBOX_WORDS = 256;                   // 2 KB header in front of p
 
 struct PeerWin {
     int rank, world;
@@ -67,50 +68,73 @@ __device__ __forceinline__ bool peer_spin(const unsigned long long *flag, unsign
     return true;
 }
 
-// one thread: this rank's NV partial sums -> every rank's mailbox, then the stamps
+__device__ __forceinline__ void st_relaxed_sys_v2(unsigned long long *p, unsigned long long a, unsigned long long b)
+{
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void ld_relaxed_sys_v2(const unsigned long long *p, unsigned long long &a, unsigned long long &b)
+{
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+
+// one thread: this rank's NV partial sums -> every rank's mailbox as LL words
 template <int NV>
 __device__ __forceinline__ void peer_red_push(PeerWin *pw, const double (&v)[NV])
 {
     const unsigned long long stamp = pw->seq_red + 1;
+    const unsigned long long tag = (stamp & 0xffffffffull) << 32;
     const int par = (int)(stamp & 1), me = pw->rank;
-    for (int r = 0; r < pw->world; r++) {
-        double *val = reinterpret_cast<double *>(pw->mbox[r] + MBOX_RED_VAL) + (par * PEER_MAX + me) * 4;
+    unsigned long long w[NV][2];
 #pragma unroll
-        for (int k = 0; k < NV; k++) st_volatile_f64(val + k, v[k]);
+    for (int k = 0; k < NV; k++) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(v[k]);
+        w[k][0] = (bits & 0xffffffffull) | tag;
+        w[k][1] = (bits >> 32) | tag;
     }
-    __threadfence_system();
-    for (int r = 0; r < pw->world; r++) st_release_sys(pw->mbox[r] + MBOX_RED_SEQ + par * PEER_MAX + me, stamp);
+    for (int r = 0; r < pw->world; r++) {
+        unsigned long long *slot = pw->mbox[r] + MBOX_RED + ((par * PEER_MAX + me) * 4) * 2;
+#pragma unroll
+        for (int k = 0; k < NV; k++) st_relaxed_sys_v2(slot + 2 * k, w[k][0], w[k][1]);
+    }
     pw->seq_red = stamp;
 }
 
 // whole block: wait for every rank's contribution to the reduction this rank produced last, add in rank
-// order.  Returns false on timeout (state marked FS_ERR_COMM by the caller).
+// order.  Lane (r, k) of warp 0 polls value k of rank r, so the wait costs one round trip, not `world`.
+// Returns false on timeout (state marked FS_ERR_COMM by the caller).
 template <int NV>
 __device__ __forceinline__ bool peer_red_wait(PeerWin *pw, double (&out)[NV])
 {
-    __shared__ double s_sum[4];
-    __shared__ int s_ok;
-    if (threadIdx.x == 0) {
+    __shared__ double s_val[PEER_MAX * 4];
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    const int world = pw->world;
+    if (threadIdx.x < world * NV) {
+        const int r = threadIdx.x / NV, k = threadIdx.x - NV * r;
         const unsigned long long stamp = *reinterpret_cast<volatile unsigned long long *>(&pw->seq_red);
-        const int par = (int)(stamp & 1);
-        const unsigned long long *mb = pw->mbox[pw->rank];
-        bool ok = true;
-        for (int r = 0; r < pw->world && ok; r++) ok = peer_spin(mb + MBOX_RED_SEQ + par * PEER_MAX + r, stamp, pw->spin_limit);
-        double acc[NV];
-#pragma unroll
-        for (int k = 0; k < NV; k++) acc[k] = 0.0;
-        const double *val = reinterpret_cast<const double *>(mb + MBOX_RED_VAL) + par * PEER_MAX * 4;
-        for (int r = 0; r < pw->world; r++)
-#pragma unroll
-            for (int k = 0; k < NV; k++) acc[k] += ld_volatile_f64(val + 4 * r + k);
-#pragma unroll
-        for (int k = 0; k < NV; k++) s_sum[k] = acc[k];
-        s_ok = ok ? 1 : 0;
+        const unsigned long long tag = stamp & 0xffffffffull;
+        const unsigned long long *slot = pw->mbox[pw->rank] + MBOX_RED + (((int)(stamp & 1) * PEER_MAX + r) * 4 + k) * 2;
+        unsigned long long a, b;
+        ld_relaxed_sys_v2(slot, a, b);
+        if ((a >> 32) != tag || (b >> 32) != tag) {
+            const long long t0 = clock64();
+            for (;;) {
+                ld_relaxed_sys_v2(slot, a, b);
+                if ((a >> 32) == tag && (b >> 32) == tag) break;
+                if (clock64() - t0 > pw->spin_limit) { s_bad = 1; break; }
+            }
+        }
+        s_val[4 * r + k] = __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < NV; k++) out[k] = s_sum[k];
-    const bool ok = s_ok != 0;
+    for (int k = 0; k < NV; k++) {
+        double acc = 0.0;
+        for (int r = 0; r < world; r++) acc += s_val[4 * r + k];
+        out[k] = acc;
+    }
+    const bool ok = s_bad == 0;
     __syncthreads();
     return ok;
 }
