@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(HERE, "libfemshell_b200.so")
 
 TRI3, QUAD4 = 3, 5
 DOF_FIRST_ENCOUNTER, DOF_NODE_ID = 0, 1
-PC_NONE, PC_JACOBI, PC_BJACOBI6 = 0, 1, 2
+PC_NONE, PC_JACOBI, PC_BJACOBI6, PC_MLRBM = 0, 1, 2, 3
 NORM_UNPRECONDITIONED, NORM_PRECONDITIONED = 0, 1
 QUIRKS_REFERENCE = 3
 COMM_AUTO, COMM_NCCL, COMM_PEER = 0, 1, 2   # how the CG iteration talks between GPUs (fs_peer.cuh)
@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = [
     "fs_set_nodal_loads", "fs_set_interface_loads", "fs_build_rhs", "fs_assemble", "fs_solve",
     "fs_get_solution", "fs_solve_host", "fs_interface_nodes", "fs_step", "fs_commit_step", "fs_get_sizes",
     "fs_export_dof_order", "fs_export_csr", "fs_export_rhs", "fs_debug_element_matrices", "fs_spmv_host",
-    "fs_bench_spmv", "fs_bench_fp64_peak", "fs_partition_plan", "fs_meshgen", "fs_read_xda", "fs_read_forces", "fs_write_xda",
+    "fs_bench_spmv", "fs_bench_fp64_peak", "fs_set_ml_options", "fs_get_ml_info", "fs_debug_ml_level", "fs_apply_mlrbm_host", "fs_partition_plan", "fs_meshgen", "fs_read_xda", "fs_read_forces", "fs_write_xda",
 ]
 
 
@@ -345,6 +345,32 @@ class FemShell:
         y = np.empty_like(x)
         self._ck(self.lib.fs_spmv_host(self.ctx, _p(x), _p(y)))
         return y
+
+    def set_ml_options(self, max_points=1 << 22, dense_points=200, gamma=2):
+        self._ck(self.lib.fs_set_ml_options(self.ctx, C.c_int64(max_points), C.c_int(dense_points), C.c_int(gamma)))
+
+    def ml_info(self):
+        lv = C.c_int64(0)
+        cells = (C.c_int64 * 42)()
+        w = (C.c_double * 15)()
+        ms = C.c_double(0.0)
+        self._ck(self.lib.fs_get_ml_info(self.ctx, C.byref(lv), cells, w, C.byref(ms)))
+        n = int(lv.value)
+        return {"levels": n, "cells": [tuple(int(cells[3 * l + d]) for d in range(3)) for l in range(n)],
+                "lambda": [float(w[i]) for i in range(n + 1)], "setup_ms": float(ms.value)}
+
+    def ml_level(self, level, what):
+        n = C.c_int64(0)
+        self._ck(self.lib.fs_debug_ml_level(self.ctx, C.c_int(level), C.c_int(what), None, C.c_int64(0), C.byref(n)))
+        out = np.empty(n.value)
+        self._ck(self.lib.fs_debug_ml_level(self.ctx, C.c_int(level), C.c_int(what), _p(out), C.c_int64(out.size), C.byref(n)))
+        return out
+
+    def apply_mlrbm(self, r):
+        r = _f64(r).ravel()
+        z = np.empty_like(r)
+        self._ck(self.lib.fs_apply_mlrbm_host(self.ctx, _p(r), _p(z)))
+        return z
 
     def bench_fp64_peak(self) -> float:
         t = C.c_double()

@@ -211,6 +211,7 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
     c->pattern_ready = c->assembled = c->loads_set = c->rhs_ready = c->have_solution = false;
     c->gather_ready = c->gather_unavailable = false;
     c->sell_checked = c->sell_active = c->sell_layout_ready = false;
+    c->ml_geom_ready = c->ml_values_ready = false;
     if (c->cg_graph_exec) { cudaGraphExecDestroy(c->cg_graph_exec); c->cg_graph_exec = nullptr; }
 
     // ---- DOF order (a12) ----
@@ -219,6 +220,32 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
     c->node_of_dof.assign(n_g, -1);
     for (int64_t i = 0; i < n_nodes; i++)
         if (c->dofnode[i] >= 0) c->node_of_dof[c->dofnode[i]] = (int32_t)i;
+
+    // bounding box of the nodes that carry DOFs (lattice of the multilevel preconditioner, fs_mlpc.cuh)
+    {
+        bool first = true;
+        for (int64_t i = 0; i < n_nodes; i++) {
+            if (c->dofnode[i] < 0) continue;
+            for (int d = 0; d < 3; d++) {
+                const double v = xyz[3 * i + d];
+                if (first || v < c->bbox_lo[d]) c->bbox_lo[d] = v;
+                if (first || v > c->bbox_hi[d]) c->bbox_hi[d] = v;
+            }
+            first = false;
+        }
+        // largest element extent per axis: the cells of the first lattice are three of these wide
+        for (int d = 0; d < 3; d++) c->ml_h[d] = 0.0;
+        for (int64_t e = 0; e < n_elem; e++)
+            for (int d = 0; d < 3; d++) {
+                double lo = xyz[3 * (int64_t)enodes[eptr[e]] + d], hi = lo;
+                for (int64_t k = eptr[e] + 1; k < eptr[e + 1]; k++) {
+                    const double v = xyz[3 * (int64_t)enodes[k] + d];
+                    lo = std::min(lo, v);
+                    hi = std::max(hi, v);
+                }
+                c->ml_h[d] = std::max(c->ml_h[d], hi - lo);
+            }
+    }
 
     // ---- Dirichlet bits (fs.cpp:90-120) and coupling interface (fsp.cpp:55-71) ----
     c->node_mask.assign(n_nodes, 0);
@@ -598,14 +625,71 @@ int fs_bench_spmv(fs_context *c, int reps, fs_solve_info *info)
     FS_CHECK_CTX(c);
     if (!c->assembled || reps <= 0 || !info) return fail(c, FS_ERR_STATE, "not assembled / bad reps");
     FS_CUDA(c, cudaSetDevice(c->device));
-    FS_TRY(spmv_once(c, c->d_b.p, c->d_q.p));  // warm-up
-    FS_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-    for (int i = 0; i < reps; i++) FS_TRY(spmv_once(c, c->d_b.p, c->d_q.p));
-    FS_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    return spmv_kernel_time(c, reps, &info->spmv_ms);
+}
+
+int fs_set_ml_options(fs_context *c, int64_t max_points, int dense_points, int gamma)
+{
+    FS_CHECK_CTX(c);
+    if (max_points < 1 || dense_points < 1 || dense_points > fs::ML_DENSE_MAX_POINTS || gamma < 1 || gamma > 3)
+        return fail(c, FS_ERR_ARG, "multilevel options out of range");
+    if (max_points != c->ml_max_points || dense_points != c->ml_dense_points || gamma != c->ml_gamma) {
+        c->ml_max_points = max_points;
+        c->ml_dense_points = dense_points;
+        c->ml_gamma = gamma;
+        c->ml_geom_ready = c->ml_values_ready = false;
+        if (c->cg_graph_exec) { cudaGraphExecDestroy(c->cg_graph_exec); c->cg_graph_exec = nullptr; }
+    }
+    return FS_OK;
+}
+
+int fs_get_ml_info(fs_context *c, int64_t *levels, int64_t *cells, double *weights, double *setup_ms)
+{
+    FS_CHECK_CTX(c);
+    if (!levels) return fail(c, FS_ERR_ARG, "null levels");
+    *levels = c->ml_geom_ready ? c->ml.n_lat : 0;
+    for (int l = 0; l < (c->ml_geom_ready ? c->ml.n_lat : 0); l++) {
+        if (cells)
+            for (int d = 0; d < 3; d++) cells[3 * l + d] = c->ml.lat[l].g.np[d];
+        if (weights) weights[l + 1] = c->ml.lat[l].lambda;
+    }
+    if (weights) weights[0] = c->ml.lambda0;
+    if (setup_ms) *setup_ms = c->ml_values_ready ? c->ml.setup_ms : 0.0;
+    return FS_OK;
+}
+
+int fs_debug_ml_level(fs_context *c, int level, int what, double *out, int64_t capacity, int64_t *count)
+{
+    FS_CHECK_CTX(c);
+    if (!c->ml_values_ready) return fail(c, FS_ERR_STATE, "multilevel preconditioner not set up");
+    if (level < 0 || level >= c->ml.n_lat || !count) return fail(c, FS_ERR_ARG, "bad level");
+    fs::MlLevelBuf &L = c->ml.lat[level];
+    const int64_t n6 = 6 * (int64_t)L.g.n;
+    const double *src = nullptr;
+    int64_t n = 0;
+    if (what == 0) { src = L.A.p; n = (int64_t)L.g.ns * 6 * n6; }
+    else if (what == 1) { src = L.dinv.p; n = 6 * n6; }
+    else if (what == 2 && L.dense) { src = L.minv.p; n = n6 * n6; }
+    else return fail(c, FS_ERR_ARG, "nothing of that kind on this level");
+    *count = n;
+    if (!out) return FS_OK;
+    if (capacity < n) return fail(c, FS_ERR_ARG, "buffer too small");
+    FS_CUDA(c, cudaSetDevice(c->device));
+    FS_CUDA(c, cudaMemcpy(out, src, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return FS_OK;
+}
+
+int fs_apply_mlrbm_host(fs_context *c, const double *r, double *z)
+{
+    FS_CHECK_CTX(c);
+    if (!c->assembled) return fail(c, FS_ERR_STATE, "not assembled");
+    if (c->world != 1) return fail(c, FS_ERR_STATE, "single-rank only");
+    if (!r || !z) return fail(c, FS_ERR_ARG, "null vector");
+    FS_CUDA(c, cudaSetDevice(c->device));
+    FS_CUDA(c, cudaMemcpyAsync(c->d_r.p, r, sizeof(double) * 6 * c->n_own, cudaMemcpyHostToDevice, c->stream));
+    FS_TRY(pc_apply_mlrbm_once(c));
+    FS_CUDA(c, cudaMemcpyAsync(z, c->d_z.p, sizeof(double) * 6 * c->n_own, cudaMemcpyDeviceToHost, c->stream));
     FS_CUDA(c, cudaStreamSynchronize(c->stream));
-    float ms = 0.f;
-    FS_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    info->spmv_ms = ms / reps;
     return FS_OK;
 }
 

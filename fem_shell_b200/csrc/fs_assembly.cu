@@ -708,6 +708,7 @@ int assemble_values(fs_context *c, float *ms)
         if (ms) FS_CUDA(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
         c->assembled = true;
         c->minv_kind = -1;
+        c->ml_values_ready = false;
         c->sell_checked = false;
         return FS_OK;
     }
@@ -729,6 +730,7 @@ int assemble_values(fs_context *c, float *ms)
     if (ms) FS_CUDA(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
     c->assembled = true;
     c->minv_kind = -1;
+    c->ml_values_ready = false;
     c->sell_checked = false;
     return FS_OK;
 }

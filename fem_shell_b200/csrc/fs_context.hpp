@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/femshell_b200.h"
+#include "fs_mlpc.cuh"
 
 struct ncclComm;
 namespace fs { struct PeerWin; }
@@ -77,6 +78,28 @@ struct Peer {
     int64_t recv_count = 0;   // nodes
     int64_t send_off = 0;     // offset (nodes) into the packed send buffer / send index list
     int64_t recv_off = 0;     // offset (nodes) into the halo segment of the local vector
+};
+
+// one lattice level of the multilevel preconditioner (fs_mlpc.cuh)
+struct MlLevelBuf {
+    LatGeom g;
+    bool dense = false;          // coarsest level: minv holds the dense pseudo-inverse
+    DevBuf<double> A;            // ns * 36 * n stencil values (structure of arrays, fs_mlpc.cu)
+    DevBuf<double> dinv;         // 36 * n pseudo-inverses of the diagonal blocks
+    DevBuf<double> minv;         // (6n)^2, dense level only
+    DevBuf<double> x, xb, b, r, t;  // 6n each
+    double omega = 0.0, lambda = 0.0;
+};
+
+struct MlHier {
+    int n_lat = 0;
+    MlLevelBuf lat[ML_MAX_LEVELS];
+    DevBuf<int32_t> d_agg;       // n_local: cell of the first lattice holding each local node
+    DevBuf<int32_t> d_sup_ptr, d_sup_node;  // cell -> owned nodes (owned-relative ids)
+    DevBuf<double> d_r1, d_t;    // 6 * n_local work vectors of the mesh level
+    DevBuf<double> d_scalar;
+    double omega0 = 0.0, lambda0 = 0.0;
+    float setup_ms = 0.f;
 };
 
 }  // namespace fs
@@ -167,6 +190,15 @@ struct fs_context {
     fs::DevBuf<double> d_b, d_x, d_r, d_p, d_q, d_z;
     fs::DevBuf<double> d_minv;             // 6*n_own (Jacobi) or 36*n_own (block)
     int minv_kind = -1;
+
+    // multilevel rigid-body-mode preconditioner (fs_mlpc.cuh / fs_mlpc.cu)
+    double bbox_lo[3] = {0, 0, 0}, bbox_hi[3] = {0, 0, 0};  // of all mesh nodes (identical on every rank)
+    double ml_h[3] = {0, 0, 0};            // largest element extent per axis (identical on every rank)
+    int64_t ml_max_points = 1 << 22;       // cap on the cells of the first lattice
+    int ml_dense_points = fs::ML_DENSE_MAX_POINTS;  // a lattice with at most this many cells is solved densely
+    int ml_gamma = 2;                      // cycle index on the lattice levels (1 = V, 2 = W)
+    bool ml_geom_ready = false, ml_values_ready = false;
+    fs::MlHier ml;
     fs::DevBuf<double> d_partials;         // per-block partial sums
     fs::DevBuf<fs::CgState> d_state;
     fs::DevBuf<unsigned int> d_counter;
@@ -216,9 +248,17 @@ int debug_element_matrices(fs_context *c, double *out_host);
 int solver_query_occupancy(fs_context *c);
 int solver_prepare(fs_context *c, int pc);
 int solver_run(fs_context *c, const fs_solve_opts *o, fs_solve_info *info);
-int spmv_once(fs_context *c, const double *d_in, double *d_out);
+int spmv_once(fs_context *c, const double *d_in, double *d_out, bool check_done = false);   // halo exchange + SpMV
+int spmv_local(fs_context *c, const double *d_in, double *d_out, bool check_done = false);  // SpMV only (halo already valid)
 int halo_exchange(fs_context *c, double *d_vec);
 int spmv_format_prepare(fs_context *c);
+int pc_apply_mlrbm_once(fs_context *c);
+int spmv_kernel_time(fs_context *c, int reps, float *ms_per_launch);
+
+// mlpc.cu
+int ml_prepare(fs_context *c);
+int ml_enqueue_apply(fs_context *c, bool init, double *red, int fin, int vec_grid);
+int ml_ensure_partials(fs_context *c);
 
 // peer.cu
 int peer_window_setup(fs_context *c);     // collective; call after the vectors are sized

@@ -1,0 +1,913 @@
+// fs_mlpc.cu -- multilevel rigid-body-mode preconditioner (FS_PC_MLRBM): lattice hierarchy, the kernels of
+// one cycle, and the set-up of the coarse stencils by probing with the cycle's own transfer kernels.
+// What it is and why it exists: fs_mlpc.cuh.
+//
+// One application z = M^-1 r (all on the context stream, fixed summation order, no atomics):
+//   mesh level      k_f_smooth0       x = w D^-1 r
+//                   SpMV, k_f_resid   r1 = r - A x ; t = D^-1 r1
+//                   SpMV, k_f_restrict  b_1 = P_t^T (r1 - w A t)          (8 lanes per aggregate)
+//                   [ncclAllReduce of b_1 when there are several ranks]
+//   lattice level   k_lat_smooth0, then gamma times { k_lat_stencil<RESID>, <RSMOOTH>, k_lat_restrict,
+//                   recurse, k_lat_prolong_t, k_lat_stencil<PADD> }, k_lat_stencil<POST>
+//   coarsest        k_dense_matvec with the pseudo-inverse
+//   mesh level      k_f_prolong_t, SpMV, k_f_prolong_add   x += t - w D^-1 A t,  t = P_t e_1
+//                   SpMV, k_f_post_finish   z = x + w D^-1 (r - A x); partial r.z; advances the CG recurrence
+#include <algorithm>
+#include <cmath>
+
+#include "fs_cg_device.cuh"
+#include "fs_context.hpp"
+#include "fs_mlpc.cuh"
+#include "fs_nccl.hpp"
+
+namespace fs {
+
+static inline unsigned int nblk(int64_t n, int bs) { return (unsigned int)std::max<int64_t>(1, (n + bs - 1) / bs); }
+
+#define FS_NCCL_ML(ctx, call)                                                                  \
+    do {                                                                                       \
+        ncclResult_t r__ = (call);                                                             \
+        if (r__ != ncclSuccess)                                                                \
+            return fs::fail(ctx, FS_ERR_COMM, std::string(#call) + ": " + fs::nccl().GetErrorString(r__)); \
+    } while (0)
+
+// nodal values (u, theta) of the rigid-body mode e = (t, w) about a centre at distance rho: u = t + w x rho
+__device__ __forceinline__ void rbm_apply(const double rho[3], const double e[6], double v[6])
+{
+    v[0] = e[0] + e[4] * rho[2] - e[5] * rho[1];
+    v[1] = e[1] + e[5] * rho[0] - e[3] * rho[2];
+    v[2] = e[2] + e[3] * rho[1] - e[4] * rho[0];
+    v[3] = e[3];
+    v[4] = e[4];
+    v[5] = e[5];
+}
+
+// transpose: y += B^T s
+__device__ __forceinline__ void rbm_apply_t(const double rho[3], const double s[6], double y[6])
+{
+    y[0] += s[0];
+    y[1] += s[1];
+    y[2] += s[2];
+    y[3] += s[3] + rho[1] * s[2] - rho[2] * s[1];
+    y[4] += s[4] + rho[2] * s[0] - rho[0] * s[2];
+    y[5] += s[5] + rho[0] * s[1] - rho[1] * s[0];
+}
+
+#define ML_RETURN_IF_DONE(state, chk) \
+    if ((chk) && (state)->done) return
+
+// ---------------------------------------------------------------------------------------------
+// mesh level (thread = one DOF of an owned node unless noted; dinv = 6x6 block inverses, row-major)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double dinv_row(const double *__restrict__ dinv, int64_t t, const double *__restrict__ v6)
+{
+    // row (t % 6) of block (t / 6) times the node's six values
+    const double2 *d = reinterpret_cast<const double2 *>(dinv + 6 * t);
+    const double2 *v = reinterpret_cast<const double2 *>(v6);
+    double s = 0.0;
+#pragma unroll
+    for (int h = 0; h < 3; h++) {
+        const double2 a = d[h], b = v[h];
+        s += a.x * b.x + a.y * b.y;
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(256)
+k_f_smooth0(int64_t n6, const double *__restrict__ b, const double *__restrict__ dinv, double omega, double *__restrict__ x,
+            const CgState *state, int chk)
+{
+    ML_RETURN_IF_DONE(state, chk);
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n6) return;
+    x[t] = omega * dinv_row(dinv, t, b + 6 * (t / 6));
+}
+
+// r1 = b - q (b may be null: zero) ; t = D^-1 r1
+__global__ void __launch_bounds__(192)
+k_f_resid(int64_t n6, const double *__restrict__ b, const double *__restrict__ q, const double *__restrict__ dinv,
+          double *__restrict__ r1, double *__restrict__ tv, const CgState *state, int chk)
+{
+    ML_RETURN_IF_DONE(state, chk);
+    __shared__ __align__(16) double sh[192];
+    const int64_t t = blockIdx.x * (int64_t)192 + threadIdx.x;
+    const bool valid = t < n6;
+    double rr = 0.0;
+    if (valid) {
+        rr = (b ? b[t] : 0.0) - q[t];
+        r1[t] = rr;
+    }
+    sh[threadIdx.x] = rr;
+    __syncthreads();
+    if (valid) tv[t] = dinv_row(dinv, t, sh + (threadIdx.x / 6) * 6);
+}
+
+// b_1[a] = sum over the owned nodes i of aggregate a of B_i^T (r1_i - w q_i); eight lanes per aggregate
+__global__ void __launch_bounds__(256)
+k_f_restrict(const __grid_constant__ LatGeom g, const int32_t *__restrict__ sup_ptr, const int32_t *__restrict__ sup_node,
+             const double *__restrict__ xyz_own, const uint8_t *__restrict__ mask_own, const double *__restrict__ r1,
+             const double *__restrict__ q, double omega, double *__restrict__ y, const CgState *state, int chk)
+{
+    ML_RETURN_IF_DONE(state, chk);
+    const int a = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3), sub = threadIdx.x & 7;
+    const bool valid = a < g.n;  // whole groups of eight share `a`; shuffles below stay inside the group
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    if (valid) {
+        int k[3];
+        double ca[3];
+        lat_unindex(g, a, k);
+        lat_centre(g, k, ca);
+        const int e1 = sup_ptr[a + 1];
+        for (int e = sup_ptr[a] + sub; e < e1; e += 8) {
+            const int p = sup_node[e];
+            const double rho[3] = {xyz_own[3 * (size_t)p] - ca[0], xyz_own[3 * (size_t)p + 1] - ca[1], xyz_own[3 * (size_t)p + 2] - ca[2]};
+            double rv[6], qv[6];
+            load6(r1 + 6 * (size_t)p, rv);
+            load6(q + 6 * (size_t)p, qv);
+            const unsigned m = mask_own[p];
+#pragma unroll
+            for (int c = 0; c < 6; c++) rv[c] = ((m >> c) & 1u) ? 0.0 : rv[c] - omega * qv[c];
+            rbm_apply_t(rho, rv, acc);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 4);
+        acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
+        acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
+    }
+    if (valid && sub == 0) store6(y + 6 * (size_t)a, acc);
+}
+
+// t_i = B_i e[aggregate of i] for every LOCAL node (owned and halo: e is replicated, so no exchange is needed)
+__global__ void __launch_bounds__(256)
+k_f_prolong_t(const __grid_constant__ LatGeom g, int64_t n_local, const int32_t *__restrict__ agg, const double *__restrict__ xyz,
+              const uint8_t *__restrict__ mask, const double *__restrict__ e, double *__restrict__ tv, const CgState *state, int chk)
+{
+    ML_RETURN_IF_DONE(state, chk);
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_local) return;
+    const int a = agg[i];
+    int k[3];
+    double ca[3], ev[6], v[6];
+    lat_unindex(g, a, k);
+    lat_centre(g, k, ca);
+    const double rho[3] = {xyz[3 * i] - ca[0], xyz[3 * i + 1] - ca[1], xyz[3 * i + 2] - ca[2]};
+    load6(e + 6 * (size_t)a, ev);
+    rbm_apply(rho, ev, v);
+    const unsigned m = mask[i];
+#pragma unroll
+    for (int c = 0; c < 6; c++)
+        if ((m >> c) & 1u) v[c] = 0.0;
+    store6(tv + 6 * i, v);
+}
+
+// x (+)= t - w D^-1 q
+__global__ void __launch_bounds__(256)
+k_f_prolong_add(int64_t n6, const double *__restrict__ tv, const double *__restrict__ q, const double *__restrict__ dinv,
+                double omega, double *__restrict__ x, int accumulate, const CgState *state, int chk)
+{
+    ML_RETURN_IF_DONE(state, chk);
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n6) return;
+    const double v = tv[t] - omega * dinv_row(dinv, t, q + 6 * (t / 6));
+    x[t] = accumulate ? x[t] + v : v;
+}
+
+// z = x + w D^-1 (b - q) ; partial b.z ; (INIT: p = z).  The block finishing the reduction advances the CG
+// recurrence: red[0] = r.z, red[1] = the norm left there by k_update_xr / k_init_r (red[2] = ||b||^2 at INIT).
+// WITH_DOT = false: plain post-smoothing step (tests, set-up).
+template <bool INIT, bool WITH_DOT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_f_post_finish(int64_t n6, const double *__restrict__ b, const double *__restrict__ q, const double *__restrict__ dinv,
+                double omega, double *__restrict__ z, double *__restrict__ p, double *partials, unsigned int *counter,
+                CgState *state, double *red, int fin_mode, int chk)
+{
+    ML_RETURN_IF_DONE(state, chk);
+    __shared__ __align__(16) double sh[BLOCK];
+    static_assert(BLOCK % 6 == 0, "whole nodes per block");
+    double rz = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * BLOCK;
+    const int64_t rounds = (n6 + stride - 1) / stride;
+    for (int64_t it = 0; it < rounds; it++) {
+        const int64_t t = it * stride + blockIdx.x * (int64_t)BLOCK + threadIdx.x;
+        const bool valid = t < n6;
+        const double bv = valid ? b[t] : 0.0;
+        __syncthreads();
+        sh[threadIdx.x] = valid ? bv - q[t] : 0.0;
+        __syncthreads();
+        if (valid) {
+            const double zv = z[t] + omega * dinv_row(dinv, t, sh + (threadIdx.x / 6) * 6);
+            z[t] = zv;
+            if (INIT) p[t] = zv;
+            rz += bv * zv;
+        }
+    }
+    if (!WITH_DOT) return;
+    double v[1] = {rz}, out[1];
+    if (grid_reduce<1, BLOCK>(v, partials, counter, out) && threadIdx.x == 0) {
+        red[0] = out[0];
+        if (fin_mode == FIN_INLINE) {
+            if (INIT) finalize_init(state, out[0], red[1], red[2]);
+            else finalize_update(state, out[0], red[1]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// lattice levels.  Stencil storage: A[(s*6 + b) * 6n + 6p + a] = entry (a, b) of the block coupling cell p to
+// its neighbour in slot s (structure of arrays: thread 6p+a streams its 6*ns values with unit stride).
+// ---------------------------------------------------------------------------------------------
+enum { LAT_RESID = 0, LAT_RSMOOTH = 1, LAT_PADD = 2, LAT_POST = 3 };
+
+// v = A in, then
+//   RESID    out1 = aux - v (aux null: zero)   out2 = D^+ out1
+//   RSMOOTH  out1 = aux - w v                  (out1 may alias aux)
+//   PADD     out1 (+)= in - w D^+ v            (flag: accumulate)
+//   POST     out1 = in + w D^+ (aux - v)       (out1 must not alias in)
+template <int MODE>
+__global__ void __launch_bounds__(192)
+k_lat_stencil(const __grid_constant__ LatGeom g, const double *__restrict__ A, const double *__restrict__ dinv,
+              const double *__restrict__ in, const double *aux, double *out1, double *__restrict__ out2, double omega,
+              int flag, const CgState *state, int chk)
+{
+    ML_RETURN_IF_DONE(state, chk);
+    __shared__ __align__(16) double sh[192];
+    const int64_t n6 = 6 * (int64_t)g.n;
+    const int64_t t = blockIdx.x * (int64_t)192 + threadIdx.x;
+    const bool valid = t < n6;
+    double v = 0.0;
+    if (valid) {
+        const int p = (int)(t / 6);
+        int k[3];
+        lat_unindex(g, p, k);
+        for (int s = 0; s < g.ns; s++) {
+            int o[3];
+            lat_stencil_off(g, s, o);
+            const int kk[3] = {k[0] + o[0], k[1] + o[1], k[2] + o[2]};
+            if (kk[0] < 0 || kk[0] >= g.np[0] || kk[1] < 0 || kk[1] >= g.np[1] || kk[2] < 0 || kk[2] >= g.np[2]) continue;
+            const double *xin = in + 6 * (size_t)lat_index(g, kk);
+            const double *as = A + (size_t)(6 * s) * n6 + t;
+#pragma unroll
+            for (int b = 0; b < 6; b++) v += as[(size_t)b * n6] * xin[b];
+        }
+    }
+    if (MODE == LAT_RSMOOTH) {
+        if (valid) out1[t] = aux[t] - omega * v;
+        return;
+    }
+    double w = v;                                        // what D^+ is applied to
+    if (MODE == LAT_RESID || MODE == LAT_POST) w = valid ? (aux ? aux[t] : 0.0) - v : 0.0;
+    sh[threadIdx.x] = w;
+    __syncthreads();
+    if (!valid) return;
+    const double dw = dinv_row(dinv, t, sh + (threadIdx.x / 6) * 6);
+    if (MODE == LAT_RESID) {
+        out1[t] = w;
+        out2[t] = dw;
+    } else if (MODE == LAT_PADD) {
+        const double add = in[t] - omega * dw;
+        out1[t] = flag ? out1[t] + add : add;
+    } else {
+        out1[t] = in[t] + omega * dw;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_lat_smooth0(int64_t n6, const double *__restrict__ b, const double *__restrict__ dinv, double omega, double *__restrict__ x,
+              const CgState *state, int chk)
+{
+    ML_RETURN_IF_DONE(state, chk);
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n6) return;
+    x[t] = omega * dinv_row(dinv, t, b + 6 * (t / 6));
+}
+
+// parent cell K gathers its (up to 3^d) children: y[K] = sum B_c^T s_c, B_c = rigid-body modes of K at the child centre
+__global__ void __launch_bounds__(128)
+k_lat_restrict(const __grid_constant__ LatGeom gc, const __grid_constant__ LatGeom gp, const double *__restrict__ s,
+               double *__restrict__ y, const CgState *state, int chk)
+{
+    ML_RETURN_IF_DONE(state, chk);
+    const int K = blockIdx.x * blockDim.x + threadIdx.x;
+    if (K >= gp.n) return;
+    int kp[3];
+    double cp[3], acc[6] = {0, 0, 0, 0, 0, 0};
+    lat_unindex(gp, K, kp);
+    lat_centre(gp, kp, cp);
+    const int n0 = gc.active[0] ? 3 : 1, n1 = gc.active[1] ? 3 : 1, n2 = gc.active[2] ? 3 : 1;
+    for (int i2 = 0; i2 < n2; i2++)
+        for (int i1 = 0; i1 < n1; i1++)
+            for (int i0 = 0; i0 < n0; i0++) {
+                const int kc[3] = {gc.active[0] ? 3 * kp[0] + i0 : 0, gc.active[1] ? 3 * kp[1] + i1 : 0, gc.active[2] ? 3 * kp[2] + i2 : 0};
+                if (kc[0] >= gc.np[0] || kc[1] >= gc.np[1] || kc[2] >= gc.np[2]) continue;
+                double cc[3], sv[6];
+                lat_centre(gc, kc, cc);
+                const double rho[3] = {cc[0] - cp[0], cc[1] - cp[1], cc[2] - cp[2]};
+                load6(s + 6 * (size_t)lat_index(gc, kc), sv);
+                rbm_apply_t(rho, sv, acc);
+            }
+    store6(y + 6 * (size_t)K, acc);
+}
+
+// child cell: t = B_c e[parent]
+__global__ void __launch_bounds__(256)
+k_lat_prolong_t(const __grid_constant__ LatGeom gc, const __grid_constant__ LatGeom gp, const double *__restrict__ e,
+                double *__restrict__ tv, const CgState *state, int chk)
+{
+    ML_RETURN_IF_DONE(state, chk);
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= gc.n) return;
+    int kc[3], kp[3];
+    double cc[3], cp[3], ev[6], v[6];
+    lat_unindex(gc, c, kc);
+    for (int d = 0; d < 3; d++) kp[d] = gc.active[d] ? kc[d] / 3 : 0;
+    lat_centre(gc, kc, cc);
+    lat_centre(gp, kp, cp);
+    const double rho[3] = {cc[0] - cp[0], cc[1] - cp[1], cc[2] - cp[2]};
+    load6(e + 6 * (size_t)lat_index(gp, kp), ev);
+    rbm_apply(rho, ev, v);
+    store6(tv + 6 * (size_t)c, v);
+}
+
+// x = Minv b, one warp per row
+__global__ void __launch_bounds__(256)
+k_dense_matvec(int n, const double *__restrict__ Minv, const double *__restrict__ b, double *__restrict__ x, const CgState *state, int chk)
+{
+    ML_RETURN_IF_DONE(state, chk);
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= n) return;
+    double s = 0.0;
+    for (int j = lane; j < n; j += 32) s += Minv[(size_t)row * n + j] * b[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) x[row] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// set-up kernels
+// ---------------------------------------------------------------------------------------------
+// probing vector on a lattice: unit mode `mode` on every cell of colour col (index mod 3 per active dimension)
+__global__ void k_lat_set_probe(const __grid_constant__ LatGeom g, int c0, int c1, int c2, int mode, double *__restrict__ e)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= g.n) return;
+    int k[3];
+    lat_unindex(g, a, k);
+    const bool hit = (!g.active[0] || k[0] % 3 == c0) && (!g.active[1] || k[1] % 3 == c1) && (!g.active[2] || k[2] % 3 == c2);
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    if (hit) v[mode] = 1.0;
+    store6(e + 6 * (size_t)a, v);
+}
+
+// y = -(P^T A P) e for the probing vector above: column `mode` of the block coupling each cell to its one
+// neighbour of colour col
+__global__ void k_lat_collect(const __grid_constant__ LatGeom g, int c0, int c1, int c2, int mode, const double *__restrict__ y,
+                              double *__restrict__ A)
+{
+    const int64_t n6 = 6 * (int64_t)g.n;
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n6) return;
+    const int a = (int)(t / 6);
+    int k[3], o[3];
+    lat_unindex(g, a, k);
+    const int col[3] = {c0, c1, c2};
+    for (int d = 0; d < 3; d++) {
+        o[d] = g.active[d] ? ((col[d] - k[d] % 3 + 1) % 3 + 3) % 3 - 1 : 0;
+        const int kk = k[d] + o[d];
+        if (kk < 0 || kk >= g.np[d]) return;
+    }
+    const int s = lat_stencil_slot(g, o);
+    A[(size_t)(6 * s + mode) * n6 + t] = -y[t];
+}
+
+// generalised inverse of a symmetric positive semi-definite 6x6 block: Gauss-Jordan with diagonal pivoting; pivots
+// below 1e-12 of the largest diagonal entry (empty cells, aggregates whose free DOFs do not carry a mode) are
+// left out and their rows/columns zeroed, i.e. the inverse on the pivoted coordinates
+__device__ void ginv6(double M[6][6])
+{
+    bool used[6] = {false, false, false, false, false, false};
+    double dmax = 0.0;
+    for (int a = 0; a < 6; a++) dmax = fmax(dmax, M[a][a]);
+    const double tol = 1e-12 * dmax;
+    for (int step = 0; step < 6; step++) {
+        int k = -1;
+        double best = tol;
+        for (int a = 0; a < 6; a++)
+            if (!used[a] && M[a][a] > best) {
+                best = M[a][a];
+                k = a;
+            }
+        if (k < 0) break;
+        used[k] = true;
+        const double ip = 1.0 / M[k][k];
+        double col[6], row[6];
+        for (int j = 0; j < 6; j++) {
+            col[j] = M[j][k];
+            row[j] = M[k][j] * ip;
+        }
+        for (int i = 0; i < 6; i++)
+            for (int j = 0; j < 6; j++) {
+                if (i == k && j == k) M[i][j] = ip;
+                else if (i == k) M[i][j] = row[j];
+                else if (j == k) M[i][j] = -col[i] * ip;
+                else M[i][j] -= col[i] * row[j];
+            }
+    }
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++)
+            if (!used[i] || !used[j]) M[i][j] = 0.0;
+}
+
+__global__ void k_lat_extract_dinv(const __grid_constant__ LatGeom g, const double *__restrict__ A, double *__restrict__ dinv)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= g.n) return;
+    const int64_t n6 = 6 * (int64_t)g.n;
+    const int zero[3] = {0, 0, 0};
+    const int sc = lat_stencil_slot(g, zero);
+    double D[6][6], S[6][6];
+    for (int a = 0; a < 6; a++)
+        for (int b = 0; b < 6; b++) D[a][b] = A[(size_t)(6 * sc + b) * n6 + 6 * (size_t)p + a];
+    for (int a = 0; a < 6; a++)
+        for (int b = 0; b < 6; b++) S[a][b] = 0.5 * (D[a][b] + D[b][a]);
+    ginv6(S);
+    for (int a = 0; a < 6; a++)
+        for (int b = 0; b < 6; b++) dinv[36 * (size_t)p + 6 * a + b] = 0.5 * (S[a][b] + S[b][a]);
+}
+
+// dense copy of a lattice stencil (coarsest level), M zeroed beforehand
+__global__ void k_lat_to_dense(const __grid_constant__ LatGeom g, const double *__restrict__ A, double *__restrict__ M)
+{
+    const int64_t n6 = 6 * (int64_t)g.n;
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n6) return;
+    int k[3];
+    lat_unindex(g, (int)(t / 6), k);
+    for (int s = 0; s < g.ns; s++) {
+        int o[3];
+        lat_stencil_off(g, s, o);
+        const int kk[3] = {k[0] + o[0], k[1] + o[1], k[2] + o[2]};
+        if (kk[0] < 0 || kk[0] >= g.np[0] || kk[1] < 0 || kk[1] >= g.np[1] || kk[2] < 0 || kk[2] >= g.np[2]) continue;
+        const int64_t c0 = 6 * (int64_t)lat_index(g, kk);
+        for (int b = 0; b < 6; b++) M[t * n6 + c0 + b] = A[(size_t)(6 * s + b) * n6 + t];
+    }
+}
+
+// M <- (M + M^T) / 2
+__global__ void k_dense_symmetrize(int n, double *M)
+{
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n * n) return;
+    const int i = (int)(idx / n), j = (int)(idx % n);
+    if (i >= j) return;
+    const double v = 0.5 * (M[(size_t)i * n + j] + M[(size_t)j * n + i]);
+    M[(size_t)i * n + j] = v;
+    M[(size_t)j * n + i] = v;
+}
+
+// in-place Gauss-Jordan inversion of a symmetric positive semi-definite matrix by ONE thread block; pivots
+// below 1e-12 of the largest diagonal entry (empty cells) are skipped and their rows/columns zeroed, which
+// yields the inverse on the complement
+constexpr int ML_DENSE_MAX_N = 6 * ML_DENSE_MAX_POINTS;
+__global__ void __launch_bounds__(1024)
+k_dense_invert(int n, double *M)
+{
+    __shared__ double colk[ML_DENSE_MAX_N], rowk[ML_DENSE_MAX_N];
+    __shared__ double s_dmax, s_piv;
+    __shared__ double s_part[32];
+    const int tid = threadIdx.x;
+    double dm = 0.0;
+    for (int i = tid; i < n; i += blockDim.x) dm = fmax(dm, M[(size_t)i * n + i]);
+    for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+    if ((tid & 31) == 0) s_part[tid >> 5] = dm;
+    __syncthreads();
+    if (tid == 0) {
+        double m = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) m = fmax(m, s_part[w]);
+        s_dmax = m;
+    }
+    __syncthreads();
+    const double tol = 1e-12 * s_dmax;
+    for (int k = 0; k < n; k++) {
+        if (tid == 0) s_piv = M[(size_t)k * n + k];
+        __syncthreads();
+        const double piv = s_piv;
+        if (!(piv > tol)) {
+            for (int j = tid; j < n; j += blockDim.x) {
+                M[(size_t)k * n + j] = 0.0;
+                M[(size_t)j * n + k] = 0.0;
+            }
+            __syncthreads();
+            continue;
+        }
+        const double ip = 1.0 / piv;
+        for (int j = tid; j < n; j += blockDim.x) {
+            colk[j] = M[(size_t)j * n + k];
+            rowk[j] = M[(size_t)k * n + j] * ip;
+        }
+        __syncthreads();
+        for (int i = tid >> 5; i < n; i += (int)(blockDim.x >> 5)) {  // one warp per row: coalesced row updates
+            const double ci = colk[i];
+            double *Mi = M + (size_t)i * n;
+            if (i == k) {
+                for (int j = tid & 31; j < n; j += 32) Mi[j] = (j == k) ? ip : rowk[j];
+            } else {
+                for (int j = tid & 31; j < n; j += 32) Mi[j] = (j == k) ? -ci * ip : Mi[j] - ci * rowk[j];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// deterministic pseudo-random start vector of the power iterations
+__global__ void k_fill_hash(int64_t n, uint64_t salt, double *__restrict__ v)
+{
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    uint64_t h = (uint64_t)t + salt;
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdULL; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ULL; h ^= h >> 33;
+    v[t] = (double)(h >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+}
+
+// out[0] = sum v^2 (deterministic)
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_norm2(int64_t n, const double *__restrict__ v, double *partials, unsigned int *counter, double *out)
+{
+    double s = 0.0;
+    for (int64_t t = blockIdx.x * (int64_t)BLOCK + threadIdx.x; t < n; t += (int64_t)gridDim.x * BLOCK) s += v[t] * v[t];
+    double a[1] = {s}, r[1];
+    if (grid_reduce<1, BLOCK>(a, partials, counter, r) && threadIdx.x == 0) out[0] = r[0];
+}
+
+__global__ void k_scale_copy(int64_t n, const double *__restrict__ in, double f, double *__restrict__ out)
+{
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n) out[t] = f * in[t];
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: hierarchy
+// ---------------------------------------------------------------------------------------------
+static int ml_build_geometry(fs_context *c)
+{
+    MlHier &m = c->ml;
+    m.n_lat = 0;
+    double ext[3], maxext = 0.0;
+    for (int d = 0; d < 3; d++) {
+        ext[d] = c->bbox_hi[d] - c->bbox_lo[d];
+        maxext = std::max(maxext, ext[d]);
+    }
+    LatGeom g = {};
+    for (int d = 0; d < 3; d++) g.active[d] = (maxext > 0.0 && ext[d] > 1e-9 * maxext) ? 1 : 0;
+    if (!(g.active[0] || g.active[1] || g.active[2])) return fail(c, FS_ERR_STATE, "multilevel preconditioner: mesh has no extent");
+    // first lattice: cells three element widths wide, enlarged until the cap on cells holds
+    double scale = 1.0;
+    for (;;) {
+        int64_t tot = 1;
+        g.ns = 1;
+        for (int d = 0; d < 3; d++) {
+            if (g.active[d]) {
+                const double h = c->ml_h[d] > 0.0 ? c->ml_h[d] : ext[d];
+                g.H[d] = 3.0 * h * scale;
+                g.lo[d] = c->bbox_lo[d] - 0.5 * h;
+                g.np[d] = (int)std::floor((c->bbox_hi[d] - g.lo[d]) / g.H[d]) + 1;
+                g.ns *= 3;
+            } else {
+                g.H[d] = 0.0;
+                g.lo[d] = c->bbox_lo[d];
+                g.np[d] = 1;
+            }
+            tot *= g.np[d];
+        }
+        if (tot <= std::max<int64_t>(c->ml_max_points, 64)) {
+            g.n = (int)tot;
+            break;
+        }
+        scale *= 1.2;
+    }
+    for (int l = 0; l < ML_MAX_LEVELS; l++) {
+        MlLevelBuf &L = m.lat[l];
+        L.g = g;
+        L.dense = (g.n <= c->ml_dense_points) || (l == ML_MAX_LEVELS - 1);
+        m.n_lat = l + 1;
+        if (L.dense) break;
+        int64_t tot = 1;
+        for (int d = 0; d < 3; d++)
+            if (g.active[d]) {
+                g.np[d] = (g.np[d] + 2) / 3;
+                g.H[d] *= 3.0;
+                tot *= g.np[d];
+            }
+        g.n = (int)tot;
+    }
+    if (m.lat[m.n_lat - 1].g.n > ML_DENSE_MAX_POINTS) return fail(c, FS_ERR_STATE, "multilevel preconditioner: coarsest lattice too large");
+
+    for (int l = 0; l < m.n_lat; l++) {
+        MlLevelBuf &L = m.lat[l];
+        const size_t n6 = 6 * (size_t)L.g.n;
+        FS_CUDA(c, L.A.alloc((size_t)L.g.ns * 6 * n6));
+        FS_CUDA(c, L.dinv.alloc(6 * n6));
+        FS_CUDA(c, L.x.alloc(n6));
+        FS_CUDA(c, L.xb.alloc(n6));
+        FS_CUDA(c, L.b.alloc(n6));
+        FS_CUDA(c, L.r.alloc(n6));
+        FS_CUDA(c, L.t.alloc(n6));
+        if (L.dense) FS_CUDA(c, L.minv.alloc(n6 * n6));
+        L.omega = 0.0;
+    }
+
+    // aggregates of the first lattice: cell of every LOCAL node, and per cell the list of OWNED nodes in it
+    const int64_t n_local = c->n_local, n_own = c->n_own, own_lo = c->own_lo;
+    std::vector<double> x(3 * (size_t)n_local);
+    FS_CUDA(c, cudaMemcpy(x.data(), c->d_xyz.p, sizeof(double) * 3 * n_local, cudaMemcpyDeviceToHost));
+    const LatGeom &g1 = m.lat[0].g;
+    std::vector<int32_t> agg(n_local), ptr((size_t)g1.n + 1, 0), sup(n_own);
+    for (int64_t i = 0; i < n_local; i++) agg[i] = lat_cell_of(g1, &x[3 * i]);
+    for (int64_t p = 0; p < n_own; p++) ptr[agg[own_lo + p] + 1]++;
+    for (int a = 0; a < g1.n; a++) ptr[a + 1] += ptr[a];
+    {
+        std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
+        for (int64_t p = 0; p < n_own; p++) sup[fill[agg[own_lo + p]]++] = (int32_t)p;
+    }
+    FS_CUDA(c, m.d_agg.alloc(n_local));
+    FS_CUDA(c, m.d_sup_ptr.alloc(ptr.size()));
+    FS_CUDA(c, m.d_sup_node.alloc(std::max<size_t>(1, sup.size())));
+    FS_CUDA(c, cudaMemcpy(m.d_agg.p, agg.data(), sizeof(int32_t) * n_local, cudaMemcpyHostToDevice));
+    FS_CUDA(c, cudaMemcpy(m.d_sup_ptr.p, ptr.data(), sizeof(int32_t) * ptr.size(), cudaMemcpyHostToDevice));
+    if (!sup.empty()) FS_CUDA(c, cudaMemcpy(m.d_sup_node.p, sup.data(), sizeof(int32_t) * sup.size(), cudaMemcpyHostToDevice));
+    FS_CUDA(c, m.d_r1.alloc(6 * (size_t)n_local));
+    FS_CUDA(c, m.d_t.alloc(6 * (size_t)n_local));
+    FS_CUDA(c, cudaMemset(m.d_r1.p, 0, sizeof(double) * 6 * n_local));
+    FS_CUDA(c, cudaMemset(m.d_t.p, 0, sizeof(double) * 6 * n_local));
+    FS_CUDA(c, m.d_scalar.alloc(4));
+    c->ml_geom_ready = true;
+    c->ml_values_ready = false;
+    return FS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the building blocks of the cycle (enqueue only)
+// ---------------------------------------------------------------------------------------------
+static const CgState *st_of(fs_context *c) { return c->d_state.p; }
+
+// mesh level: b_1 = P^T (b - A x).  b and x are LOCAL-layout vectors (b may be null: zero); x's halo is refreshed.
+static int fine_restrict_chain(fs_context *c, const double *b, double *x, int chk)
+{
+    MlHier &m = c->ml;
+    cudaStream_t st = c->stream;
+    const int64_t o6 = 6 * c->own_lo, n6 = 6 * c->n_own;
+    int rc = spmv_once(c, x, c->d_q.p, chk != 0);
+    if (rc) return rc;
+    k_f_resid<<<nblk(n6, 192), 192, 0, st>>>(n6, b ? b + o6 : nullptr, c->d_q.p + o6, c->d_minv.p, m.d_r1.p + o6, m.d_t.p + o6, st_of(c), chk);
+    rc = spmv_once(c, m.d_t.p, c->d_q.p, chk != 0);
+    if (rc) return rc;
+    const LatGeom &g1 = m.lat[0].g;
+    k_f_restrict<<<nblk(8 * (int64_t)g1.n, 256), 256, 0, st>>>(g1, m.d_sup_ptr.p, m.d_sup_node.p, c->d_xyz.p + 3 * c->own_lo,
+                                                              c->d_mask.p + c->own_lo, m.d_r1.p + o6, c->d_q.p + o6, m.omega0,
+                                                              m.lat[0].b.p, st_of(c), chk);
+    if (c->world > 1)
+        FS_NCCL_ML(c, nccl().AllReduce(m.lat[0].b.p, m.lat[0].b.p, 6 * (size_t)g1.n, ncclDouble, ncclSum, (ncclComm_t)c->comm, st));
+    return FS_OK;
+}
+
+// mesh level: x (+)= P e  (e on the first lattice, replicated)
+static int fine_prolong_chain(fs_context *c, const double *e, double *x, bool accumulate, int chk)
+{
+    MlHier &m = c->ml;
+    cudaStream_t st = c->stream;
+    const int64_t o6 = 6 * c->own_lo, n6 = 6 * c->n_own;
+    k_f_prolong_t<<<nblk(c->n_local, 256), 256, 0, st>>>(m.lat[0].g, c->n_local, m.d_agg.p, c->d_xyz.p, c->d_mask.p, e, m.d_t.p, st_of(c), chk);
+    int rc = spmv_local(c, m.d_t.p, c->d_q.p, chk != 0);  // t is complete on owned and halo nodes: no exchange
+    if (rc) return rc;
+    k_f_prolong_add<<<nblk(n6, 256), 256, 0, st>>>(n6, m.d_t.p + o6, c->d_q.p + o6, c->d_minv.p, m.omega0, x + o6, accumulate ? 1 : 0, st_of(c), chk);
+    return FS_OK;
+}
+
+static void lat_restrict_chain(fs_context *c, int l, const double *b, const double *x, int chk)
+{
+    MlHier &m = c->ml;
+    MlLevelBuf &L = m.lat[l], &N = m.lat[l + 1];
+    cudaStream_t st = c->stream;
+    const int64_t n6 = 6 * (int64_t)L.g.n;
+    k_lat_stencil<LAT_RESID><<<nblk(n6, 192), 192, 0, st>>>(L.g, L.A.p, L.dinv.p, x, b, L.r.p, L.t.p, L.omega, 0, st_of(c), chk);
+    k_lat_stencil<LAT_RSMOOTH><<<nblk(n6, 192), 192, 0, st>>>(L.g, L.A.p, L.dinv.p, L.t.p, L.r.p, L.r.p, nullptr, L.omega, 0, st_of(c), chk);
+    k_lat_restrict<<<nblk(N.g.n, 128), 128, 0, st>>>(L.g, N.g, L.r.p, N.b.p, st_of(c), chk);
+}
+
+static void lat_prolong_chain(fs_context *c, int l, const double *e, double *x, bool accumulate, int chk)
+{
+    MlHier &m = c->ml;
+    MlLevelBuf &L = m.lat[l], &N = m.lat[l + 1];
+    cudaStream_t st = c->stream;
+    const int64_t n6 = 6 * (int64_t)L.g.n;
+    k_lat_prolong_t<<<nblk(L.g.n, 256), 256, 0, st>>>(L.g, N.g, e, L.t.p, st_of(c), chk);
+    k_lat_stencil<LAT_PADD><<<nblk(n6, 192), 192, 0, st>>>(L.g, L.A.p, L.dinv.p, L.t.p, nullptr, x, nullptr, L.omega, accumulate ? 1 : 0, st_of(c), chk);
+}
+
+// one cycle on lattice level l for the right-hand side in lat[l].b; returns where the result lives
+static const double *lat_cycle(fs_context *c, int l, int chk)
+{
+    MlHier &m = c->ml;
+    MlLevelBuf &L = m.lat[l];
+    cudaStream_t st = c->stream;
+    const int64_t n6 = 6 * (int64_t)L.g.n;
+    if (L.dense) {
+        k_dense_matvec<<<nblk(32 * n6, 256), 256, 0, st>>>((int)n6, L.minv.p, L.b.p, L.xb.p, st_of(c), chk);
+        return L.xb.p;
+    }
+    k_lat_smooth0<<<nblk(n6, 256), 256, 0, st>>>(n6, L.b.p, L.dinv.p, L.omega, L.x.p, st_of(c), chk);
+    for (int gmm = 0; gmm < c->ml_gamma; gmm++) {
+        lat_restrict_chain(c, l, L.b.p, L.x.p, chk);
+        const double *e = lat_cycle(c, l + 1, chk);
+        lat_prolong_chain(c, l, e, L.x.p, true, chk);
+    }
+    k_lat_stencil<LAT_POST><<<nblk(n6, 192), 192, 0, st>>>(L.g, L.A.p, L.dinv.p, L.x.p, L.b.p, L.xb.p, nullptr, L.omega, 0, st_of(c), chk);
+    return L.xb.p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// set-up of the values: smoother weights, coarse stencils, dense coarsest inverse
+// ---------------------------------------------------------------------------------------------
+static int read_scalar(fs_context *c, const double *d, int count, double *h, bool all_reduce)
+{
+    if (all_reduce && c->world > 1)
+        FS_NCCL_ML(c, nccl().AllReduce(d, const_cast<double *>(d), count, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
+    FS_CUDA(c, cudaMemcpyAsync(h, d, sizeof(double) * count, cudaMemcpyDeviceToHost, c->stream));
+    FS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FS_OK;
+}
+
+// the reduction scratch must hold the largest grid of any reducing kernel (+ the spare doubles run_pcg uses)
+int ml_ensure_partials(fs_context *c)
+{
+    const size_t need = (size_t)c->sm_count * 64 * 4 + 64;
+    if (c->d_partials.n < need) {
+        if (c->cg_graph_exec) { cudaGraphExecDestroy(c->cg_graph_exec); c->cg_graph_exec = nullptr; }
+        FS_CUDA(c, c->d_partials.alloc(need));
+    }
+    return FS_OK;
+}
+
+constexpr int ML_POWER_ITS = 20;
+
+// largest eigenvalue of D^-1 A on the mesh level (power iteration), with a safety margin
+static int fine_lambda(fs_context *c, double *lam)
+{
+    MlHier &m = c->ml;
+    cudaStream_t st = c->stream;
+    const int64_t o6 = 6 * c->own_lo, n6 = 6 * c->n_own;
+    const int grid = (int)std::min<int64_t>(nblk(n6, 256), (int64_t)c->sm_count * 4);
+    int rc = ml_ensure_partials(c);
+    if (rc) return rc;
+    FS_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned int), st));
+    double *v = c->d_z.p;  // local layout
+    k_fill_hash<<<nblk(n6, 256), 256, 0, st>>>(n6, 0x9e3779b97f4a7c15ULL + (uint64_t)(6 * c->own_begin), v + o6);
+    double est = 1.0;
+    for (int it = 0; it < ML_POWER_ITS; it++) {
+        rc = spmv_once(c, v, c->d_q.p, false);
+        if (rc) return rc;
+        // t = -D^-1 A v ; r1 = -A v
+        k_f_resid<<<nblk(n6, 192), 192, 0, st>>>(n6, nullptr, c->d_q.p + o6, c->d_minv.p, m.d_r1.p + o6, m.d_t.p + o6, st_of(c), 0);
+        k_norm2<256><<<grid, 256, 0, st>>>(n6, v + o6, c->d_partials.p, c->d_counter.p, m.d_scalar.p);
+        k_norm2<256><<<grid, 256, 0, st>>>(n6, m.d_t.p + o6, c->d_partials.p, c->d_counter.p, m.d_scalar.p + 1);
+        double h[2];
+        rc = read_scalar(c, m.d_scalar.p, 2, h, true);
+        if (rc) return rc;
+        if (!(h[0] > 0.0) || !(h[1] > 0.0)) return fail(c, FS_ERR_BREAKDOWN, "multilevel set-up: power iteration collapsed");
+        est = std::sqrt(h[1] / h[0]);
+        k_scale_copy<<<nblk(n6, 256), 256, 0, st>>>(n6, m.d_t.p + o6, 1.0 / std::sqrt(h[1]), v + o6);
+    }
+    *lam = 1.1 * est;
+    return FS_OK;
+}
+
+static int lat_lambda(fs_context *c, int l, double *lam)
+{
+    MlHier &m = c->ml;
+    MlLevelBuf &L = m.lat[l];
+    cudaStream_t st = c->stream;
+    const int64_t n6 = 6 * (int64_t)L.g.n;
+    const int grid = (int)std::min<int64_t>(nblk(n6, 256), (int64_t)c->sm_count * 4);
+    int rc = ml_ensure_partials(c);
+    if (rc) return rc;
+    FS_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned int), st));
+    k_fill_hash<<<nblk(n6, 256), 256, 0, st>>>(n6, 0x51ed270b7f4a7c15ULL + (uint64_t)l, L.x.p);
+    double est = 1.0;
+    for (int it = 0; it < ML_POWER_ITS; it++) {
+        // r = -A x ; t = -D^+ A x
+        k_lat_stencil<LAT_RESID><<<nblk(n6, 192), 192, 0, st>>>(L.g, L.A.p, L.dinv.p, L.x.p, nullptr, L.r.p, L.t.p, 0.0, 0, st_of(c), 0);
+        k_norm2<256><<<grid, 256, 0, st>>>(n6, L.x.p, c->d_partials.p, c->d_counter.p, m.d_scalar.p);
+        k_norm2<256><<<grid, 256, 0, st>>>(n6, L.t.p, c->d_partials.p, c->d_counter.p, m.d_scalar.p + 1);
+        double h[2];
+        rc = read_scalar(c, m.d_scalar.p, 2, h, false);
+        if (rc) return rc;
+        if (!(h[0] > 0.0) || !(h[1] > 0.0)) return fail(c, FS_ERR_BREAKDOWN, "multilevel set-up: power iteration collapsed on a lattice");
+        est = std::sqrt(h[1] / h[0]);
+        k_scale_copy<<<nblk(n6, 256), 256, 0, st>>>(n6, L.t.p, 1.0 / std::sqrt(h[1]), L.x.p);
+    }
+    *lam = 1.1 * est;
+    return FS_OK;
+}
+
+int ml_prepare(fs_context *c)
+{
+    if (!c->ml_geom_ready) {
+        int rc = ml_build_geometry(c);
+        if (rc) return rc;
+    }
+    if (c->ml_values_ready) return FS_OK;
+    if (c->cg_graph_exec) {  // a captured iteration carries the smoother weights of the previous values
+        cudaGraphExecDestroy(c->cg_graph_exec);
+        c->cg_graph_exec = nullptr;
+    }
+    MlHier &m = c->ml;
+    cudaStream_t st = c->stream;
+    cudaEvent_t e0 = c->ev0, e1 = c->ev1;
+    FS_CUDA(c, cudaEventRecord(e0, st));
+    double lam = 1.0;
+    int rc = fine_lambda(c, &lam);
+    if (rc) return rc;
+    m.lambda0 = lam;
+    m.omega0 = (4.0 / 3.0) / lam;
+
+    for (int l = 0; l < m.n_lat; l++) {
+        MlLevelBuf &L = m.lat[l];
+        const LatGeom &g = L.g;
+        const int64_t n6 = 6 * (int64_t)g.n;
+        // stencil of this level by probing the level below through the cycle's own transfer operators
+        FS_CUDA(c, cudaMemsetAsync(L.A.p, 0, sizeof(double) * (size_t)g.ns * 6 * n6, st));
+        const int nc0 = g.active[0] ? 3 : 1, nc1 = g.active[1] ? 3 : 1, nc2 = g.active[2] ? 3 : 1;
+        for (int c2 = 0; c2 < nc2; c2++)
+            for (int c1 = 0; c1 < nc1; c1++)
+                for (int c0 = 0; c0 < nc0; c0++)
+                    for (int mode = 0; mode < 6; mode++) {
+                        k_lat_set_probe<<<nblk(g.n, 256), 256, 0, st>>>(g, c0, c1, c2, mode, L.xb.p);
+                        if (l == 0) {
+                            rc = fine_prolong_chain(c, L.xb.p, c->d_z.p, false, 0);
+                            if (rc) return rc;
+                            rc = fine_restrict_chain(c, nullptr, c->d_z.p, 0);
+                            if (rc) return rc;
+                        } else {
+                            lat_prolong_chain(c, l - 1, L.xb.p, m.lat[l - 1].x.p, false, 0);
+                            lat_restrict_chain(c, l - 1, nullptr, m.lat[l - 1].x.p, 0);
+                        }
+                        k_lat_collect<<<nblk(n6, 256), 256, 0, st>>>(g, c0, c1, c2, mode, L.b.p, L.A.p);
+                    }
+        FS_CUDA(c, cudaGetLastError());
+        if (L.dense) {
+            FS_CUDA(c, cudaMemsetAsync(L.minv.p, 0, sizeof(double) * (size_t)n6 * n6, st));
+            k_lat_to_dense<<<nblk(n6, 128), 128, 0, st>>>(g, L.A.p, L.minv.p);
+            k_dense_symmetrize<<<nblk(n6 * n6, 256), 256, 0, st>>>((int)n6, L.minv.p);
+            k_dense_invert<<<1, 1024, 0, st>>>((int)n6, L.minv.p);
+            k_dense_symmetrize<<<nblk(n6 * n6, 256), 256, 0, st>>>((int)n6, L.minv.p);
+            L.omega = 0.0;
+            L.lambda = 0.0;
+        } else {
+            k_lat_extract_dinv<<<nblk(g.n, 64), 64, 0, st>>>(g, L.A.p, L.dinv.p);
+            rc = lat_lambda(c, l, &lam);
+            if (rc) return rc;
+            L.lambda = lam;
+            L.omega = (4.0 / 3.0) / lam;
+        }
+        FS_CUDA(c, cudaGetLastError());
+    }
+    FS_CUDA(c, cudaEventRecord(e1, st));
+    FS_CUDA(c, cudaStreamSynchronize(st));
+    FS_CUDA(c, cudaEventElapsedTime(&m.setup_ms, e0, e1));
+    c->ml_values_ready = true;
+    return FS_OK;
+}
+
+// one application inside the CG iteration (or at its start): r (d_r) -> z (d_z) (+ p at INIT), recurrence advanced.
+// red == nullptr: plain application without the dot product (tests).
+int ml_enqueue_apply(fs_context *c, bool init, double *red, int fin, int vec_grid)
+{
+    MlHier &m = c->ml;
+    cudaStream_t st = c->stream;
+    const int64_t o6 = 6 * c->own_lo, n6 = 6 * c->n_own;
+    const int chk = (init || !red) ? 0 : 1;
+    k_f_smooth0<<<nblk(n6, 256), 256, 0, st>>>(n6, c->d_r.p + o6, c->d_minv.p, m.omega0, c->d_z.p + o6, st_of(c), chk);
+    int rc = fine_restrict_chain(c, c->d_r.p, c->d_z.p, chk);
+    if (rc) return rc;
+    const double *e = lat_cycle(c, 0, chk);
+    rc = fine_prolong_chain(c, e, c->d_z.p, true, chk);
+    if (rc) return rc;
+    rc = spmv_once(c, c->d_z.p, c->d_q.p, chk != 0);
+    if (rc) return rc;
+    constexpr int PB = 192;
+    const int grid = std::max(1, vec_grid);
+    if (!red)
+        k_f_post_finish<false, false, PB><<<grid, PB, 0, st>>>(n6, c->d_r.p + o6, c->d_q.p + o6, c->d_minv.p, m.omega0, c->d_z.p + o6, nullptr,
+                                                                 c->d_partials.p, c->d_counter.p, c->d_state.p, nullptr, fin, 0);
+    else if (init)
+        k_f_post_finish<true, true, PB><<<grid, PB, 0, st>>>(n6, c->d_r.p + o6, c->d_q.p + o6, c->d_minv.p, m.omega0, c->d_z.p + o6, c->d_p.p + o6,
+                                                               c->d_partials.p, c->d_counter.p, c->d_state.p, red, fin, 0);
+    else
+        k_f_post_finish<false, true, PB><<<grid, PB, 0, st>>>(n6, c->d_r.p + o6, c->d_q.p + o6, c->d_minv.p, m.omega0, c->d_z.p + o6, c->d_p.p + o6,
+                                                                c->d_partials.p, c->d_counter.p, c->d_state.p, red, fin, 1);
+    return FS_OK;
+}
+
+}  // namespace fs

@@ -68,7 +68,7 @@ k_spmv_sell(int n_own, int n_slices, const int32_t *__restrict__ sptr, const int
             double *red, int fin_mode, PeerWin *pw)
 {
     constexpr int NZ = sell_popcount(MASK);
-    if (WITH_DOT && state->done) return;
+    if (WITH_DOT ? state->done : (state && state->done)) return;  // without the dot product: checked only when a state is passed
     if (WITH_DOT && pw && !peer_halo_wait(pw)) {  // the neighbours' boundary values of x must have landed
         if (blockIdx.x == 0 && threadIdx.x == 0) peer_fail(state);
         return;

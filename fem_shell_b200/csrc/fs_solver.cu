@@ -56,7 +56,7 @@ k_spmv(int n_own, const int32_t *__restrict__ nptr, const int32_t *__restrict__ 
        const double *__restrict__ x_own, double *partials, unsigned int *counter, CgState *state,
        double *red, int fin_mode, PeerWin *pw)
 {
-    if (WITH_DOT && state->done) return;
+    if (WITH_DOT ? state->done : (state && state->done)) return;  // without the dot product: checked only when a state is passed
     if (WITH_DOT && pw && !peer_halo_wait(pw)) {  // the neighbours' boundary values of x must have landed
         if (blockIdx.x == 0 && threadIdx.x == 0) peer_fail(state);
         return;
@@ -204,6 +204,62 @@ k_update(int64_t n_own, double *__restrict__ x, double *__restrict__ r, const do
     }
     double v[2] = {rz, nn}, out[2];
     if (grid_reduce<2, BLOCK>(v, partials, counter, out) && threadIdx.x == 0) finish_dot<2>(out, red, fin_mode, state, pw);
+}
+
+// x += alpha p ; r -= alpha q ; partial ||r||^2 -- first half of k_update for the multilevel preconditioner
+// (z needs the globally restricted r, fs_mlpc.cu).  The norm is left in red[0]; the recurrence advances in
+// k_ml_prolong_finish.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_update_xr(int64_t n_own, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
+            const double *__restrict__ q, double *partials, unsigned int *counter, CgState *state, double *red)
+{
+    if (state->done) return;
+    const double alpha = state->alpha;
+    double nn = 0.0;
+    for (int64_t n = blockIdx.x * (int64_t)BLOCK + threadIdx.x; n < n_own; n += (int64_t)gridDim.x * BLOCK) {
+        double xv[6], rv[6], pv[6], qv[6];
+        load6(x + 6 * n, xv);
+        load6(r + 6 * n, rv);
+        load6(p + 6 * n, pv);
+        load6(q + 6 * n, qv);
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            xv[a] += alpha * pv[a];
+            rv[a] -= alpha * qv[a];
+            nn += rv[a] * rv[a];
+        }
+        store6(x + 6 * n, xv);
+        store6(r + 6 * n, rv);
+    }
+    double v[1] = {nn}, out[1];
+    if (grid_reduce<1, BLOCK>(v, partials, counter, out) && threadIdx.x == 0) red[0] = out[0];
+}
+
+// r = b - q ; partial ||r||^2 and ||b||^2 into red[0], red[1] (multilevel preconditioner: z follows in fs_mlpc.cu)
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_init_r(int64_t n_own, const double *__restrict__ b, const double *__restrict__ q, double *__restrict__ r,
+         double *partials, unsigned int *counter, double *red)
+{
+    double nn = 0.0, bb = 0.0;
+    for (int64_t n = blockIdx.x * (int64_t)BLOCK + threadIdx.x; n < n_own; n += (int64_t)gridDim.x * BLOCK) {
+        double bv[6], qv[6], rv[6];
+        load6(b + 6 * n, bv);
+        load6(q + 6 * n, qv);
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            rv[a] = bv[a] - qv[a];
+            nn += rv[a] * rv[a];
+            bb += bv[a] * bv[a];
+        }
+        store6(r + 6 * n, rv);
+    }
+    double v[2] = {nn, bb}, out[2];
+    if (grid_reduce<2, BLOCK>(v, partials, counter, out) && threadIdx.x == 0) {
+        red[0] = out[0];
+        red[1] = out[1];
+    }
 }
 
 // p = z + beta p
@@ -409,22 +465,30 @@ int spmv_format_prepare(fs_context *c)
 }
 
 template <unsigned long long MASK, bool WITH_DOT>
-static void launch_sell(fs_context *c, const double *x, double *y_own, const double *x_own, double *red, int fin_mode, PeerWin *pw)
+static void launch_sell(fs_context *c, const double *x, double *y_own, const double *x_own, double *red, int fin_mode, PeerWin *pw,
+                        CgState *state)
 {
     const int64_t want = (c->sell_slices + SELL_BLOCK / 32 - 1) / (SELL_BLOCK / 32);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->sm_count * c->sell_blocks_per_sm));
     k_spmv_sell<MASK, WITH_DOT, SELL_BLOCK, SELL_MINB><<<grid, SELL_BLOCK, 0, c->stream>>>(
         (int)c->n_own, (int)c->sell_slices, c->d_sell_sptr.p, c->d_sell_adj.p, c->d_sell_vals.p, x, y_own, x_own,
-        c->d_partials.p, c->d_counter.p, c->d_state.p, red, fin_mode, pw);
+        c->d_partials.p, c->d_counter.p, state, red, fin_mode, pw);
 }
 
 int solver_prepare(fs_context *c, int pc)
 {
     if (!c->assembled) return fail(c, FS_ERR_STATE, "fs_solve before fs_assemble");
-    if (pc < 0 || pc > 2) return fail(c, FS_ERR_ARG, "unknown preconditioner");
+    if (pc < 0 || pc > 3) return fail(c, FS_ERR_ARG, "unknown preconditioner");
     {
         int rc = spmv_format_prepare(c);
         if (rc) return rc;
+    }
+    if (pc == FS_PC_MLRBM) {  // multigrid cycle whose mesh-level smoother is block Jacobi (fs_mlpc.cu)
+        int rc = solver_prepare(c, FS_PC_BJACOBI6);
+        if (rc) return rc;
+        rc = ml_ensure_partials(c);
+        if (rc) return rc;
+        return ml_prepare(c);
     }
     if (c->minv_kind == pc) return FS_OK;
     if (pc != FS_PC_NONE) {
@@ -492,26 +556,38 @@ static int vec_grid(fs_context *c)
 
 // y_own = A x (+ partial x_own.y_own) on whichever copy of the matrix is current
 template <bool WITH_DOT>
-static void launch_spmv(fs_context *c, const double *x, double *y_own, const double *x_own, double *red, int fin_mode, PeerWin *pw)
+static void launch_spmv(fs_context *c, const double *x, double *y_own, const double *x_own, double *red, int fin_mode, PeerWin *pw,
+                        bool check_done = true)
 {
+    // the kernels with the dot product always honour the done flag; the plain ones only when handed the state
+    CgState *state = (WITH_DOT || check_done) ? c->d_state.p : nullptr;
     if (c->sell_active) {
-        if (c->sell_mask == SELL_MASK_XY) launch_sell<SELL_MASK_XY, WITH_DOT>(c, x, y_own, x_own, red, fin_mode, pw);
-        else if (c->sell_mask == SELL_MASK_XZ) launch_sell<SELL_MASK_XZ, WITH_DOT>(c, x, y_own, x_own, red, fin_mode, pw);
-        else launch_sell<SELL_MASK_YZ, WITH_DOT>(c, x, y_own, x_own, red, fin_mode, pw);
+        if (c->sell_mask == SELL_MASK_XY) launch_sell<SELL_MASK_XY, WITH_DOT>(c, x, y_own, x_own, red, fin_mode, pw, state);
+        else if (c->sell_mask == SELL_MASK_XZ) launch_sell<SELL_MASK_XZ, WITH_DOT>(c, x, y_own, x_own, red, fin_mode, pw, state);
+        else launch_sell<SELL_MASK_YZ, WITH_DOT>(c, x, y_own, x_own, red, fin_mode, pw, state);
         return;
     }
     k_spmv<WITH_DOT, SPMV_BLOCK><<<spmv_grid(c), SPMV_BLOCK, 0, c->stream>>>(
         (int)c->n_own, c->d_nptr.p, c->d_nadj.p, c->d_vals.p, x, y_own, x_own, c->d_partials.p, c->d_counter.p,
-        c->d_state.p, red, fin_mode, pw);
+        state, red, fin_mode, pw);
 }
 
-int spmv_once(fs_context *c, const double *d_in, double *d_out)
+int spmv_once(fs_context *c, const double *d_in, double *d_out, bool check_done)
 {
     int rc = spmv_format_prepare(c);
     if (rc) return rc;
     rc = halo_exchange(c, const_cast<double *>(d_in));
     if (rc) return rc;
-    launch_spmv<false>(c, d_in, d_out + 6 * c->own_lo, nullptr, nullptr, FIN_RED, nullptr);
+    launch_spmv<false>(c, d_in, d_out + 6 * c->own_lo, nullptr, nullptr, FIN_RED, nullptr, check_done);
+    FS_CUDA(c, cudaGetLastError());
+    return FS_OK;
+}
+
+int spmv_local(fs_context *c, const double *d_in, double *d_out, bool check_done)
+{
+    int rc = spmv_format_prepare(c);
+    if (rc) return rc;
+    launch_spmv<false>(c, d_in, d_out + 6 * c->own_lo, nullptr, nullptr, FIN_RED, nullptr, check_done);
     FS_CUDA(c, cudaGetLastError());
     return FS_OK;
 }
@@ -519,7 +595,7 @@ int spmv_once(fs_context *c, const double *d_in, double *d_out)
 template <int PC, int NORM>
 static int enqueue_iteration(fs_context *c, double *red, int sg, int vg)
 {
-    const bool single = (c->world == 1), peer = !single && c->peer_ready;
+    const bool single = (c->world == 1), peer = !single && c->peer_ready && PC != 3;
     const int fin = single ? FIN_INLINE : (peer ? FIN_PEER : FIN_RED);
     PeerWin *pw = peer ? c->d_pw.p : nullptr;
     const int64_t o6 = 6 * c->own_lo;
@@ -535,7 +611,19 @@ static int enqueue_iteration(fs_context *c, double *red, int sg, int vg)
         FS_NCCL(c, nccl().AllReduce(red, red, 1, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
         k_finalize<<<1, 1, 0, c->stream>>>(c->d_state.p, red, 1);
     }
-    k_update<PC, NORM, 256><<<vg, 256, 0, c->stream>>>(c->n_own, c->d_x.p + o6, c->d_r.p + o6, c->d_p.p + o6,
+    if (PC == 3) {  // z needs the lattice restriction of the updated r: update, restrict, coarse levels, prolong
+        k_update_xr<256><<<vg, 256, 0, c->stream>>>(c->n_own, c->d_x.p + o6, c->d_r.p + o6, c->d_p.p + o6, c->d_q.p + o6,
+                                                    c->d_partials.p, c->d_counter.p, c->d_state.p, red + 5);
+        int rc = ml_enqueue_apply(c, false, red + 4, fin, vg);
+        if (rc) return rc;
+        if (fin == FIN_RED) {
+            FS_NCCL(c, nccl().AllReduce(red + 4, red + 4, 2, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
+            k_finalize<<<1, 1, 0, c->stream>>>(c->d_state.p, red + 4, 2);
+        }
+        k_direction<256><<<vg, 256, 0, c->stream>>>(c->n_own, c->d_z.p + o6, c->d_p.p + o6, c->d_state.p, pw, c->d_counter.p);
+        return FS_OK;
+    }
+    k_update<PC == 3 ? 1 : PC, NORM, 256><<<vg, 256, 0, c->stream>>>(c->n_own, c->d_x.p + o6, c->d_r.p + o6, c->d_p.p + o6,
                                                        c->d_q.p + o6, c->d_z.p + o6, c->d_minv.p, c->d_partials.p,
                                                        c->d_counter.p, c->d_state.p, red + 4, fin, pw);
     if (fin == FIN_RED) {
@@ -550,13 +638,13 @@ template <int PC, int NORM>
 static int run_pcg(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
 {
     cudaStream_t st = c->stream;
-    const bool single = (c->world == 1), peer = !single && c->peer_ready;
+    const bool single = (c->world == 1), peer = !single && c->peer_ready && PC != 3;
     const int fin = single ? FIN_INLINE : (peer ? FIN_PEER : FIN_RED);
     PeerWin *pw = peer ? c->d_pw.p : nullptr;
     const int64_t o6 = 6 * c->own_lo;
     const int sg = spmv_grid(c), vg = vec_grid(c);
     const int maxgrid = std::max(std::max(sg, vg), c->sm_count * c->sell_blocks_per_sm);
-    if (c->d_partials.n < (size_t)maxgrid * 4) FS_CUDA(c, c->d_partials.alloc((size_t)maxgrid * 4 + 16));
+    if (c->d_partials.n < (size_t)maxgrid * 4 + 16) FS_CUDA(c, c->d_partials.alloc((size_t)maxgrid * 4 + 16));
     double *red = c->d_partials.p + (size_t)maxgrid * 4;  // 16 spare doubles behind the partials
 
     CgState h = {};
@@ -572,9 +660,14 @@ static int run_pcg(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
     // r = b - A x0
     int rc = spmv_once(c, c->d_x.p, c->d_q.p);
     if (rc) return rc;
-    k_init<PC, NORM, 256><<<vg, 256, 0, st>>>(c->n_own, c->d_b.p + o6, c->d_q.p + o6, c->d_r.p + o6, c->d_z.p + o6,
-                                              c->d_p.p + o6, c->d_minv.p, c->d_partials.p, c->d_counter.p,
-                                              c->d_state.p, red + 8, fin, pw);
+    if (PC == 3) {
+        k_init_r<256><<<vg, 256, 0, st>>>(c->n_own, c->d_b.p + o6, c->d_q.p + o6, c->d_r.p + o6, c->d_partials.p, c->d_counter.p, red + 9);
+        rc = ml_enqueue_apply(c, true, red + 8, fin, vg);
+        if (rc) return rc;
+    } else
+        k_init<PC == 3 ? 1 : PC, NORM, 256><<<vg, 256, 0, st>>>(c->n_own, c->d_b.p + o6, c->d_q.p + o6, c->d_r.p + o6, c->d_z.p + o6,
+                                                                 c->d_p.p + o6, c->d_minv.p, c->d_partials.p, c->d_counter.p,
+                                                                 c->d_state.p, red + 8, fin, pw);
     if (fin == FIN_RED) {
         FS_NCCL(c, nccl().AllReduce(red + 8, red + 8, 3, ncclDouble, ncclSum, (ncclComm_t)c->comm, st));
         k_finalize<<<1, 1, 0, st>>>(c->d_state.p, red + 8, 0);
@@ -583,7 +676,7 @@ static int run_pcg(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
     }
     // The iteration is captured once into a CUDA graph of GRAPH_ITERS iterations and replayed; kernels
     // past convergence (or past max_its) see done != 0 and return, so replaying whole graphs is exact.
-    constexpr int GRAPH_ITERS = 8;
+    constexpr int GRAPH_ITERS = (PC == 3) ? 1 : 8;  // a multilevel iteration is ~100 launches already
     const int key = PC * 2 + NORM + (c->sell_active ? 8 * (1 + c->sell_kind) : 0) + (peer ? 64 : 0);
     if (!c->cg_graph_exec || c->cg_graph_key != key || c->cg_graph_red != red) {
         if (c->cg_graph_exec) cudaGraphExecDestroy(c->cg_graph_exec);
@@ -603,7 +696,7 @@ static int run_pcg(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
         c->cg_graph_key = key;
         c->cg_graph_red = red;
     }
-    const int batch = o->check_every > 0 ? o->check_every : 64;
+    const int batch = o->check_every > 0 ? o->check_every : (PC == 3 ? 4 : 64);
     for (;;) {
         FS_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state.p, sizeof(CgState), cudaMemcpyDeviceToHost, st));
         FS_CUDA(c, cudaStreamSynchronize(st));
@@ -630,6 +723,37 @@ static int run_pcg(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
     return FS_OK;
 }
 
+// z = M^-1 r once, on device vectors in the local layout (tests of the multilevel preconditioner): r in d_r, z in d_z
+int pc_apply_mlrbm_once(fs_context *c)
+{
+    int rc = solver_prepare(c, FS_PC_MLRBM);
+    if (rc) return rc;
+    rc = ml_enqueue_apply(c, true, nullptr, FIN_RED, vec_grid(c));
+    if (rc) return rc;
+    FS_CUDA(c, cudaGetLastError());
+    return FS_OK;
+}
+
+// the SpMV kernel alone (no halo exchange, no reduction), reps launches between two events
+int spmv_kernel_time(fs_context *c, int reps, float *ms_per_launch)
+{
+    int rc = spmv_format_prepare(c);
+    if (rc) return rc;
+    rc = halo_exchange(c, c->d_b.p);
+    if (rc) return rc;
+    const int64_t o6 = 6 * c->own_lo;
+    launch_spmv<false>(c, c->d_b.p, c->d_q.p + o6, nullptr, nullptr, FIN_RED, nullptr, false);
+    FS_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < reps; i++) launch_spmv<false>(c, c->d_b.p, c->d_q.p + o6, nullptr, nullptr, FIN_RED, nullptr, false);
+    FS_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    FS_CUDA(c, cudaStreamSynchronize(c->stream));
+    FS_CUDA(c, cudaGetLastError());
+    float ms = 0.f;
+    FS_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    *ms_per_launch = ms / reps;
+    return FS_OK;
+}
+
 int solver_run(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
 {
     if (!c->rhs_ready) return fail(c, FS_ERR_STATE, "no right-hand side: set loads first");
@@ -642,7 +766,9 @@ int solver_run(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
     case 2: return run_pcg<1, 0>(c, o, info);
     case 3: return run_pcg<1, 1>(c, o, info);
     case 4: return run_pcg<2, 0>(c, o, info);
-    default: return run_pcg<2, 1>(c, o, info);
+    case 5: return run_pcg<2, 1>(c, o, info);
+    case 6: return run_pcg<3, 0>(c, o, info);
+    default: return fail(c, FS_ERR_ARG, "FS_PC_MLRBM tests convergence in the unpreconditioned norm only");
     }
 }
 

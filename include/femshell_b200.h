@@ -50,7 +50,11 @@ enum { FS_TRI3 = 3, FS_QUAD4 = 5 };
 enum { FS_DOF_FIRST_ENCOUNTER = 0, FS_DOF_NODE_ID = 1 };
 
 /* -pc_type none | jacobi | pbjacobi (PETSc flags passed through by the reference, doc/implementation.tex:68-72) */
-enum { FS_PC_NONE = 0, FS_PC_JACOBI = 1, FS_PC_BJACOBI6 = 2 };
+enum { FS_PC_NONE = 0, FS_PC_JACOBI = 1, FS_PC_BJACOBI6 = 2,
+       /* beyond the reference's documented options: one smoothed-aggregation multigrid cycle with rigid-body-mode
+        * coarse spaces on nested lattices over the mesh (fem_shell_b200/csrc/fs_mlpc.cuh).  Same Krylov method,
+        * same converged displacements, O(1000x) fewer iterations on large plates; unpreconditioned norm only. */
+       FS_PC_MLRBM = 3 };
 
 /* convergence norm: ||r||/||b|| or PETSc's default preconditioned ||M^-1 r||/||M^-1 b|| */
 enum { FS_NORM_UNPRECONDITIONED = 0, FS_NORM_PRECONDITIONED = 1 };
@@ -192,6 +196,24 @@ int fs_bench_spmv(fs_context *ctx, int reps, fs_solve_info *info);
 /* measured FP64 FMA peak of the device in TFLOP/s (dependent-FMA micro-benchmark): the roofline of the
  * element kernels, which MEASURED_PEAKS.json does not carry */
 int fs_bench_fp64_peak(fs_context *ctx, double *tflops);
+
+/* ---- FS_PC_MLRBM (fem_shell_b200/csrc/fs_mlpc.cuh; no counterpart in the reference) ---- */
+/* max_points: cap on the cells of the first lattice (default 4194304; its vectors are replicated on every rank and
+ * all-reduced once per iteration).  dense_points: a lattice with at most this many cells is inverted densely
+ * (default and maximum 200).  gamma: cycle index on the lattice levels, 1 = V, 2 = W (default).  Same values on
+ * all ranks. */
+int fs_set_ml_options(fs_context *ctx, int64_t max_points, int dense_points, int gamma);
+/* *levels = number of lattice levels (0 before the first use); cells[3*l..3*l+2] = cells per axis of lattice l
+ * (room for 3*14); weights[0] = estimate of lambda_max(D^-1 A) on the mesh, weights[1+l] = on lattice l (room
+ * for 15; 0 for the dense level); *setup_ms = device time of the last values set-up.  Arrays may be NULL. */
+int fs_get_ml_info(fs_context *ctx, int64_t *levels, int64_t *cells, double *weights, double *setup_ms);
+/* parity tests: copy of lattice level `level`: what = 0 the stencil (structure of arrays: entry (a,b) of the block
+ * coupling cell p to its neighbour in slot s at [(6s+b)*6n + 6p + a], slot digits base 3 over the active axes,
+ * offset = digit - 1), 1 the 36n pseudo-inverses of the diagonal blocks, 2 the dense inverse of the coarsest
+ * level.  out = NULL: only *count is set. */
+int fs_debug_ml_level(fs_context *ctx, int level, int what, double *out, int64_t capacity, int64_t *count);
+/* z = M^-1 r on host vectors in dof order (6 * n_dofnodes), single rank: for parity tests of the preconditioner */
+int fs_apply_mlrbm_host(fs_context *ctx, const double *r, double *z);
 
 /* host-only (no GPU): the node-block partition plan rank `rank` of `world` derives from the replicated
  * mesh -- owned range, local nodes, local elements, halo send lists and recv segments.  Two-call
