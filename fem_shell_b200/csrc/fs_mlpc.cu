@@ -220,12 +220,19 @@ k_f_post_finish(int64_t n6, const double *__restrict__ b, const double *__restri
 // ---------------------------------------------------------------------------------------------
 enum { LAT_RESID = 0, LAT_RSMOOTH = 1, LAT_PADD = 2, LAT_POST = 3 };
 
+#define LAT_STENCIL_LAUNCH(MODE, geom, grid, stream, ...)                                          \
+    do {                                                                                           \
+        if ((geom).ns == 9) k_lat_stencil<MODE, 9><<<grid, 192, 0, stream>>>(__VA_ARGS__);         \
+        else if ((geom).ns == 27) k_lat_stencil<MODE, 27><<<grid, 192, 0, stream>>>(__VA_ARGS__);  \
+        else k_lat_stencil<MODE, 3><<<grid, 192, 0, stream>>>(__VA_ARGS__);                        \
+    } while (0)
+
 // v = A in, then
 //   RESID    out1 = aux - v (aux null: zero)   out2 = D^+ out1
 //   RSMOOTH  out1 = aux - w v                  (out1 may alias aux)
 //   PADD     out1 (+)= in - w D^+ v            (flag: accumulate)
 //   POST     out1 = in + w D^+ (aux - v)       (out1 must not alias in)
-template <int MODE>
+template <int MODE, int NS>
 __global__ void __launch_bounds__(192)
 k_lat_stencil(const __grid_constant__ LatGeom g, const double *__restrict__ A, const double *__restrict__ dinv,
               const double *__restrict__ in, const double *aux, double *out1, double *__restrict__ out2, double omega,
@@ -241,12 +248,16 @@ k_lat_stencil(const __grid_constant__ LatGeom g, const double *__restrict__ A, c
         const int p = (int)(t / 6);
         int k[3];
         lat_unindex(g, p, k);
-        for (int s = 0; s < g.ns; s++) {
+        // NS is a compile-time constant: the slot loop unrolls, the offsets fold, and all 6*NS value loads are in
+        // flight together.  Slots that leave the lattice hold zeros (never written by the probing), so their
+        // neighbour is redirected to the cell itself instead of being skipped.
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
             int o[3];
             lat_stencil_off(g, s, o);
             const int kk[3] = {k[0] + o[0], k[1] + o[1], k[2] + o[2]};
-            if (kk[0] < 0 || kk[0] >= g.np[0] || kk[1] < 0 || kk[1] >= g.np[1] || kk[2] < 0 || kk[2] >= g.np[2]) continue;
-            const double *xin = in + 6 * (size_t)lat_index(g, kk);
+            const bool inside = kk[0] >= 0 && kk[0] < g.np[0] && kk[1] >= 0 && kk[1] < g.np[1] && kk[2] >= 0 && kk[2] < g.np[2];
+            const double *xin = in + 6 * (size_t)(inside ? lat_index(g, kk) : p);
             const double *as = A + (size_t)(6 * s) * n6 + t;
 #pragma unroll
             for (int b = 0; b < 6; b++) v += as[(size_t)b * n6] * xin[b];
@@ -466,57 +477,54 @@ __global__ void k_dense_symmetrize(int n, double *M)
     M[(size_t)j * n + i] = v;
 }
 
-// in-place Gauss-Jordan inversion of a symmetric positive semi-definite matrix by ONE thread block; pivots
-// below 1e-12 of the largest diagonal entry (empty cells) are skipped and their rows/columns zeroed, which
-// yields the inverse on the complement
-constexpr int ML_DENSE_MAX_N = 6 * ML_DENSE_MAX_POINTS;
-__global__ void __launch_bounds__(1024)
-k_dense_invert(int n, double *M)
+// In-place Gauss-Jordan inversion of a symmetric positive semi-definite matrix, one launch per pivot, one thread
+// block per row.  Pivots below 1e-12 of the largest diagonal entry (empty cells) are skipped and their rows and
+// columns zeroed, which yields the inverse on the complement.  The pivot row is read from a snapshot (rowin)
+// taken by the previous launch, so no block reads entries another block is overwriting; the block owning row
+// k+1 leaves the snapshot for the next launch in rowout.
+__global__ void __launch_bounds__(256)
+k_dense_diag_max(int n, const double *__restrict__ M, double *__restrict__ dmax, double *__restrict__ row0)
 {
-    __shared__ double colk[ML_DENSE_MAX_N], rowk[ML_DENSE_MAX_N];
-    __shared__ double s_dmax, s_piv;
-    __shared__ double s_part[32];
-    const int tid = threadIdx.x;
+    __shared__ double s_part[8];
     double dm = 0.0;
-    for (int i = tid; i < n; i += blockDim.x) dm = fmax(dm, M[(size_t)i * n + i]);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        dm = fmax(dm, M[(size_t)i * n + i]);
+        row0[i] = M[i];
+    }
     for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
-    if ((tid & 31) == 0) s_part[tid >> 5] = dm;
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = dm;
     __syncthreads();
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         double m = 0.0;
         for (int w = 0; w < (int)(blockDim.x >> 5); w++) m = fmax(m, s_part[w]);
-        s_dmax = m;
+        dmax[0] = m;
     }
-    __syncthreads();
-    const double tol = 1e-12 * s_dmax;
-    for (int k = 0; k < n; k++) {
-        if (tid == 0) s_piv = M[(size_t)k * n + k];
-        __syncthreads();
-        const double piv = s_piv;
-        if (!(piv > tol)) {
-            for (int j = tid; j < n; j += blockDim.x) {
-                M[(size_t)k * n + j] = 0.0;
-                M[(size_t)j * n + k] = 0.0;
-            }
-            __syncthreads();
-            continue;
-        }
+}
+
+__global__ void __launch_bounds__(256)
+k_dense_gj_step(int n, int k, double *__restrict__ M, const double *__restrict__ rowin, double *__restrict__ rowout,
+                const double *__restrict__ dmax)
+{
+    const int i = blockIdx.x;
+    double *Mi = M + (size_t)i * n;
+    const double piv = rowin[k];
+    const double ci = Mi[k];
+    __syncthreads();  // every thread holds the old M[i][k] before one of them overwrites it
+    if (!(piv > 1e-12 * dmax[0])) {
+        if (i == k) {
+            for (int j = threadIdx.x; j < n; j += blockDim.x) Mi[j] = 0.0;
+        } else if ((int)threadIdx.x == k % (int)blockDim.x) Mi[k] = 0.0;  // the thread that owns column k in the loops below
+    } else {
         const double ip = 1.0 / piv;
-        for (int j = tid; j < n; j += blockDim.x) {
-            colk[j] = M[(size_t)j * n + k];
-            rowk[j] = M[(size_t)k * n + j] * ip;
+        if (i == k) {
+            for (int j = threadIdx.x; j < n; j += blockDim.x) Mi[j] = (j == k) ? ip : rowin[j] * ip;
+        } else {
+            const double f = ci * ip;
+            for (int j = threadIdx.x; j < n; j += blockDim.x) Mi[j] = (j == k) ? -f : Mi[j] - f * rowin[j];
         }
-        __syncthreads();
-        for (int i = tid >> 5; i < n; i += (int)(blockDim.x >> 5)) {  // one warp per row: coalesced row updates
-            const double ci = colk[i];
-            double *Mi = M + (size_t)i * n;
-            if (i == k) {
-                for (int j = tid & 31; j < n; j += 32) Mi[j] = (j == k) ? ip : rowk[j];
-            } else {
-                for (int j = tid & 31; j < n; j += 32) Mi[j] = (j == k) ? -ci * ip : Mi[j] - ci * rowk[j];
-            }
-        }
-        __syncthreads();
+    }
+    if (i == k + 1) {  // each thread re-reads exactly the entries it wrote
+        for (int j = threadIdx.x; j < n; j += blockDim.x) rowout[j] = Mi[j];
     }
 }
 
@@ -691,8 +699,8 @@ static void lat_restrict_chain(fs_context *c, int l, const double *b, const doub
     MlLevelBuf &L = m.lat[l], &N = m.lat[l + 1];
     cudaStream_t st = c->stream;
     const int64_t n6 = 6 * (int64_t)L.g.n;
-    k_lat_stencil<LAT_RESID><<<nblk(n6, 192), 192, 0, st>>>(L.g, L.A.p, L.dinv.p, x, b, L.r.p, L.t.p, L.omega, 0, st_of(c), chk);
-    k_lat_stencil<LAT_RSMOOTH><<<nblk(n6, 192), 192, 0, st>>>(L.g, L.A.p, L.dinv.p, L.t.p, L.r.p, L.r.p, nullptr, L.omega, 0, st_of(c), chk);
+    LAT_STENCIL_LAUNCH(LAT_RESID, L.g, nblk(n6, 192), st, L.g, L.A.p, L.dinv.p, x, b, L.r.p, L.t.p, L.omega, 0, st_of(c), chk);
+    LAT_STENCIL_LAUNCH(LAT_RSMOOTH, L.g, nblk(n6, 192), st, L.g, L.A.p, L.dinv.p, L.t.p, L.r.p, L.r.p, nullptr, L.omega, 0, st_of(c), chk);
     k_lat_restrict<<<nblk(N.g.n, 128), 128, 0, st>>>(L.g, N.g, L.r.p, N.b.p, st_of(c), chk);
 }
 
@@ -703,7 +711,7 @@ static void lat_prolong_chain(fs_context *c, int l, const double *e, double *x, 
     cudaStream_t st = c->stream;
     const int64_t n6 = 6 * (int64_t)L.g.n;
     k_lat_prolong_t<<<nblk(L.g.n, 256), 256, 0, st>>>(L.g, N.g, e, L.t.p, st_of(c), chk);
-    k_lat_stencil<LAT_PADD><<<nblk(n6, 192), 192, 0, st>>>(L.g, L.A.p, L.dinv.p, L.t.p, nullptr, x, nullptr, L.omega, accumulate ? 1 : 0, st_of(c), chk);
+    LAT_STENCIL_LAUNCH(LAT_PADD, L.g, nblk(n6, 192), st, L.g, L.A.p, L.dinv.p, L.t.p, nullptr, x, nullptr, L.omega, accumulate ? 1 : 0, st_of(c), chk);
 }
 
 // one cycle on lattice level l for the right-hand side in lat[l].b; returns where the result lives
@@ -723,7 +731,7 @@ static const double *lat_cycle(fs_context *c, int l, int chk)
         const double *e = lat_cycle(c, l + 1, chk);
         lat_prolong_chain(c, l, e, L.x.p, true, chk);
     }
-    k_lat_stencil<LAT_POST><<<nblk(n6, 192), 192, 0, st>>>(L.g, L.A.p, L.dinv.p, L.x.p, L.b.p, L.xb.p, nullptr, L.omega, 0, st_of(c), chk);
+    LAT_STENCIL_LAUNCH(LAT_POST, L.g, nblk(n6, 192), st, L.g, L.A.p, L.dinv.p, L.x.p, L.b.p, L.xb.p, nullptr, L.omega, 0, st_of(c), chk);
     return L.xb.p;
 }
 
@@ -797,7 +805,7 @@ static int lat_lambda(fs_context *c, int l, double *lam)
     double est = 1.0;
     for (int it = 0; it < ML_POWER_ITS; it++) {
         // r = -A x ; t = -D^+ A x
-        k_lat_stencil<LAT_RESID><<<nblk(n6, 192), 192, 0, st>>>(L.g, L.A.p, L.dinv.p, L.x.p, nullptr, L.r.p, L.t.p, 0.0, 0, st_of(c), 0);
+        LAT_STENCIL_LAUNCH(LAT_RESID, L.g, nblk(n6, 192), st, L.g, L.A.p, L.dinv.p, L.x.p, nullptr, L.r.p, L.t.p, 0.0, 0, st_of(c), 0);
         k_norm2<256><<<grid, 256, 0, st>>>(n6, L.x.p, c->d_partials.p, c->d_counter.p, m.d_scalar.p);
         k_norm2<256><<<grid, 256, 0, st>>>(n6, L.t.p, c->d_partials.p, c->d_counter.p, m.d_scalar.p + 1);
         double h[2];
@@ -860,7 +868,10 @@ int ml_prepare(fs_context *c)
             FS_CUDA(c, cudaMemsetAsync(L.minv.p, 0, sizeof(double) * (size_t)n6 * n6, st));
             k_lat_to_dense<<<nblk(n6, 128), 128, 0, st>>>(g, L.A.p, L.minv.p);
             k_dense_symmetrize<<<nblk(n6 * n6, 256), 256, 0, st>>>((int)n6, L.minv.p);
-            k_dense_invert<<<1, 1024, 0, st>>>((int)n6, L.minv.p);
+            // scratch: level vectors of this (dense) level -- r, t hold the two pivot-row snapshots, x the diagonal maximum
+            k_dense_diag_max<<<1, 256, 0, st>>>((int)n6, L.minv.p, L.x.p, L.r.p);
+            for (int k = 0; k < (int)n6; k++)
+                k_dense_gj_step<<<(unsigned int)n6, 256, 0, st>>>((int)n6, k, L.minv.p, (k & 1) ? L.t.p : L.r.p, (k & 1) ? L.r.p : L.t.p, L.x.p);
             k_dense_symmetrize<<<nblk(n6 * n6, 256), 256, 0, st>>>((int)n6, L.minv.p);
             L.omega = 0.0;
             L.lambda = 0.0;
