@@ -39,6 +39,8 @@ def main():
         s1.assemble()
         i1 = s1.solve(rtol=1e-12, max_its=400000, pc=fsb.PC_BJACOBI6, warm_start=False)
         u1 = s1.solution()
+        m1 = s1.solve(rtol=1e-12, max_its=3000, pc=fsb.PC_MLRBM, warm_start=False)   # multilevel cycle, single GPU
+        assert np.linalg.norm(s1.solution() - uo) <= 1e-8 * np.linalg.norm(uo), name
         s1.close()
         its = {}
         # NVLink peer windows (kernels push halos / partial sums themselves) and the NCCL path
@@ -68,6 +70,11 @@ def main():
             assert abs(i1.iterations - info.iterations) <= max(3, i1.iterations // 50), (name, comm, i1.iterations, info.iterations)
             assert np.linalg.norm(u - u1) <= 1e-8 * np.linalg.norm(u1)
             its[comm] = info.iterations
+            # multilevel preconditioner across ranks: lattice levels replicated, restricted residual all-reduced
+            mi = s.solve(rtol=1e-12, max_its=3000, pc=fsb.PC_MLRBM, warm_start=False)
+            um = s.solution()
+            assert np.linalg.norm(um - uo) <= 1e-8 * np.linalg.norm(uo), (name, comm, "mlrbm")
+            assert abs(mi.iterations - m1.iterations) <= 2, (name, comm, mi.iterations, m1.iterations)
             # a second load case on the same matrix (stamps / mailboxes carry over between solves), Jacobi this time
             s.build_rhs(-2.5)
             s.solve(rtol=1e-12, max_its=400000, pc=fsb.PC_JACOBI, warm_start=True)
@@ -77,8 +84,8 @@ def main():
             dist.barrier()
         assert abs(its[fsb.COMM_PEER] - its[fsb.COMM_NCCL]) <= max(3, i1.iterations // 50), (name, its)
         if rank == 0:
-            print("dist ok %-6s world=%d iterations peer %d nccl %d (single %d) err %.2e"
-                  % (name, world, its[fsb.COMM_PEER], its[fsb.COMM_NCCL], i1.iterations, err), flush=True)
+            print("dist ok %-6s world=%d iterations peer %d nccl %d (single %d) multilevel %d (single %d) err %.2e"
+                  % (name, world, its[fsb.COMM_PEER], its[fsb.COMM_NCCL], i1.iterations, mi.iterations, m1.iterations, err), flush=True)
     dist.destroy_process_group()
 
 
