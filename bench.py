@@ -41,6 +41,18 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel, override):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/ncu_traffic.json; same c2 per-GPU workload), or the --traffic override"""
+    if override is not None:
+        return override
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return float(json.load(open(p))[kernel]["traffic"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region"""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -345,7 +357,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": spmv_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "bytes_per_launch": actual_b, "csr_equiv_bytes_per_launch": csr_b,
                      "csr_equiv_gbs": csr_b / (spmv_ms * 1e-3) / 1e9, "ms_per_launch": spmv_ms,
-                     "share_of_step": spmv_ms * (iters + 1) / ms_per_step, "traffic": args.traffic},
+                     "share_of_step": spmv_ms * (iters + 1) / ms_per_step, "traffic": ncu_traffic(spmv_kernel, args.traffic) if args.nodes == 1000 else args.traffic},
         "assembly_roofline": assembly_roofline,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(Fh.nbytes if world == 1 else 48 * n_own),
