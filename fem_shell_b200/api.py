@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "fs_create", "fs_destroy", "fs_last_error", "fs_get_stream", "fs_dist_unique_id", "fs_dist_init", "fs_set_comm_mode", "fs_get_comm_mode",
     "fs_set_material", "fs_set_quirks", "fs_set_dof_order", "fs_set_assembly_mode", "fs_set_spmv_format", "fs_get_spmv_format", "fs_set_mesh",
     "fs_set_nodal_loads", "fs_set_interface_loads", "fs_build_rhs", "fs_assemble", "fs_solve",
-    "fs_get_solution", "fs_solve_host", "fs_interface_nodes", "fs_step", "fs_commit_step", "fs_get_sizes",
+    "fs_get_solution", "fs_recover_resultants", "fs_solve_host", "fs_interface_nodes", "fs_step", "fs_commit_step", "fs_get_sizes",
     "fs_export_dof_order", "fs_export_csr", "fs_export_rhs", "fs_debug_element_matrices", "fs_spmv_host",
     "fs_bench_spmv", "fs_bench_fp64_peak", "fs_set_ml_options", "fs_get_ml_info", "fs_debug_ml_level", "fs_apply_mlrbm_host", "fs_partition_plan", "fs_meshgen", "fs_read_xda", "fs_read_forces", "fs_write_xda",
 ]
@@ -177,7 +177,7 @@ class FemShell:
         rc = self.lib.fs_create(C.byref(self.ctx), C.c_int(device))
         if rc:
             raise FemShellError(rc, "fs_create(device=%d) failed: no usable CUDA device (there is no CPU fallback)" % device)
-        self.n_nodes = 0
+        self.n_nodes = self.n_elem = 0
         self.world, self.rank = world, rank
         if world > 1:
             buf = (C.c_uint8 * 128).from_buffer_copy(bytes(nccl_id))
@@ -243,7 +243,7 @@ class FemShell:
     def set_mesh(self, xyz, etype, eptr, enodes, bc):
         xyz, etype, eptr, enodes = _f64(xyz), _i32(etype), _i64(eptr), _i32(enodes)
         bc = _i32(bc).reshape(-1, 3)
-        self.n_nodes = xyz.shape[0]
+        self.n_nodes, self.n_elem = xyz.shape[0], etype.size
         self._ck(self.lib.fs_set_mesh(self.ctx, C.c_int64(self.n_nodes), _p(xyz), C.c_int64(etype.size), _p(etype), _p(eptr),
                                       _p(enodes), C.c_int64(bc.shape[0]), _p(bc)))
 
@@ -280,6 +280,12 @@ class FemShell:
         sols = np.empty((self.n_nodes, 6)) if out is None else out
         self._ck(self.lib.fs_get_solution(self.ctx, _p(sols)))
         return sols
+
+    def recover_resultants(self):
+        """(n_elem, 6): membrane stresses and bending moments at the element centroids, local element axes"""
+        out = np.empty((self.n_elem, 6))
+        self._ck(self.lib.fs_recover_resultants(self.ctx, _p(out)))
+        return out
 
     def solve_host(self, F, sols, reassemble=False, rtol=1e-12, max_its=5000, pc=PC_JACOBI, norm_type=NORM_UNPRECONDITIONED,
                    warm_start=True, check_every=0, allow_not_converged=False) -> SolveInfo:

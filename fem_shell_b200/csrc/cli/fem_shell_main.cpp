@@ -136,7 +136,11 @@ int main(int argc, char **argv)
         }
         std::cout << "]" << std::endl << std::endl;
 
-        if (a.has_out && !fs::app::write_vtk(a.out + ".vtk", mesh, sols)) std::cerr << "could not write " << a.out << ".vtk\n";
+        if (a.has_out) {  // nodal displacements + element stress resultants (doc/shellelements.tex:1394-1403)
+            std::vector<double> res;
+            es.build_resultants(res);
+            if (!fs::app::write_vtk(a.out + ".vtk", mesh, sols, &res)) std::cerr << "could not write " << a.out << ".vtk\n";
+        }
         std::cout << "All done :)\n";
         return status == FS_OK ? 0 : 1;
     } catch (const fs::app::Error &e) {

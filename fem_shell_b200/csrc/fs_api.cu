@@ -476,6 +476,28 @@ int fs_get_solution(fs_context *c, double *sols)
     return FS_OK;
 }
 
+int fs_recover_resultants(fs_context *c, double *out)
+{
+    FS_CHECK_CTX(c);
+    if (!c->have_solution) return fail(c, FS_ERR_STATE, "no solution yet");
+    if (!out) return fail(c, FS_ERR_ARG, "null output");
+    FS_CUDA(c, cudaSetDevice(c->device));
+    int rc = halo_exchange(c, c->d_x.p);  // the elements of the cut rows read displacements of halo nodes
+    if (rc) return rc;
+    DevBuf<double> res;
+    FS_CUDA(c, res.alloc((size_t)6 * c->n_elem));
+    FS_CUDA(c, cudaMemsetAsync(res.p, 0, sizeof(double) * 6 * c->n_elem, c->stream));
+    rc = recover_resultants(c, c->d_x.p, res.p);
+    if (rc) return rc;
+    if (c->world > 1) {  // every element was written by exactly one rank (owner of its first node)
+        ncclResult_t r = nccl().AllReduce(res.p, res.p, 6 * c->n_elem, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream);
+        if (r != ncclSuccess) return fail(c, FS_ERR_COMM, std::string("ncclAllReduce: ") + nccl().GetErrorString(r));
+    }
+    FS_CUDA(c, cudaMemcpyAsync(out, res.p, sizeof(double) * 6 * c->n_elem, cudaMemcpyDeviceToHost, c->stream));
+    FS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FS_OK;
+}
+
 int fs_solve_host(fs_context *c, const double *F, int reassemble, const fs_solve_opts *opts, double *sols,
                   fs_solve_info *info)
 {

@@ -820,4 +820,163 @@ int debug_element_matrices(fs_context *c, double *out_host)
     return FS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// stress resultants at the element centroids.  The reference ships only the
+// formulas (doc/shellelements.tex:524 sigma = Dm B u, :1394-1403 M = Dp B w); they are evaluated here
+// with the same strain-displacement columns the stiffness kernels use (tri_bcols / quad_bcols, CST and
+// bilinear membrane) on the nodal unknowns rotated into the element frame (u_loc = T u_glob, the inverse
+// of fs.cpp:1094-1095).  Thread = element; the element is written by the rank owning its first node.
+// out[6*gid..] = sigma_xx, sigma_yy, sigma_xy, M_x, M_y, M_xy in local element axes.
+// ---------------------------------------------------------------------------------------------
+template <int J>
+__device__ __forceinline__ void tri_curv_add(const TriGeom &g, const TriGp &t, const double *w, double k[3])
+{
+    double Bc[3][3];
+    tri_bcols<J>(g, t, Bc);
+#pragma unroll
+    for (int r = 0; r < 3; r++) k[r] += Bc[r][0] * w[3 * J] + Bc[r][1] * w[3 * J + 1] + Bc[r][2] * w[3 * J + 2];
+}
+
+template <int K>
+__device__ __forceinline__ void quad_curv_add(const QuadH &h, double i00, double i01, double i10, double i11,
+                                              const double *w, double k[3])
+{
+    double Bc[3][3];
+    quad_bcols<K>(h, 0.0, 0.0, i00, i01, i10, i11, Bc);
+#pragma unroll
+    for (int r = 0; r < 3; r++) k[r] += Bc[r][0] * w[3 * K] + Bc[r][1] * w[3 * K + 1] + Bc[r][2] * w[3 * K + 2];
+}
+
+template <int NEN>
+__global__ void __launch_bounds__(128)
+k_recover_resultants(const int32_t *__restrict__ conn, const int32_t *__restrict__ gid, int64_t ne,
+                     const double *__restrict__ xyz, const double *__restrict__ x, int own_lo, int n_own,
+                     double *__restrict__ out)
+{
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    int nodes[NEN];
+#pragma unroll
+    for (int k = 0; k < NEN; k++) nodes[k] = conn[e * NEN + k];
+    if (nodes[0] < own_lo || nodes[0] >= own_lo + n_own) return;
+    double X[NEN * 3];
+#pragma unroll
+    for (int k = 0; k < NEN; k++)
+#pragma unroll
+        for (int d = 0; d < 3; d++) X[3 * k + d] = xyz[3 * (size_t)nodes[k] + d];
+    double T[3][3], um[2 * NEN], wp[3 * NEN], eps[3] = {0, 0, 0}, kap[3] = {0, 0, 0};
+    TriGeom tg;
+    QuadGeom qg;
+    if (NEN == 3) {
+        tri_geom(X, tg);
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) T[r][c] = tg.T[r][c];
+    } else {
+        quad_geom(X, qg);
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) T[r][c] = qg.T[r][c];
+    }
+#pragma unroll
+    for (int k = 0; k < NEN; k++) {
+        const double *u = x + 6 * (size_t)nodes[k];
+        double ul[3], tl[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            ul[r] = T[r][0] * u[0] + T[r][1] * u[1] + T[r][2] * u[2];
+            tl[r] = T[r][0] * u[3] + T[r][1] * u[4] + T[r][2] * u[5];
+        }
+        um[2 * k] = ul[0]; um[2 * k + 1] = ul[1];
+        wp[3 * k] = ul[2]; wp[3 * k + 1] = tl[0]; wp[3 * k + 2] = tl[1];
+    }
+    if (NEN == 3) {
+        const TriGeom &g = tg;
+        const double s = 1.0 / (2.0 * g.area);
+        const double px[3] = {g.y23 * s, g.y31 * s, g.y12 * s};      // fs.cpp:452-463
+        const double py[3] = {-g.x23 * s, -g.x31 * s, -g.x12 * s};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            eps[0] += px[k] * um[2 * k];
+            eps[1] += py[k] * um[2 * k + 1];
+            eps[2] += py[k] * um[2 * k] + px[k] * um[2 * k + 1];
+        }
+        const double C0 = g.x12 * g.x12 + g.y12 * g.y12, C1 = g.x31 * g.x31 + g.y31 * g.y31, C2 = g.x23 * g.x23 + g.y23 * g.y23;
+        const double mu1 = (C0 - C1) / C2, mu2 = (C2 - C0) / C1, mu3 = (C1 - C2) / C0;  // fs.cpp:702-704
+        TriGp t;
+        tri_gp_terms(1.0 / 3.0, 1.0 / 3.0, mu1, mu2, mu3, t);
+        double kt[3] = {0, 0, 0};
+        tri_curv_add<0>(g, t, wp, kt);
+        tri_curv_add<1>(g, t, wp, kt);
+        tri_curv_add<2>(g, t, wp, kt);
+        const double sc = 1.0 / (4.0 * g.area * g.area);  // Y of fs.cpp:578-588
+        const double y20 = -2.0 * g.x23 * g.y23;
+        const double y21 = (c_el.quirks & FS_Q_Y21) ? -2.0 * g.x31 * g.x31 : -2.0 * g.x31 * g.y31;
+        const double y22 = -g.x23 * g.y31 - g.x31 * g.y23;
+        kap[0] = (g.y23 * g.y23 * kt[0] + g.y31 * g.y31 * kt[1] + g.y23 * g.y31 * kt[2]) * sc;
+        kap[1] = (g.x23 * g.x23 * kt[0] + g.x31 * g.x31 * kt[1] + g.x31 * g.x23 * kt[2]) * sc;
+        kap[2] = (y20 * kt[0] + y21 * kt[1] + y22 * kt[2]) * sc;
+    } else {
+        const QuadGeom &g = qg;
+        const double dr[4] = {-0.25, 0.25, 0.25, -0.25}, ds[4] = {-0.25, -0.25, 0.25, 0.25};  // fs.cpp:490-497 at r = s = 0
+        double j00 = 0, j01 = 0, j10 = 0, j11 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            j00 += dr[k] * g.lx[k]; j01 += dr[k] * g.ly[k];
+            j10 += ds[k] * g.lx[k]; j11 += ds[k] * g.ly[k];
+        }
+        const double di = 1.0 / (j00 * j11 - j01 * j10);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const double px = (j11 * dr[k] - j01 * ds[k]) * di, py = (-j10 * dr[k] + j00 * ds[k]) * di;
+            eps[0] += px * um[2 * k];
+            eps[1] += py * um[2 * k + 1];
+            eps[2] += py * um[2 * k] + px * um[2 * k + 1];
+        }
+        QuadH h;  // fs.cpp:613-621
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const double dx = g.dx[k], dy = g.dy[k];
+            const double si = 1.0 / (dx * dx + dy * dy);
+            h.a[k] = -dx * si;
+            h.b[k] = 0.75 * dx * dy * si;
+            h.c[k] = (0.25 * dx * dx - 0.5 * dy * dy) * si;
+            h.d[k] = -dy * si;
+            h.e[k] = (0.25 * dy * dy - 0.5 * dx * dx) * si;
+        }
+        const double p00 = 0.25 * (-g.dx[0] + g.dx[2]), p01 = 0.25 * (-g.dy[0] + g.dy[2]);  // fs.cpp:641-645 at the centre
+        const double p10 = 0.25 * (-g.dx[1] + g.dx[3]), p11 = 0.25 * (-g.dy[1] + g.dy[3]);
+        const double dp = 1.0 / (p00 * p11 - p01 * p10);
+        const double i00 = p11 * dp, i01 = -p01 * dp, i10 = -p10 * dp, i11 = p00 * dp;
+        quad_curv_add<0>(h, i00, i01, i10, i11, wp, kap);
+        quad_curv_add<1>(h, i00, i01, i10, i11, wp, kap);
+        quad_curv_add<2>(h, i00, i01, i10, i11, wp, kap);
+        quad_curv_add<3>(h, i00, i01, i10, i11, wp, kap);
+    }
+    double *o = out + 6 * (size_t)gid[e];
+    o[0] = c_el.dm11 * eps[0] + c_el.dm12 * eps[1];
+    o[1] = c_el.dm12 * eps[0] + c_el.dm11 * eps[1];
+    o[2] = c_el.dm33 * eps[2];
+    o[3] = c_el.dp11 * kap[0] + c_el.dp12 * kap[1];
+    o[4] = c_el.dp12 * kap[0] + c_el.dp11 * kap[1];
+    o[5] = c_el.dp33 * kap[2];
+}
+
+// d_out: 6*n_elem doubles, zero-filled by the caller; d_x: solution in the local vector layout with valid halos
+int recover_resultants(fs_context *c, const double *d_x, double *d_out)
+{
+    int rc = upload_element_constants(c);
+    if (rc) return rc;
+    if (c->n_tri)
+        k_recover_resultants<3><<<nblk(c->n_tri, 128), 128, 0, c->stream>>>(c->d_tri.p, c->d_tri_gid.p, c->n_tri, c->d_xyz.p, d_x,
+                                                                             (int)c->own_lo, (int)c->n_own, d_out);
+    if (c->n_quad)
+        k_recover_resultants<4><<<nblk(c->n_quad, 128), 128, 0, c->stream>>>(c->d_quad.p, c->d_quad_gid.p, c->n_quad, c->d_xyz.p, d_x,
+                                                                              (int)c->own_lo, (int)c->n_own, d_out);
+    FS_CUDA(c, cudaGetLastError());
+    return FS_OK;
+}
+
 }  // namespace fs

@@ -243,6 +243,7 @@ int assemble_values(fs_context *c, float *ms);
 int build_gather_schedule(fs_context *c);
 int build_rhs(fs_context *c, double scale);
 int debug_element_matrices(fs_context *c, double *out_host);
+int recover_resultants(fs_context *c, const double *d_x, double *d_out);
 
 // solver.cu
 int solver_query_occupancy(fs_context *c);

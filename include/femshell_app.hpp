@@ -114,6 +114,13 @@ public:
         check(fs_get_solution(ctx_, sols.data()));
     }
 
+    // membrane stresses and bending moments at the element centroids (fs_recover_resultants): 6 per element
+    void build_resultants(std::vector<double> &res)
+    {
+        res.resize(6 * mesh_.n_elem());
+        check(fs_recover_resultants(ctx_, res.data()));
+    }
+
     float assemble_ms() const { return assemble_ms_; }
 
     void check(int rc)
@@ -133,7 +140,9 @@ private:
 
 // legacy-VTK (ASCII, unstructured grid) writer of the displaced mesh with the six nodal fields; stands in for the
 // reference's ExodusII / VTK output (fs.cpp:1240-1251, fsp.cpp:1526-1561), whose libraries are not available here
-inline bool write_vtk(const std::string &path, const Mesh &m, const std::vector<double> &sols)
+// `resultants` (optional, 6 per element from fs_recover_resultants) is written as cell data
+inline bool write_vtk(const std::string &path, const Mesh &m, const std::vector<double> &sols,
+                      const std::vector<double> *resultants = nullptr)
 {
     FILE *f = fopen(path.c_str(), "w");
     if (!f) return false;
@@ -154,6 +163,14 @@ inline bool write_vtk(const std::string &path, const Mesh &m, const std::vector<
     for (int v = 0; v < 6; v++) {
         fprintf(f, "SCALARS %s double 1\nLOOKUP_TABLE default\n", names[v]);
         for (int64_t i = 0; i < nn; i++) fprintf(f, "%.17g\n", sols[6 * i + v]);
+    }
+    if (resultants && (int64_t)resultants->size() == 6 * ne) {
+        static const char *rnames[6] = {"sigma_xx", "sigma_yy", "sigma_xy", "M_x", "M_y", "M_xy"};
+        fprintf(f, "CELL_DATA %lld\n", (long long)ne);
+        for (int v = 0; v < 6; v++) {
+            fprintf(f, "SCALARS %s double 1\nLOOKUP_TABLE default\n", rnames[v]);
+            for (int64_t e = 0; e < ne; e++) fprintf(f, "%.17g\n", (*resultants)[6 * e + v]);
+        }
     }
     fclose(f);
     return true;

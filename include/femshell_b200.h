@@ -154,6 +154,13 @@ int fs_assemble(fs_context *ctx, float *ms);
 int fs_solve(fs_context *ctx, const fs_solve_opts *opts, fs_solve_info *info);
 /* replaces build_solution_vector (fs.cpp:140-141): sols[6*node_id+var]; every rank gets the full vector */
 int fs_get_solution(fs_context *ctx, double *sols);
+/* stress resultants of the current solution at the element centroids, in the local axes of each element
+ * (x along fs.cpp:318 / :364, z = element normal): out[6*e + k] = sigma_xx, sigma_yy, sigma_xy (membrane stress,
+ * sigma = Dm B u, doc/shellelements.tex:524) and M_x, M_y, M_xy (bending moments per unit length, M = Dp B w,
+ * doc/shellelements.tex:1394-1403), e = element id of fs_set_mesh.  The reference states these formulas but
+ * ships no code for them; B is the element's own strain-displacement operator, so the
+ * curvature sign follows it: Specht Tri-3 +d2w, DKQ Quad-4 -d2w.  Every rank receives all n_elem rows. */
+int fs_recover_resultants(fs_context *ctx, double *out /* 6*n_elem */);
 /* equation_systems.solve() + build_solution_vector in one call with HOST buffers, as the
  * reference's coupling loop does per iteration (fsp.cpp:271-274).  F may be NULL (keep loads).
  * reassemble != 0 re-runs the values pass like the reference does on every solve. */

@@ -621,6 +621,124 @@ void fso_element_parts(int type, const double *xyz, double nu, double em, double
 }
 
 /* ------------------------------------------------------------------ */
+/* Stress resultants at the element centroid. */
+/* NOT in the reference code: the thesis only states the formulas,     */
+/*   membrane  sigma = Dm B u      doc/shellelements.tex:524           */
+/*   bending   M = Dp B(x,y) w     doc/shellelements.tex:1394-1403     */
+/* They are evaluated with the element's own strain-displacement       */
+/* operators, i.e. exactly the B of calc_plane / calc_plate above      */
+/* (Tri-3: Y * B~ of fs.cpp:578-595 at L1=L2=1/3; Quad-4: Bm*G of      */
+/* fs.cpp:490-529 and evalBQuad at xi=eta=0, plain 2x2 determinant),   */
+/* on the nodal displacements rotated into the element frame with the  */
+/* transformation of fs.cpp:378-384 (u_loc = T u_glob, the inverse of  */
+/* fs.cpp:1094-1095).  sols[6*node+var] as printed by fs.cpp:163-169.  */
+/* out[6e..6e+5] = sigma_xx, sigma_yy, sigma_xy, M_x, M_y, M_xy in the */
+/* local axes of element e.                                            */
+/* ------------------------------------------------------------------ */
+void fso_recover_resultants(const double *xyz, int64_t n_elem, const int32_t *etype,
+                            const int64_t *eptr, const int32_t *enodes, double nu, double em,
+                            double thickness, int quirks, const double *sols, double *out)
+{
+    double Dm[9], Dp[9];
+    fso_material(nu, em, thickness, Dm, Dp);
+    for (int64_t e = 0; e < n_elem; e++) {
+        int type = etype[e];
+        int nen = (int)(eptr[e + 1] - eptr[e]);
+        const int32_t *en = enodes + eptr[e];
+        double X[12], trafo[9], loc[12], dphi[8], area;
+        for (int i = 0; i < nen; i++)
+            for (int d = 0; d < 3; d++) X[3 * i + d] = xyz[3 * (int64_t)en[i] + d];
+        init_element(type, X, trafo, loc, dphi, &area);
+        double um[8], wp[12]; /* membrane (u,v) and plate (w,tx,ty) unknowns, node-major */
+        for (int i = 0; i < nen; i++) {
+            const double *g = sols + 6 * (int64_t)en[i];
+            double ul[3], tl[3];
+            mm(3, 3, 1, trafo, g, ul);
+            mm(3, 3, 1, trafo, g + 3, tl);
+            um[2 * i + 0] = ul[0];
+            um[2 * i + 1] = ul[1];
+            wp[3 * i + 0] = ul[2];
+            wp[3 * i + 1] = tl[0];
+            wp[3 * i + 2] = tl[1];
+        }
+        double eps[3], kap[3];
+        if (type == FSO_TRI3) {
+            double x12 = dphi[0], y12 = dphi[1], x31 = dphi[2], y31 = dphi[3], x23 = dphi[4],
+                   y23 = dphi[5];
+            double B[18];
+            memset(B, 0, sizeof B);
+            B[0 * 6 + 0] = y23;  B[0 * 6 + 2] = y31;  B[0 * 6 + 4] = y12;
+            B[1 * 6 + 1] = -x23; B[1 * 6 + 3] = -x31; B[1 * 6 + 5] = -x12;
+            B[2 * 6 + 0] = -x23; B[2 * 6 + 1] = y23;
+            B[2 * 6 + 2] = -x31; B[2 * 6 + 3] = y31;
+            B[2 * 6 + 4] = -x12; B[2 * 6 + 5] = y12;
+            double s = 1.0 / (2.0 * area);
+            for (int i = 0; i < 18; i++) B[i] *= s;
+            mm(3, 6, 1, B, um, eps);
+            double side[3], Bt[27], Y[9], kt[3];
+            for (int i = 0; i < 3; i++)
+                side[i] = pow(dphi[2 * i], 2.0) + pow(dphi[2 * i + 1], 2.0);
+            eval_b_tri(side, 1.0 / 3.0, 1.0 / 3.0, dphi, Bt);
+            Y[0] = pow(y23, 2.0); Y[1] = pow(y31, 2.0); Y[2] = y23 * y31;
+            Y[3] = pow(x23, 2.0); Y[4] = pow(x31, 2.0); Y[5] = x31 * x23;
+            Y[6] = -2.0 * x23 * y23;
+            Y[7] = (quirks & FSO_QUIRK_Y21) ? -2.0 * x31 * x31 : -2.0 * x31 * y31;
+            Y[8] = -x23 * y31 - x31 * y23;
+            double sc = 1.0 / (4.0 * pow(area, 2.0));
+            for (int i = 0; i < 9; i++) Y[i] *= sc;
+            mm(3, 9, 1, Bt, wp, kt);
+            mm(3, 3, 1, Y, kt, kap);
+        } else {
+            double dhdr[4] = {-0.25, 0.25, 0.25, -0.25}, dhds[4] = {-0.25, -0.25, 0.25, 0.25};
+            double J[4] = {0, 0, 0, 0};
+            for (int i = 0; i < 4; i++) {
+                J[0] += dhdr[i] * loc[0 * 4 + i];
+                J[1] += dhdr[i] * loc[1 * 4 + i];
+                J[2] += dhds[i] * loc[0 * 4 + i];
+                J[3] += dhds[i] * loc[1 * 4 + i];
+            }
+            double di = 1.0 / (J[0] * J[3] - J[1] * J[2]);
+            double Bm[12], G[32], B[24];
+            memset(Bm, 0, sizeof Bm);
+            memset(G, 0, sizeof G);
+            Bm[0 * 4 + 0] = J[3];  Bm[0 * 4 + 1] = -J[1];
+            Bm[1 * 4 + 2] = -J[2]; Bm[1 * 4 + 3] = J[0];
+            Bm[2 * 4 + 0] = -J[2]; Bm[2 * 4 + 1] = J[0];
+            Bm[2 * 4 + 2] = J[3];  Bm[2 * 4 + 3] = -J[1];
+            for (int i = 0; i < 12; i++) Bm[i] *= di;
+            for (int i = 0; i < 4; i++) {
+                G[0 * 8 + 2 * i] = dhdr[i];
+                G[1 * 8 + 2 * i] = dhds[i];
+                G[2 * 8 + 1 + 2 * i] = dhdr[i];
+                G[3 * 8 + 1 + 2 * i] = dhds[i];
+            }
+            mm(3, 4, 8, Bm, G, B);
+            mm(3, 8, 1, B, um, eps);
+            double H[20], Jp[4], Jinv[4], Bp[36];
+            for (int i = 0; i < 4; i++) {
+                double dx = dphi[2 * i], dy = dphi[2 * i + 1];
+                double sd = pow(dx, 2.0) + pow(dy, 2.0);
+                H[0 * 4 + i] = -dx / sd;
+                H[1 * 4 + i] = 0.75 * dx * dy / sd;
+                H[2 * 4 + i] = (0.25 * pow(dx, 2.0) - 0.5 * pow(dy, 2.0)) / sd;
+                H[3 * 4 + i] = -dy / sd;
+                H[4 * 4 + i] = (0.25 * pow(dy, 2.0) - 0.5 * pow(dx, 2.0)) / sd;
+            }
+            Jp[0] = 0.25 * (-dphi[0] + dphi[4]);
+            Jp[1] = 0.25 * (-dphi[1] + dphi[5]);
+            Jp[2] = 0.25 * (-dphi[2] + dphi[6]);
+            Jp[3] = 0.25 * (-dphi[3] + dphi[7]);
+            double dp = 1.0 / (Jp[0] * Jp[3] - Jp[1] * Jp[2]);
+            Jinv[0] = Jp[3] * dp; Jinv[1] = -Jp[1] * dp; Jinv[2] = -Jp[2] * dp; Jinv[3] = Jp[0] * dp;
+            eval_b_quad(H, 0.0, 0.0, Jinv, Bp);
+            mm(3, 12, 1, Bp, wp, kap);
+        }
+        mm(3, 3, 1, Dm, eps, out + 6 * e);
+        mm(3, 3, 1, Dp, kap, out + 6 * e + 3);
+    }
+}
+
+/* ------------------------------------------------------------------ */
 /* DOF numbering (libMesh DofMap, var-major distribution, one variable */
 /* group of six FIRST/LAGRANGE variables): node bases are handed out   */
 /* in first-encounter order over elements in id order, nodes in local  */

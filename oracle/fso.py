@@ -328,3 +328,15 @@ def direct_solve(mesh: Mesh, sysm: System):
 
 def max_threads():
     return int(lib().fso_max_threads())
+
+
+def recover_resultants(mesh: Mesh, sols, nu, em, t, quirks=QUIRKS_REFERENCE):
+    """membrane stresses and bending moments at the element centroids, local element axes
+    (fso_recover_resultants; thesis doc/shellelements.tex:524 and :1394-1403) -> (n_elem, 6)"""
+    out = np.zeros(6 * mesh.n_elem)
+    xyz = np.ascontiguousarray(mesh.xyz, np.float64)
+    s = np.ascontiguousarray(sols, np.float64).reshape(-1)
+    assert s.size == 6 * mesh.n_nodes
+    lib().fso_recover_resultants(_p(xyz), C.c_int64(mesh.n_elem), _p(mesh.etype), _p(mesh.eptr), _p(mesh.enodes),
+                                 C.c_double(nu), C.c_double(em), C.c_double(t), C.c_int(quirks), _p(s), _p(out))
+    return out.reshape(-1, 6)

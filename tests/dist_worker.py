@@ -70,6 +70,10 @@ def main():
             assert abs(i1.iterations - info.iterations) <= max(3, i1.iterations // 50), (name, comm, i1.iterations, info.iterations)
             assert np.linalg.norm(u - u1) <= 1e-8 * np.linalg.norm(u1)
             its[comm] = info.iterations
+            # stress resultants: elements of the cut rows read halo displacements; every rank gets all rows
+            res = s.recover_resultants()
+            ro = fso.recover_resultants(om, u, nu, E, t)
+            assert np.abs(res - ro).max() <= 1e-10 * np.abs(ro).max(), (name, comm, "resultants")
             # multilevel preconditioner across ranks: lattice levels replicated, restricted residual all-reduced
             mi = s.solve(rtol=1e-12, max_its=3000, pc=fsb.PC_MLRBM, warm_start=False)
             um = s.solution()

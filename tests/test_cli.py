@@ -75,6 +75,7 @@ def test_fem_shell_cli_reproduces_thesis_values(fso, ref_meshes, tmp_path):
         assert os.path.exists(base + ".vtk")
         vtk = open(base + ".vtk").read()
         assert "POINTS %d double" % mesh.n_nodes in vtk and "SCALARS tz double 1" in vtk
+        assert "CELL_DATA %d" % mesh.n_elem in vtk and "SCALARS M_xy double 1" in vtk
 
 
 @pytest.mark.gpu

@@ -245,6 +245,28 @@ def test_mixed_folded_cantilever_solution(fso, fsb):
         assert np.linalg.norm(u - uo) <= 1e-8 * np.linalg.norm(uo)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("quirks", [3, 0])
+def test_stress_resultants_match_oracle(fso, fsb, quirks):
+    """fs_recover_resultants against the oracle's restatement on the SAME displacements:
+    mixed skewed folded cantilever (both element types, rotated frames, quirks on and off) and a meshGen plate"""
+    cases = [(meshes.folded_cantilever(skew=0.35), 0.3, 1e4, 0.25), (meshes.folded_cantilever(skew=0.0), 0.3, 1e4, 0.25),
+             (fsb.meshgen("t", 16, 16, 0, 0, 10, 10, (1, 1, 1, 1), 300.0, 2, 1), 0.3, 1e7, 0.5),
+             (fsb.meshgen("q", 12, 9, 0, 0, 10, 7, (0, 1, 0, 1), 300.0, 2, 1), 0.3, 1e7, 0.5)]
+    for m, nu, E, t in cases:
+        s = gpu_system(fsb, m, nu, E, t, quirks=quirks, loads=m["forces"])
+        with pytest.raises(fsb.FemShellError):
+            s.recover_resultants()          # no solution yet
+        s.solve(rtol=1e-12, max_its=400000, pc=fsb.PC_BJACOBI6)
+        u = s.solution()
+        res = s.recover_resultants()
+        ro = fso.recover_resultants(as_fso_mesh(fso, m), u, nu, E, t, quirks=quirks)
+        assert res.shape == ro.shape
+        for cols in (slice(0, 3), slice(3, 6)):   # bit-level agreement is not required: FMA contraction differs
+            assert np.abs(res[:, cols] - ro[:, cols]).max() <= 1e-10 * np.abs(ro[:, cols]).max()
+        s.close()
+
+
 def test_max_its_and_error_paths(fso, fsb):
     m, nu, E, t = CASES["quad24"](fsb)
     s = gpu_system(fsb, m, nu, E, t, loads=m["forces"])
