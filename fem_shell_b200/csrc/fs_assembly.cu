@@ -468,9 +468,10 @@ k_assemble_colored(const int32_t *__restrict__ conn, const int32_t *__restrict__
 // values pass, row gather ("owner computes").  A WARP owns a run of block rows whose CSR values fit
 // in its slice of shared memory.  Lane = one (element, node row I) incidence of those rows; it forms
 // its row slice in registers (run-time I, selects only, so lanes with different I do not diverge),
-// then the incidences of a row add their 6x6 blocks into shared memory in a fixed order (round r =
-// r-th incident element of the row, triangles first, then by element id; rows are disjoint, so a
-// round needs no atomics and only __syncwarp).  Finally the warp streams its rows to HBM: every CSR
+// then all lanes add their j-th 6x6 block into shared memory in step j; incidences of one row that
+// would meet in a slot at the same step are separated into phases by the host schedule (one phase
+// on structured quads; rows are disjoint, so a step needs no atomics and only __syncwarp; the order
+// of the sums is fixed by the mesh).  Finally the warp streams its rows to HBM: every CSR
 // value is written exactly once, coalesced, and never read.  Warps never wait for each other.
 // ---------------------------------------------------------------------------------------------
 constexpr int GATHER_WARPS = 4;                       // warps (= chunks) per thread block
@@ -518,6 +519,8 @@ __device__ __forceinline__ void gather_emit(const double T[3][3], double Km[4][2
     }
 }
 
+// KINDS: 1 = the mesh has only Quad-4, 2 = only Tri-3, 3 = both (a pure mesh does not carry the other path's code)
+template <int KINDS>
 __global__ void __launch_bounds__(GATHER_THREADS, 2)
 k_assemble_gather(const GatherChunk *__restrict__ chunks, int n_chunks, const int32_t *__restrict__ g_elem,
                   const int32_t *__restrict__ g_meta, const int32_t *__restrict__ tri,
@@ -532,21 +535,26 @@ k_assemble_gather(const GatherChunk *__restrict__ chunks, int n_chunks, const in
     if (ci >= n_chunks) return;
     double *sv = sv_all + (size_t)warp * GATHER_WARP_VALS;
     const GatherChunk ch = chunks[ci];
-    for (int i = lane; i < ch.val_count; i += 32) sv[i] = 0.0;
+    {
+        double2 *z2 = reinterpret_cast<double2 *>(sv);
+#pragma unroll 4
+        for (int i = lane; i < ch.val_count / 2; i += 32) z2[i] = make_double2(0.0, 0.0);
+    }
 
     int e = -1, meta = 0;
     if (lane < ch.n_threads) {
         e = g_elem[ch.thread_off + lane];
         meta = g_meta[ch.thread_off + lane];
     }
-    const int I = meta & 3, is_quad = (meta >> 2) & 1, round = (meta >> 3) & 31;
+    const int I = meta & 3, round = (meta >> 3) & 31;
+    const int is_quad = KINDS == 3 ? (meta >> 2) & 1 : (KINDS == 1);
     double Km[4][2][2], Kp[4][3][3], T[3][3];
     int slot[4];
     unsigned mcol[4];
     double *srow = sv;
     int L = 0;
     if (e >= 0) {
-        if (is_quad) {
+        if ((KINDS & 1) && is_quad) {
             double X[12];
             int row = 0;
 #pragma unroll
@@ -568,7 +576,7 @@ k_assemble_gather(const GatherChunk *__restrict__ chunks, int n_chunks, const in
                 for (int c2 = 0; c2 < 3; c2++) T[r][c2] = g.T[r][c2];
             quad_membrane_row_rt(g, I, Km);
             quad_plate_row_rt(g, I, Kp);
-        } else {
+        } else if (KINDS & 2) {
             double X[9];
             int row = 0;
 #pragma unroll
@@ -595,13 +603,14 @@ k_assemble_gather(const GatherChunk *__restrict__ chunks, int n_chunks, const in
     }
     __syncwarp();
     // a chunk holds quads in its leading lanes and triangles behind them (both only in mixed meshes)
-    const bool any_quad = __any_sync(0xffffffffu, e >= 0 && is_quad);
-    const bool any_tri = __any_sync(0xffffffffu, e >= 0 && !is_quad);
+    const bool any_quad = (KINDS & 1) && __any_sync(0xffffffffu, e >= 0 && is_quad);
+    const bool any_tri = (KINDS & 2) && __any_sync(0xffffffffu, e >= 0 && !is_quad);
     if (any_quad) gather_emit<4>(T, Km, Kp, I, slot, mcol, srow, L, e >= 0 && is_quad, round, ch.n_rounds);
     if (any_tri) gather_emit<3>(T, Km, Kp, I, slot, mcol, srow, L, e >= 0 && !is_quad, round, ch.n_rounds);
     // stream the finished rows out (contiguous in the CSR value array)
     double2 *out = reinterpret_cast<double2 *>(vals + 36 * (size_t)nptr[ch.row0]);
     const double2 *s2 = reinterpret_cast<const double2 *>(sv);
+#pragma unroll 4
     for (int i = lane; i < ch.val_count / 2; i += 32) __stcs(out + i, s2[i]);
 }
 
@@ -635,10 +644,37 @@ int build_gather_schedule(fs_context *c)
         for (int k = 0; k < 3; k++) { int p = tri[3 * e + k] - own_lo; if (p >= 0 && p < n_own) inc[fill[p]++] = {(int32_t)p, tgid[e], (int32_t)e, 0, (uint8_t)k}; }
     for (int64_t e = 0; e < nq; e++)
         for (int k = 0; k < 4; k++) { int p = quad[4 * e + k] - own_lo; if (p >= 0 && p < n_own) inc[fill[p]++] = {(int32_t)p, qgid[e], (int32_t)e, 1, (uint8_t)k}; }
-    for (int64_t p = 0; p < n_own; p++)  // fixed summation order inside a row: triangles first, then by element id
+    // Phases.  All lanes emit block j (the element's j-th node column) in the same step, so two incidences of
+    // one row may share a step iff they never meet in a slot at the same j, i.e. no node sits at the same local
+    // index in both elements.  On a structured Quad-4 mesh the four elements around a node see every shared
+    // neighbour under different local indices -> one phase; meshGen's triangle pairs share their hypotenuse end
+    // node at the same index -> a few phases.  Greedy colouring in a fixed order (triangles first, then by
+    // element id) keeps the summation order of every CSR value a function of the mesh alone.
+    std::vector<uint8_t> phase(inc.size(), 0);
+    for (int64_t p = 0; p < n_own; p++) {
         std::sort(inc.begin() + cnt[p], inc.begin() + cnt[p + 1], [](const Inc &a, const Inc &b) {
             return a.type != b.type ? a.type < b.type : a.gid < b.gid;
         });
+        for (int k = cnt[p]; k < cnt[p + 1]; k++) {
+            const int nen = inc[k].type ? 4 : 3;
+            const int32_t *ek = inc[k].type ? &quad[4 * (int64_t)inc[k].eidx] : &tri[3 * (int64_t)inc[k].eidx];
+            unsigned used = 0;
+            for (int m = cnt[p]; m < k; m++) {
+                if (inc[m].type != inc[k].type) continue;  // quads and triangles are emitted one after the other
+                const int32_t *em = inc[m].type ? &quad[4 * (int64_t)inc[m].eidx] : &tri[3 * (int64_t)inc[m].eidx];
+                bool clash = false;
+                for (int j = 0; j < nen; j++) clash |= ek[j] == em[j];
+                if (clash) used |= 1u << phase[m];
+            }
+            int ph = 0;
+            while (used & (1u << ph)) ph++;
+            if (ph > 31) {  // more than 32 mutually clashing elements at one node: leave this mesh to the coloured pass
+                c->gather_unavailable = true;
+                return FS_OK;
+            }
+            phase[k] = (uint8_t)ph;
+        }
+    }
 
     std::vector<GatherChunk> chunks;
     std::vector<int32_t> g_elem, g_meta;
@@ -652,7 +688,7 @@ int build_gather_schedule(fs_context *c)
             if (t2 > 32 || v2 > GATHER_WARP_VALS) break;
             threads = t2;
             vals = v2;
-            rounds = std::max(rounds, cnt[r1 + 1] - cnt[r1]);
+            for (int k = cnt[r1]; k < cnt[r1 + 1]; k++) rounds = std::max(rounds, (int)phase[k] + 1);
             r1++;
         }
         if (r1 == row) {  // a single row does not fit a warp: leave this mesh to the coloured pass
@@ -671,7 +707,7 @@ int build_gather_schedule(fs_context *c)
                 for (int k = cnt[p]; k < cnt[p + 1]; k++)
                     if (inc[k].type == pass) {
                         g_elem.push_back(inc[k].eidx);
-                        g_meta.push_back(inc[k].I | (inc[k].type << 2) | ((k - cnt[p]) << 3));
+                        g_meta.push_back(inc[k].I | (inc[k].type << 2) | ((int)phase[k] << 3));
                     }
         chunks.push_back(ch);
         row = r1;
@@ -683,7 +719,10 @@ int build_gather_schedule(fs_context *c)
     FS_CUDA(c, cudaMemcpy(c->d_g_chunks.p, chunks.data(), sizeof(GatherChunk) * chunks.size(), cudaMemcpyHostToDevice));
     FS_CUDA(c, cudaMemcpy(c->d_g_elem.p, g_elem.data(), sizeof(int32_t) * g_elem.size(), cudaMemcpyHostToDevice));
     FS_CUDA(c, cudaMemcpy(c->d_g_meta.p, g_meta.data(), sizeof(int32_t) * g_meta.size(), cudaMemcpyHostToDevice));
-    FS_CUDA(c, cudaFuncSetAttribute(k_assemble_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, GATHER_WARPS * GATHER_WARP_VALS * (int)sizeof(double)));
+    constexpr int smem = GATHER_WARPS * GATHER_WARP_VALS * (int)sizeof(double);
+    FS_CUDA(c, cudaFuncSetAttribute(k_assemble_gather<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    FS_CUDA(c, cudaFuncSetAttribute(k_assemble_gather<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    FS_CUDA(c, cudaFuncSetAttribute(k_assemble_gather<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     c->gather_ready = true;
     return FS_OK;
 }
@@ -699,7 +738,8 @@ int assemble_values(fs_context *c, float *ms)
     }
     FS_CUDA(c, cudaEventRecord(c->ev0, st));
     if (c->asm_mode == FS_ASM_GATHER && c->gather_ready) {
-        k_assemble_gather<<<nblk(c->n_g_chunks, GATHER_WARPS), GATHER_THREADS, GATHER_WARPS * GATHER_WARP_VALS * sizeof(double), st>>>(
+        auto kern = c->n_tri == 0 ? k_assemble_gather<1> : (c->n_quad == 0 ? k_assemble_gather<2> : k_assemble_gather<3>);
+        kern<<<nblk(c->n_g_chunks, GATHER_WARPS), GATHER_THREADS, GATHER_WARPS * GATHER_WARP_VALS * sizeof(double), st>>>(
             c->d_g_chunks.p, (int)c->n_g_chunks, c->d_g_elem.p, c->d_g_meta.p, c->d_tri.p, c->d_tri_pos.p, c->d_quad.p, c->d_quad_pos.p,
             c->d_xyz.p, c->d_mask.p, c->d_nptr.p, c->d_vals.p, (int)c->own_lo);
         FS_CUDA(c, cudaEventRecord(c->ev1, st));

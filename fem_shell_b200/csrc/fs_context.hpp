@@ -68,7 +68,7 @@ struct GatherChunk {
     int row0, row1;      // owned block rows
     int thread_off;      // first entry of this chunk in the thread table
     int n_threads;       // entries (padded per (type, I) group to whole warps)
-    int n_rounds;        // max number of elements incident to one row of the chunk
+    int n_rounds;        // phases of the chunk's emit steps (build_gather_schedule)
     int val_count;       // 36 * (nptr[row1] - nptr[row0]) doubles staged in shared memory
 };
 
