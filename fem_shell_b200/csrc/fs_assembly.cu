@@ -364,6 +364,13 @@ int upload_element_constants(fs_context *c)
     h.thickness = c->thickness;
     h.quirks = c->quirks;
     FS_CUDA(c, cudaMemcpyToSymbolAsync(c_el, &h, sizeof h, 0, cudaMemcpyHostToDevice, c->stream));
+    if (!c->d_qgp.p) {  // Gauss-point table of the gather kernel's run-time node rows (fs_elements.cuh)
+        QuadGpTab t;
+        quad_gp_table(t);
+        FS_CUDA(c, c->d_qgp.alloc(96));
+        FS_CUDA(c, cudaMemcpyAsync(c->d_qgp.p, &t, sizeof t, cudaMemcpyHostToDevice, c->stream));
+        FS_CUDA(c, cudaStreamSynchronize(c->stream));  // t is a stack object
+    }
     return FS_OK;
 }
 
@@ -527,10 +534,15 @@ k_assemble_gather(const GatherChunk *__restrict__ chunks, int n_chunks, const in
                   const int32_t *__restrict__ tri_pos, const int32_t *__restrict__ quad,
                   const int32_t *__restrict__ quad_pos, const double *__restrict__ xyz,
                   const uint8_t *__restrict__ mask, const int32_t *__restrict__ nptr, double *__restrict__ vals,
-                  int own_lo)
+                  int own_lo, const double *__restrict__ qgp)
 {
     extern __shared__ double sv_all[];
+    __shared__ __align__(16) double s_qtab[96];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (KINDS & 1) {
+        if (threadIdx.x < 96) s_qtab[threadIdx.x] = qgp[threadIdx.x];
+        __syncthreads();
+    }
     const int ci = blockIdx.x * GATHER_WARPS + warp;
     if (ci >= n_chunks) return;
     double *sv = sv_all + (size_t)warp * GATHER_WARP_VALS;
@@ -575,7 +587,7 @@ k_assemble_gather(const GatherChunk *__restrict__ chunks, int n_chunks, const in
 #pragma unroll
                 for (int c2 = 0; c2 < 3; c2++) T[r][c2] = g.T[r][c2];
             quad_membrane_row_rt(g, I, Km);
-            quad_plate_row_rt(g, I, Kp);
+            quad_plate_row_rt(g, I, s_qtab, Kp);
         } else if (KINDS & 2) {
             double X[9];
             int row = 0;
@@ -741,7 +753,7 @@ int assemble_values(fs_context *c, float *ms)
         auto kern = c->n_tri == 0 ? k_assemble_gather<1> : (c->n_quad == 0 ? k_assemble_gather<2> : k_assemble_gather<3>);
         kern<<<nblk(c->n_g_chunks, GATHER_WARPS), GATHER_THREADS, GATHER_WARPS * GATHER_WARP_VALS * sizeof(double), st>>>(
             c->d_g_chunks.p, (int)c->n_g_chunks, c->d_g_elem.p, c->d_g_meta.p, c->d_tri.p, c->d_tri_pos.p, c->d_quad.p, c->d_quad_pos.p,
-            c->d_xyz.p, c->d_mask.p, c->d_nptr.p, c->d_vals.p, (int)c->own_lo);
+            c->d_xyz.p, c->d_mask.p, c->d_nptr.p, c->d_vals.p, (int)c->own_lo, c->d_qgp.p);
         FS_CUDA(c, cudaEventRecord(c->ev1, st));
         FS_CUDA(c, cudaStreamSynchronize(st));
         FS_CUDA(c, cudaGetLastError());

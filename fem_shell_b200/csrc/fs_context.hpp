@@ -158,6 +158,7 @@ struct fs_context {
     // row-gather assembly schedule (fs_assembly.cu, build_gather_schedule)
     fs::DevBuf<fs::GatherChunk> d_g_chunks;
     fs::DevBuf<int32_t> d_g_elem, d_g_meta;
+    fs::DevBuf<double> d_qgp;              // 96 doubles: Gauss-point shape-derivative table (fs_elements.cuh QuadGpTab)
     int64_t n_g_chunks = 0;
     bool gather_ready = false, gather_unavailable = false;
 

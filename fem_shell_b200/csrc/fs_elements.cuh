@@ -228,8 +228,19 @@ __device__ __forceinline__ void quad_membrane_row(const QuadGeom &g, double Km[4
 }
 
 // run-time node row (callers keep I warp-uniform): same arithmetic, one copy of the code
-__device__ __forceinline__ double pick3(int I, const double v[3]) { return I == 0 ? v[0] : (I == 1 ? v[1] : v[2]); }
-__device__ __forceinline__ double pick4(int I, const double v[4]) { return I == 0 ? v[0] : (I == 1 ? v[1] : (I == 2 ? v[2] : v[3])); }
+// selp.f64 spelled out: nvcc turns nested ?: on doubles into divergent branch trees (BSSY/BRA/BSYNC), which cost
+// the gather kernel 13 % of its issue slots in branch-resolving stalls (profiles/r01h_asm_notes.txt)
+__device__ __forceinline__ double sel_f64(bool p, double a, double b)
+{
+    double d;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\tselp.f64 %0, %1, %2, q;\n\t}" : "=d"(d) : "d"(a), "d"(b), "r"((int)p));
+    return d;
+}
+__device__ __forceinline__ double pick3(int I, const double v[3]) { return sel_f64(I == 0, v[0], sel_f64(I == 1, v[1], v[2])); }
+__device__ __forceinline__ double pick4(int I, const double v[4])
+{
+    return sel_f64(I < 2, sel_f64(I == 0, v[0], v[1]), sel_f64(I == 2, v[2], v[3]));
+}
 
 __device__ __forceinline__ void tri_membrane_row_rt(const TriGeom &g, int I, double Km[4][2][2])
 {
@@ -478,9 +489,9 @@ __device__ __forceinline__ void tri_plate_row_rt(const TriGeom &g, int I, double
         double E[3][3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            const double m0 = I == 0 ? M[0][0][c] : (I == 1 ? M[1][0][c] : M[2][0][c]);
-            const double m1 = I == 0 ? M[0][1][c] : (I == 1 ? M[1][1][c] : M[2][1][c]);
-            const double m2 = I == 0 ? M[0][2][c] : (I == 1 ? M[1][2][c] : M[2][2][c]);
+            const double m0 = sel_f64(I == 0, M[0][0][c], sel_f64(I == 1, M[1][0][c], M[2][0][c]));
+            const double m1 = sel_f64(I == 0, M[0][1][c], sel_f64(I == 1, M[1][1][c], M[2][1][c]));
+            const double m2 = sel_f64(I == 0, M[0][2][c], sel_f64(I == 1, M[1][2][c], M[2][2][c]));
             E[0][c] = d11 * m0 + d12 * m1;
             E[1][c] = d12 * m0 + d11 * m1;
             E[2][c] = d33 * m2;
@@ -601,23 +612,54 @@ __device__ __forceinline__ void quad_plate_row(const QuadGeom &g, double Kp[4][3
     }
 }
 
-// columns of node K chosen at run time (selects only, no branches): K picks the corner derivative and
-// the coefficients of the two adjacent sides; xi, eta are compile-time constants after unrolling
-__device__ __forceinline__ void quad_bcols_rt(const QuadH &h, int K, double xi, double eta, double i00, double i01,
+// Shape-function derivatives of corner K and of its two adjacent mid-side nodes at the four Gauss points,
+// fs.cpp:907-923.  With a run-time K these would be selections among compile-time constants, which the
+// compiler turns into divergent branch trees; the host tabulates them once (quad_gp_table) and the lanes of
+// the gather kernel read their six numbers per Gauss point from a shared-memory copy.
+struct QuadGpTab {
+    double v[4][4][6];  // [gp][K] -> Nx_K, Ne_K, Nx_mid[K], Nx_mid[K-1], Ne_mid[K], Ne_mid[K-1]
+};
+
+inline void quad_gp_table(QuadGpTab &t)
+{
+    const double root = 0.57735026918962584;  // sqrt(1.0/3.0), fs.cpp:472
+    for (int gp = 0; gp < 4; gp++) {
+        const double xi = (gp & 2) ? -root : root, eta = (gp & 1) ? -root : root;
+        const double Nx_c[4] = {0.25 * (2.0 * xi + eta) * (1.0 - eta), 0.25 * (2.0 * xi - eta) * (1.0 - eta),
+                                0.25 * (2.0 * xi + eta) * (1.0 + eta), 0.25 * (2.0 * xi - eta) * (1.0 + eta)};
+        const double Ne_c[4] = {0.25 * (2.0 * eta + xi) * (1.0 - xi), 0.25 * (2.0 * eta - xi) * (1.0 + xi),
+                                0.25 * (2.0 * eta + xi) * (1.0 + xi), 0.25 * (2.0 * eta - xi) * (1.0 - xi)};
+        const double Nx_mid[4] = {-xi * (1.0 - eta), 0.5 * (1.0 - eta * eta), -xi * (1.0 + eta), -0.5 * (1.0 - eta * eta)};
+        const double Ne_mid[4] = {-0.5 * (1.0 - xi * xi), -eta * (1.0 + xi), 0.5 * (1.0 - xi * xi), -eta * (1.0 - xi)};
+        for (int K = 0; K < 4; K++) {
+            const int P = (K + 3) & 3;
+            double *o = t.v[gp][K];
+            o[0] = Nx_c[K]; o[1] = Ne_c[K]; o[2] = Nx_mid[K]; o[3] = Nx_mid[P]; o[4] = Ne_mid[K]; o[5] = Ne_mid[P];
+        }
+    }
+}
+
+// columns of node K chosen at run time: tb = the six tabulated numbers of (gp, K); the side coefficients are
+// register selects
+struct QuadHK {
+    double aS, aP, bS, bP, cS, cP, dS, dP, eS, eP;  // Hcoeffs of side K (after node K) and side K-1 (before it)
+};
+
+__device__ __forceinline__ void quad_pick_sides(const QuadH &h, int K, QuadHK &k)
+{
+    const int P = (K + 3) & 3;
+    k.aS = pick4(K, h.a); k.aP = pick4(P, h.a); k.bS = pick4(K, h.b); k.bP = pick4(P, h.b);
+    k.cS = pick4(K, h.c); k.cP = pick4(P, h.c); k.dS = pick4(K, h.d); k.dP = pick4(P, h.d);
+    k.eS = pick4(K, h.e); k.eP = pick4(P, h.e);
+}
+
+__device__ __forceinline__ void quad_bcols_rt(const QuadHK &k, const double *tb, double i00, double i01,
                                               double i10, double i11, double Bc[3][3])
 {
-    const double Nx_c[4] = {0.25 * (2.0 * xi + eta) * (1.0 - eta), 0.25 * (2.0 * xi - eta) * (1.0 - eta),
-                            0.25 * (2.0 * xi + eta) * (1.0 + eta), 0.25 * (2.0 * xi - eta) * (1.0 + eta)};
-    const double Ne_c[4] = {0.25 * (2.0 * eta + xi) * (1.0 - xi), 0.25 * (2.0 * eta - xi) * (1.0 + xi),
-                            0.25 * (2.0 * eta + xi) * (1.0 + xi), 0.25 * (2.0 * eta - xi) * (1.0 - xi)};
-    const double Nx_mid[4] = {-xi * (1.0 - eta), 0.5 * (1.0 - eta * eta), -xi * (1.0 + eta), -0.5 * (1.0 - eta * eta)};
-    const double Ne_mid[4] = {-0.5 * (1.0 - xi * xi), -eta * (1.0 + xi), 0.5 * (1.0 - xi * xi), -eta * (1.0 - xi)};
-    const int P = (K + 3) & 3;
-    const double Nxk = pick4(K, Nx_c), Nek = pick4(K, Ne_c);
-    const double nxs = pick4(K, Nx_mid), nxp = pick4(P, Nx_mid), nes = pick4(K, Ne_mid), nep = pick4(P, Ne_mid);
-    const double aS = pick4(K, h.a), aP = pick4(P, h.a), bS = pick4(K, h.b), bP = pick4(P, h.b);
-    const double cS = pick4(K, h.c), cP = pick4(P, h.c), dS = pick4(K, h.d), dP = pick4(P, h.d);
-    const double eS = pick4(K, h.e), eP = pick4(P, h.e);
+    const double aS = k.aS, aP = k.aP, bS = k.bS, bP = k.bP, cS = k.cS, cP = k.cP, dS = k.dS, dP = k.dP, eS = k.eS, eP = k.eP;
+    const double2 t01 = *reinterpret_cast<const double2 *>(tb), t23 = *reinterpret_cast<const double2 *>(tb + 2),
+                  t45 = *reinterpret_cast<const double2 *>(tb + 4);
+    const double Nxk = t01.x, Nek = t01.y, nxs = t23.x, nxp = t23.y, nes = t45.x, nep = t45.y;
     double hxx[3], hxe[3], hyx[3], hye[3];
     hxx[0] = 1.5 * (aS * nxs - aP * nxp);
     hxx[1] = bS * nxs + bP * nxp;
@@ -639,7 +681,8 @@ __device__ __forceinline__ void quad_bcols_rt(const QuadH &h, int K, double xi, 
     }
 }
 
-__device__ __forceinline__ void quad_plate_row_rt(const QuadGeom &g, int I, double Kp[4][3][3])
+// qtab: shared-memory copy of the QuadGpTab
+__device__ __forceinline__ void quad_plate_row_rt(const QuadGeom &g, int I, const double *qtab, double Kp[4][3][3])
 {
     QuadH h;
 #pragma unroll
@@ -652,6 +695,8 @@ __device__ __forceinline__ void quad_plate_row_rt(const QuadGeom &g, int I, doub
         h.d[k] = -dy * si;
         h.e[k] = (0.25 * dy * dy - 0.5 * dx * dx) * si;
     }
+    QuadHK hk;
+    quad_pick_sides(h, I, hk);
     const double d11 = c_el.dp11, d12 = c_el.dp12, d33 = c_el.dp33;
     const double root = 0.57735026918962584;
     const bool quirk = (c_el.quirks & FS_Q_DETLU) != 0;
@@ -672,7 +717,7 @@ __device__ __forceinline__ void quad_plate_row_rt(const QuadGeom &g, int I, doub
         const double di = 1.0 / det;
         const double i00 = j11 * di, i01 = -j01 * di, i10 = -j10 * di, i11 = j00 * di;
         double Bc[3][3], E[3][3];
-        quad_bcols_rt(h, I, r, s, i00, i01, i10, i11, Bc);
+        quad_bcols_rt(hk, qtab + (gp * 4 + I) * 6, i00, i01, i10, i11, Bc);
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             E[0][c] = (d11 * Bc[0][c] + d12 * Bc[1][c]) * det;
