@@ -527,59 +527,61 @@ __device__ __forceinline__ void gather_emit(const double T[3][3], double Km[4][2
 }
 
 // KINDS: 1 = the mesh has only Quad-4, 2 = only Tri-3, 3 = both (a pure mesh does not carry the other path's code)
+// Inputs of a lane come from the packed thread table (32 entries per chunk, build_gather_schedule): one 16-byte
+// record {meta, row info, Dirichlet bits, slots} and its node ids, both read at the kernel's first instructions
+// next to the chunk record, so the only dependent global loads are the coordinates (two levels instead of four).
 template <int KINDS>
 __global__ void __launch_bounds__(GATHER_THREADS, 2)
-k_assemble_gather(const GatherChunk *__restrict__ chunks, int n_chunks, const int32_t *__restrict__ g_elem,
-                  const int32_t *__restrict__ g_meta, const int32_t *__restrict__ tri,
-                  const int32_t *__restrict__ tri_pos, const int32_t *__restrict__ quad,
-                  const int32_t *__restrict__ quad_pos, const double *__restrict__ xyz,
-                  const uint8_t *__restrict__ mask, const int32_t *__restrict__ nptr, double *__restrict__ vals,
-                  int own_lo, const double *__restrict__ qgp)
+k_assemble_gather(const GatherChunk *__restrict__ chunks, int n_chunks, const int4 *__restrict__ g_info,
+                  const int4 *__restrict__ g_nodes, const double *__restrict__ xyz, double *__restrict__ vals,
+                  const double *__restrict__ qgp)
 {
     extern __shared__ double sv_all[];
     __shared__ __align__(16) double s_qtab[96];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ci = blockIdx.x * GATHER_WARPS + warp;
+    const bool live = ci < n_chunks;
+    GatherChunk ch = {0, 0, 0, 0, 0};
+    int4 info = make_int4(0, 0, 0, 0), nd = make_int4(0, 0, 0, 0);
+    if (live) {
+        ch = chunks[ci];
+        info = __ldcs(g_info + (size_t)ci * 32 + lane);
+        nd = __ldcs(g_nodes + (size_t)ci * 32 + lane);
+    }
     if (KINDS & 1) {
         if (threadIdx.x < 96) s_qtab[threadIdx.x] = qgp[threadIdx.x];
         __syncthreads();
     }
-    const int ci = blockIdx.x * GATHER_WARPS + warp;
-    if (ci >= n_chunks) return;
+    if (!live) return;
     double *sv = sv_all + (size_t)warp * GATHER_WARP_VALS;
-    const GatherChunk ch = chunks[ci];
     {
         double2 *z2 = reinterpret_cast<double2 *>(sv);
 #pragma unroll 4
         for (int i = lane; i < ch.val_count / 2; i += 32) z2[i] = make_double2(0.0, 0.0);
     }
-
-    int e = -1, meta = 0;
-    if (lane < ch.n_threads) {
-        e = g_elem[ch.thread_off + lane];
-        meta = g_meta[ch.thread_off + lane];
-    }
+    const int meta = info.x;
+    const bool valid = (meta >> 8) & 1;
     const int I = meta & 3, round = (meta >> 3) & 31;
     const int is_quad = KINDS == 3 ? (meta >> 2) & 1 : (KINDS == 1);
     double Km[4][2][2], Kp[4][3][3], T[3][3];
     int slot[4];
     unsigned mcol[4];
-    double *srow = sv;
-    int L = 0;
-    if (e >= 0) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        slot[k] = (info.w >> (8 * k)) & 0xff;
+        mcol[k] = ((unsigned)info.z >> (8 * k)) & 0x3fu;
+    }
+    double *srow = sv + (info.y & 0xffff);
+    const int L = 6 * ((unsigned)info.y >> 16);
+    const int nodes[4] = {nd.x, nd.y, nd.z, nd.w};
+    if (valid) {
         if ((KINDS & 1) && is_quad) {
             double X[12];
-            int row = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const int n = quad[4 * (size_t)e + k];
-                if (k == I) row = n - own_lo;
-                mcol[k] = mask[n];
-                slot[k] = quad_pos[16 * (size_t)e + 4 * I + k];
-                X[3 * k] = xyz[3 * (size_t)n]; X[3 * k + 1] = xyz[3 * (size_t)n + 1]; X[3 * k + 2] = xyz[3 * (size_t)n + 2];
+                const size_t n = (size_t)nodes[k];
+                X[3 * k] = xyz[3 * n]; X[3 * k + 1] = xyz[3 * n + 1]; X[3 * k + 2] = xyz[3 * n + 2];
             }
-            const int b0 = nptr[row];
-            L = 6 * (nptr[row + 1] - b0);
-            srow = sv + 36 * (size_t)(b0 - nptr[ch.row0]);
             QuadGeom g;
             quad_geom(X, g);
 #pragma unroll
@@ -590,19 +592,11 @@ k_assemble_gather(const GatherChunk *__restrict__ chunks, int n_chunks, const in
             quad_plate_row_rt(g, I, s_qtab, Kp);
         } else if (KINDS & 2) {
             double X[9];
-            int row = 0;
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                const int n = tri[3 * (size_t)e + k];
-                if (k == I) row = n - own_lo;
-                mcol[k] = mask[n];
-                slot[k] = tri_pos[9 * (size_t)e + 3 * I + k];
-                X[3 * k] = xyz[3 * (size_t)n]; X[3 * k + 1] = xyz[3 * (size_t)n + 1]; X[3 * k + 2] = xyz[3 * (size_t)n + 2];
+                const size_t n = (size_t)nodes[k];
+                X[3 * k] = xyz[3 * n]; X[3 * k + 1] = xyz[3 * n + 1]; X[3 * k + 2] = xyz[3 * n + 2];
             }
-            mcol[3] = 0; slot[3] = 0;
-            const int b0 = nptr[row];
-            L = 6 * (nptr[row + 1] - b0);
-            srow = sv + 36 * (size_t)(b0 - nptr[ch.row0]);
             TriGeom g;
             tri_geom(X, g);
 #pragma unroll
@@ -615,12 +609,12 @@ k_assemble_gather(const GatherChunk *__restrict__ chunks, int n_chunks, const in
     }
     __syncwarp();
     // a chunk holds quads in its leading lanes and triangles behind them (both only in mixed meshes)
-    const bool any_quad = (KINDS & 1) && __any_sync(0xffffffffu, e >= 0 && is_quad);
-    const bool any_tri = (KINDS & 2) && __any_sync(0xffffffffu, e >= 0 && !is_quad);
-    if (any_quad) gather_emit<4>(T, Km, Kp, I, slot, mcol, srow, L, e >= 0 && is_quad, round, ch.n_rounds);
-    if (any_tri) gather_emit<3>(T, Km, Kp, I, slot, mcol, srow, L, e >= 0 && !is_quad, round, ch.n_rounds);
+    const bool any_quad = (KINDS & 1) && __any_sync(0xffffffffu, valid && is_quad);
+    const bool any_tri = (KINDS & 2) && __any_sync(0xffffffffu, valid && !is_quad);
+    if (any_quad) gather_emit<4>(T, Km, Kp, I, slot, mcol, srow, L, valid && is_quad, round, ch.n_rounds);
+    if (any_tri) gather_emit<3>(T, Km, Kp, I, slot, mcol, srow, L, valid && !is_quad, round, ch.n_rounds);
     // stream the finished rows out (contiguous in the CSR value array)
-    double2 *out = reinterpret_cast<double2 *>(vals + 36 * (size_t)nptr[ch.row0]);
+    double2 *out = reinterpret_cast<double2 *>(vals + ch.val_off);
     const double2 *s2 = reinterpret_cast<const double2 *>(sv);
 #pragma unroll 4
     for (int i = lane; i < ch.val_count / 2; i += 32) __stcs(out + i, s2[i]);
@@ -632,14 +626,18 @@ int build_gather_schedule(fs_context *c)
     if (c->gather_ready || c->gather_unavailable) return FS_OK;
     const int64_t nt = c->n_tri, nq = c->n_quad, n_own = c->n_own;
     const int own_lo = (int)c->own_lo;
-    std::vector<int32_t> tri(3 * nt), quad(4 * nq), tgid(nt), qgid(nq), nptr(n_own + 1);
+    std::vector<int32_t> tri(3 * nt), quad(4 * nq), tgid(nt), qgid(nq), nptr(n_own + 1), tpos(9 * nt), qpos(16 * nq);
+    std::vector<uint8_t> mask(c->n_local);
+    FS_CUDA(c, cudaMemcpy(mask.data(), c->d_mask.p, c->n_local, cudaMemcpyDeviceToHost));
     if (nt) {
         FS_CUDA(c, cudaMemcpy(tri.data(), c->d_tri.p, sizeof(int32_t) * 3 * nt, cudaMemcpyDeviceToHost));
         FS_CUDA(c, cudaMemcpy(tgid.data(), c->d_tri_gid.p, sizeof(int32_t) * nt, cudaMemcpyDeviceToHost));
+        FS_CUDA(c, cudaMemcpy(tpos.data(), c->d_tri_pos.p, sizeof(int32_t) * 9 * nt, cudaMemcpyDeviceToHost));
     }
     if (nq) {
         FS_CUDA(c, cudaMemcpy(quad.data(), c->d_quad.p, sizeof(int32_t) * 4 * nq, cudaMemcpyDeviceToHost));
         FS_CUDA(c, cudaMemcpy(qgid.data(), c->d_quad_gid.p, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost));
+        FS_CUDA(c, cudaMemcpy(qpos.data(), c->d_quad_pos.p, sizeof(int32_t) * 16 * nq, cudaMemcpyDeviceToHost));
     }
     FS_CUDA(c, cudaMemcpy(nptr.data(), c->d_nptr.p, sizeof(int32_t) * (n_own + 1), cudaMemcpyDeviceToHost));
 
@@ -689,7 +687,7 @@ int build_gather_schedule(fs_context *c)
     }
 
     std::vector<GatherChunk> chunks;
-    std::vector<int32_t> g_elem, g_meta;
+    std::vector<int4> g_info, g_nodes;  // 32 entries per chunk
     int64_t row = 0;
     while (row < n_own) {
         int64_t r1 = row, vals = 0;
@@ -697,7 +695,7 @@ int build_gather_schedule(fs_context *c)
         while (r1 < n_own) {
             const int t2 = threads + (cnt[r1 + 1] - cnt[r1]);
             const int64_t v2 = vals + 36 * (int64_t)(nptr[r1 + 1] - nptr[r1]);
-            if (t2 > 32 || v2 > GATHER_WARP_VALS) break;
+            if (t2 > 32 || v2 > GATHER_WARP_VALS || nptr[r1 + 1] - nptr[r1] > 255) break;
             threads = t2;
             vals = v2;
             for (int k = cnt[r1]; k < cnt[r1 + 1]; k++) rounds = std::max(rounds, (int)phase[k] + 1);
@@ -708,29 +706,46 @@ int build_gather_schedule(fs_context *c)
             return FS_OK;
         }
         GatherChunk ch;
-        ch.row0 = (int)row; ch.row1 = (int)r1;
-        ch.thread_off = (int)g_elem.size();
+        ch.val_off = 36 * (long long)nptr[row];
         ch.n_threads = threads;
         ch.n_rounds = rounds;
         ch.val_count = (int)vals;
+        ch.pad = 0;
+        const size_t base = g_info.size();
+        g_info.resize(base + 32, make_int4(0, 0, 0, 0));
+        g_nodes.resize(base + 32, make_int4(0, 0, 0, 0));
+        size_t at = base;
         // quads first so that a mixed chunk splits into at most two divergent halves
         for (int pass = 1; pass >= 0; pass--)
             for (int64_t p = row; p < r1; p++)
                 for (int k = cnt[p]; k < cnt[p + 1]; k++)
                     if (inc[k].type == pass) {
-                        g_elem.push_back(inc[k].eidx);
-                        g_meta.push_back(inc[k].I | (inc[k].type << 2) | ((int)phase[k] << 3));
+                        const int nen = pass ? 4 : 3, I = inc[k].I;
+                        const int32_t *en = pass ? &quad[4 * (int64_t)inc[k].eidx] : &tri[3 * (int64_t)inc[k].eidx];
+                        const int32_t *ps = pass ? &qpos[16 * (int64_t)inc[k].eidx + 4 * I] : &tpos[9 * (int64_t)inc[k].eidx + 3 * I];
+                        int nd[4] = {0, 0, 0, 0};
+                        unsigned slots = 0, mbits = 0;
+                        for (int j = 0; j < nen; j++) {
+                            nd[j] = en[j];
+                            slots |= (unsigned)(ps[j] & 0xff) << (8 * j);
+                            mbits |= (unsigned)(mask[en[j]] & 0x3f) << (8 * j);
+                        }
+                        const unsigned soff = (unsigned)(36 * (nptr[p] - nptr[row]));
+                        const unsigned deg = (unsigned)(nptr[p + 1] - nptr[p]);
+                        g_info[at] = make_int4(I | (inc[k].type << 2) | ((int)phase[k] << 3) | (1 << 8), (int)(soff | (deg << 16)), (int)mbits, (int)slots);
+                        g_nodes[at] = make_int4(nd[0], nd[1], nd[2], nd[3]);
+                        at++;
                     }
         chunks.push_back(ch);
         row = r1;
     }
     c->n_g_chunks = (int64_t)chunks.size();
     FS_CUDA(c, c->d_g_chunks.alloc(chunks.size()));
-    FS_CUDA(c, c->d_g_elem.alloc(g_elem.size()));
-    FS_CUDA(c, c->d_g_meta.alloc(g_meta.size()));
+    FS_CUDA(c, c->d_g_info.alloc(g_info.size()));
+    FS_CUDA(c, c->d_g_nodes.alloc(g_nodes.size()));
     FS_CUDA(c, cudaMemcpy(c->d_g_chunks.p, chunks.data(), sizeof(GatherChunk) * chunks.size(), cudaMemcpyHostToDevice));
-    FS_CUDA(c, cudaMemcpy(c->d_g_elem.p, g_elem.data(), sizeof(int32_t) * g_elem.size(), cudaMemcpyHostToDevice));
-    FS_CUDA(c, cudaMemcpy(c->d_g_meta.p, g_meta.data(), sizeof(int32_t) * g_meta.size(), cudaMemcpyHostToDevice));
+    FS_CUDA(c, cudaMemcpy(c->d_g_info.p, g_info.data(), sizeof(int4) * g_info.size(), cudaMemcpyHostToDevice));
+    FS_CUDA(c, cudaMemcpy(c->d_g_nodes.p, g_nodes.data(), sizeof(int4) * g_nodes.size(), cudaMemcpyHostToDevice));
     constexpr int smem = GATHER_WARPS * GATHER_WARP_VALS * (int)sizeof(double);
     FS_CUDA(c, cudaFuncSetAttribute(k_assemble_gather<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     FS_CUDA(c, cudaFuncSetAttribute(k_assemble_gather<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -752,8 +767,7 @@ int assemble_values(fs_context *c, float *ms)
     if (c->asm_mode == FS_ASM_GATHER && c->gather_ready) {
         auto kern = c->n_tri == 0 ? k_assemble_gather<1> : (c->n_quad == 0 ? k_assemble_gather<2> : k_assemble_gather<3>);
         kern<<<nblk(c->n_g_chunks, GATHER_WARPS), GATHER_THREADS, GATHER_WARPS * GATHER_WARP_VALS * sizeof(double), st>>>(
-            c->d_g_chunks.p, (int)c->n_g_chunks, c->d_g_elem.p, c->d_g_meta.p, c->d_tri.p, c->d_tri_pos.p, c->d_quad.p, c->d_quad_pos.p,
-            c->d_xyz.p, c->d_mask.p, c->d_nptr.p, c->d_vals.p, (int)c->own_lo, c->d_qgp.p);
+            c->d_g_chunks.p, (int)c->n_g_chunks, c->d_g_info.p, c->d_g_nodes.p, c->d_xyz.p, c->d_vals.p, c->d_qgp.p);
         FS_CUDA(c, cudaEventRecord(c->ev1, st));
         FS_CUDA(c, cudaStreamSynchronize(st));
         FS_CUDA(c, cudaGetLastError());

@@ -63,13 +63,13 @@ struct CgState {
     int status;       // FS_OK / FS_ERR_NOT_CONVERGED / FS_ERR_BREAKDOWN
 };
 
-// one thread block of the row-gather assembly: block rows [row0,row1) accumulated in shared memory
+// one warp of the row-gather assembly: a run of block rows accumulated in shared memory (fs_assembly.cu)
 struct GatherChunk {
-    int row0, row1;      // owned block rows
-    int thread_off;      // first entry of this chunk in the thread table
-    int n_threads;       // entries (padded per (type, I) group to whole warps)
-    int n_rounds;        // phases of the chunk's emit steps (build_gather_schedule)
+    long long val_off;   // first CSR value of the run (36 * nptr[row0])
     int val_count;       // 36 * (nptr[row1] - nptr[row0]) doubles staged in shared memory
+    int n_rounds;        // phases of the chunk's emit steps (build_gather_schedule)
+    int n_threads;       // valid entries among the chunk's 32 thread-table slots
+    int pad;
 };
 
 struct Peer {
@@ -157,7 +157,7 @@ struct fs_context {
     int64_t n_colors = 0;
     // row-gather assembly schedule (fs_assembly.cu, build_gather_schedule)
     fs::DevBuf<fs::GatherChunk> d_g_chunks;
-    fs::DevBuf<int32_t> d_g_elem, d_g_meta;
+    fs::DevBuf<int4> d_g_info, d_g_nodes;  // packed thread table: {meta, row info, Dirichlet bits, slots}, node ids
     fs::DevBuf<double> d_qgp;              // 96 doubles: Gauss-point shape-derivative table (fs_elements.cuh QuadGpTab)
     int64_t n_g_chunks = 0;
     bool gather_ready = false, gather_unavailable = false;
