@@ -536,7 +536,7 @@ k_assemble_gather(const GatherChunk *__restrict__ chunks, int n_chunks, const in
                   const int4 *__restrict__ g_nodes, const double *__restrict__ xyz, double *__restrict__ vals,
                   const double *__restrict__ qgp)
 {
-    extern __shared__ double sv_all[];
+    extern __shared__ __align__(128) double sv_all[];
     __shared__ __align__(16) double s_qtab[96];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ci = blockIdx.x * GATHER_WARPS + warp;
@@ -554,10 +554,10 @@ k_assemble_gather(const GatherChunk *__restrict__ chunks, int n_chunks, const in
     }
     if (!live) return;
     double *sv = sv_all + (size_t)warp * GATHER_WARP_VALS;
-    {
+    {   // the whole slice, so that the stores do not wait for the chunk record (chunks are packed to ~92 % of it)
         double2 *z2 = reinterpret_cast<double2 *>(sv);
-#pragma unroll 4
-        for (int i = lane; i < ch.val_count / 2; i += 32) z2[i] = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int i = 0; i < GATHER_WARP_VALS / 64; i++) z2[i * 32 + lane] = make_double2(0.0, 0.0);
     }
     const int meta = info.x;
     const bool valid = (meta >> 8) & 1;
@@ -614,10 +614,19 @@ k_assemble_gather(const GatherChunk *__restrict__ chunks, int n_chunks, const in
     if (any_quad) gather_emit<4>(T, Km, Kp, I, slot, mcol, srow, L, valid && is_quad, round, ch.n_rounds);
     if (any_tri) gather_emit<3>(T, Km, Kp, I, slot, mcol, srow, L, valid && !is_quad, round, ch.n_rounds);
     // stream the finished rows out (contiguous in the CSR value array)
-    double2 *out = reinterpret_cast<double2 *>(vals + ch.val_off);
-    const double2 *s2 = reinterpret_cast<const double2 *>(sv);
-#pragma unroll 4
-    for (int i = lane; i < ch.val_count / 2; i += 32) __stcs(out + i, s2[i]);
+    // One bulk copy (TMA engine, shared -> global) instead of 40 LDS/STG pairs per lane whose scoreboards the
+    // store queue kept busy for 13 % of the warp's life: every lane orders its shared-memory writes before the
+    // async proxy, one lane issues the copy and waits only until the slice has been READ (the warp then exits).
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+        const unsigned src = (unsigned)__cvta_generic_to_shared(sv);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(vals + ch.val_off), "r"(src),
+                     "r"((unsigned)ch.val_count * 8u)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
 }
 
 // host: build the thread table of the row-gather pass from the colour-sorted element arrays
