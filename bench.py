@@ -260,9 +260,22 @@ def run_ours(args):
     sols_host = torch.empty((n_nodes, 6), dtype=torch.float64).pin_memory()
     Fh, Sh = F_host.numpy(), sols_host.numpy()
 
+    # N = 1: fs_solve_host returns the whole sols[6*node+var].  N > 1: every rank reads back its OWN rows
+    # (fs_get_solution_owned = the distributed vector PETSc holds before build_solution_vector replicates it,
+    # fs.cpp:140); replicating the full solution on all N hosts would cost N x the bytes for the same information.
+    own_host = None
+    if world > 1:
+        own_host = torch.empty((n_own, 6), dtype=torch.float64).pin_memory()
+        Oh = own_host.numpy()
+
     def e2e_step(k):
-        s.solve_host(Fh, Sh, reassemble=True, rtol=1e-30, max_its=iters, pc=fsb.PC_JACOBI, warm_start=False,
-                     check_every=iters, allow_not_converged=True)
+        if world == 1:
+            s.solve_host(Fh, Sh, reassemble=True, rtol=1e-30, max_its=iters, pc=fsb.PC_JACOBI, warm_start=False,
+                         check_every=iters, allow_not_converged=True)
+        else:
+            s.solve_host(Fh, None, reassemble=True, rtol=1e-30, max_its=iters, pc=fsb.PC_JACOBI, warm_start=False,
+                         check_every=iters, allow_not_converged=True)
+            s.solution_owned(out=Oh, with_ids=False)
 
     for k in range(min(args.warmup, 3)):
         e2e_step(k)
@@ -361,7 +374,8 @@ def run_ours(args):
         "assembly_roofline": assembly_roofline,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(Fh.nbytes if world == 1 else 48 * n_own),
-                "d2h_bytes_per_step": int(Sh.nbytes), "includes": "loads H2D, values re-assembly, %d PCG iterations, displacements D2H" % iters},
+                "d2h_bytes_per_step": int(Sh.nbytes if world == 1 else 48 * n_own),
+                "includes": "loads H2D, values re-assembly, %d PCG iterations, displacements D2H%s" % (iters, "" if world == 1 else " (per rank: its own strip of loads in, its own rows of the solution out)")},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
     }

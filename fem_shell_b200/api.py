@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "fs_create", "fs_destroy", "fs_last_error", "fs_get_stream", "fs_dist_unique_id", "fs_dist_init", "fs_set_comm_mode", "fs_get_comm_mode",
     "fs_set_material", "fs_set_quirks", "fs_set_dof_order", "fs_set_assembly_mode", "fs_set_spmv_format", "fs_get_spmv_format", "fs_set_mesh",
     "fs_set_nodal_loads", "fs_set_interface_loads", "fs_build_rhs", "fs_assemble", "fs_solve",
-    "fs_get_solution", "fs_recover_resultants", "fs_solve_host", "fs_interface_nodes", "fs_step", "fs_commit_step", "fs_get_sizes",
+    "fs_get_solution", "fs_get_solution_owned", "fs_recover_resultants", "fs_solve_host", "fs_interface_nodes", "fs_step", "fs_commit_step", "fs_get_sizes",
     "fs_export_dof_order", "fs_export_csr", "fs_export_rhs", "fs_debug_element_matrices", "fs_spmv_host",
     "fs_bench_spmv", "fs_bench_fp64_peak", "fs_set_ml_options", "fs_get_ml_info", "fs_debug_ml_level", "fs_apply_mlrbm_host", "fs_partition_plan", "fs_meshgen", "fs_read_xda", "fs_read_forces", "fs_write_xda",
 ]
@@ -281,6 +281,15 @@ class FemShell:
         self._ck(self.lib.fs_get_solution(self.ctx, _p(sols)))
         return sols
 
+    def solution_owned(self, out=None, with_ids=True):
+        """(node_ids, vals[n_own, 6]): this rank's rows of the solution in DOF order, no communication"""
+        n = C.c_int64()
+        self._ck(self.lib.fs_get_solution_owned(self.ctx, C.byref(n), None, None))
+        ids = np.empty(n.value, np.int32) if with_ids else None
+        vals = np.empty((n.value, 6)) if out is None else out
+        self._ck(self.lib.fs_get_solution_owned(self.ctx, C.byref(n), _p(ids) if with_ids else None, _p(vals)))
+        return ids, vals
+
     def recover_resultants(self):
         """(n_elem, 6): membrane stresses and bending moments at the element centroids, local element axes"""
         out = np.empty((self.n_elem, 6))
@@ -291,7 +300,7 @@ class FemShell:
                    warm_start=True, check_every=0, allow_not_converged=False) -> SolveInfo:
         """plugin-style call with host buffers: loads in, displacements out (fsp.cpp:271-274)"""
         o, i = self._opts(rtol, max_its, pc, norm_type, warm_start, check_every), _Info()
-        self._ck(self.lib.fs_solve_host(self.ctx, _p(F), C.c_int(1 if reassemble else 0), C.byref(o), _p(sols), C.byref(i)),
+        self._ck(self.lib.fs_solve_host(self.ctx, _p(F), C.c_int(1 if reassemble else 0), C.byref(o), _p(sols) if sols is not None else None, C.byref(i)),
                  allow=(FS_ERR_NOT_CONVERGED,) if allow_not_converged else ())
         return SolveInfo(i.iterations, i.rel_residual, i.status, i.solve_ms)
 

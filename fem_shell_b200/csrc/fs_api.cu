@@ -476,6 +476,21 @@ int fs_get_solution(fs_context *c, double *sols)
     return FS_OK;
 }
 
+int fs_get_solution_owned(fs_context *c, int64_t *n_rows, int32_t *node_ids, double *vals)
+{
+    FS_CHECK_CTX(c);
+    if (!c->have_solution) return fail(c, FS_ERR_STATE, "no solution yet");
+    if (n_rows) *n_rows = c->n_own;
+    if (node_ids)
+        for (int64_t k = 0; k < c->n_own; k++) node_ids[k] = c->node_of_dof[c->own_begin + k];
+    if (vals) {  // the owned rows are contiguous in the local vector layout: one copy, no kernel, no communication
+        FS_CUDA(c, cudaSetDevice(c->device));
+        FS_CUDA(c, cudaMemcpyAsync(vals, c->d_x.p + 6 * c->own_lo, sizeof(double) * 6 * c->n_own, cudaMemcpyDeviceToHost, c->stream));
+        FS_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return FS_OK;
+}
+
 int fs_recover_resultants(fs_context *c, double *out)
 {
     FS_CHECK_CTX(c);
@@ -506,6 +521,7 @@ int fs_solve_host(fs_context *c, const double *F, int reassemble, const fs_solve
     if (reassemble || !c->assembled) FS_TRY(fs_assemble(c, nullptr));
     int rc = fs_solve(c, opts, info);
     if (rc != FS_OK && rc != FS_ERR_NOT_CONVERGED) return rc;
+    if (!sols) return rc;  // the caller fetches its own rows with fs_get_solution_owned
     int rc2 = fs_get_solution(c, sols);
     return rc2 != FS_OK ? rc2 : rc;
 }

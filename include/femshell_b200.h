@@ -161,9 +161,14 @@ int fs_get_solution(fs_context *ctx, double *sols);
  * ships no code for them; B is the element's own strain-displacement operator, so the
  * curvature sign follows it: Specht Tri-3 +d2w, DKQ Quad-4 -d2w.  Every rank receives all n_elem rows. */
 int fs_recover_resultants(fs_context *ctx, double *out /* 6*n_elem */);
+/* this rank's rows of the solution as PETSc holds them before build_solution_vector gathers the vector onto every
+ * rank (fs.cpp:140-141): row k = k-th owned node in DOF order, node_ids[k] its mesh node id, vals[6*k+var].
+ * No communication; node_ids and vals may be NULL (sizes only).  With one rank this is the whole solution. */
+int fs_get_solution_owned(fs_context *ctx, int64_t *n_rows, int32_t *node_ids, double *vals);
 /* equation_systems.solve() + build_solution_vector in one call with HOST buffers, as the
  * reference's coupling loop does per iteration (fsp.cpp:271-274).  F may be NULL (keep loads).
- * reassemble != 0 re-runs the values pass like the reference does on every solve. */
+ * reassemble != 0 re-runs the values pass like the reference does on every solve.  sols may be NULL: nothing is
+ * gathered and the caller reads its own rows with fs_get_solution_owned (distributed runs). */
 int fs_solve_host(fs_context *ctx, const double *F, int reassemble, const fs_solve_opts *opts,
                   double *sols, fs_solve_info *info);
 

@@ -70,6 +70,8 @@ def main():
             assert abs(i1.iterations - info.iterations) <= max(3, i1.iterations // 50), (name, comm, i1.iterations, info.iterations)
             assert np.linalg.norm(u - u1) <= 1e-8 * np.linalg.norm(u1)
             its[comm] = info.iterations
+            ids, own = s.solution_owned()          # this rank's rows, no communication
+            assert ids.size == oe - ob and np.array_equal(own, u[ids]), (name, comm, "owned rows")
             # stress resultants: elements of the cut rows read halo displacements; every rank gets all rows
             res = s.recover_resultants()
             ro = fso.recover_resultants(om, u, nu, E, t)

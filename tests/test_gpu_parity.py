@@ -267,6 +267,21 @@ def test_stress_resultants_match_oracle(fso, fsb, quirks):
         s.close()
 
 
+def test_owned_rows_of_the_solution(fso, fsb):
+    """fs_get_solution_owned on one rank = the whole solution, addressed through the DOF order"""
+    m, nu, E, t = CASES["c5_folded"](fsb)
+    s = gpu_system(fsb, m, nu, E, t, loads=m["forces"])
+    F = np.ascontiguousarray(m["forces"], float)
+    info = s.solve_host(F, None, rtol=1e-12, max_its=400000, pc=fsb.PC_BJACOBI6, warm_start=False)   # sols = NULL: nothing gathered
+    assert info.status == 0
+    ids, vals = s.solution_owned()
+    u = s.solution()
+    assert sorted(ids.tolist()) == list(range(u.shape[0]))
+    assert np.array_equal(vals, u[ids])
+    assert np.array_equal(s.dof_order()[ids], np.arange(ids.size))   # row k = k-th node of the DOF order
+    s.close()
+
+
 def test_max_its_and_error_paths(fso, fsb):
     m, nu, E, t = CASES["quad24"](fsb)
     s = gpu_system(fsb, m, nu, E, t, loads=m["forces"])
