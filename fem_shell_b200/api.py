@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = [
     "fs_set_nodal_loads", "fs_set_interface_loads", "fs_build_rhs", "fs_assemble", "fs_solve",
     "fs_get_solution", "fs_get_solution_owned", "fs_recover_resultants", "fs_solve_host", "fs_interface_nodes", "fs_step", "fs_commit_step", "fs_get_sizes",
     "fs_export_dof_order", "fs_export_csr", "fs_export_rhs", "fs_debug_element_matrices", "fs_spmv_host",
-    "fs_bench_spmv", "fs_bench_fp64_peak", "fs_set_ml_options", "fs_get_ml_info", "fs_debug_ml_level", "fs_apply_mlrbm_host", "fs_partition_plan", "fs_meshgen", "fs_read_xda", "fs_read_forces", "fs_write_xda",
+    "fs_bench_spmv", "fs_bench_fp64_peak", "fs_set_ml_options", "fs_get_ml_info", "fs_debug_ml_level", "fs_apply_mlrbm_host", "fs_partition_plan", "fs_gather_plan", "fs_meshgen", "fs_read_xda", "fs_read_forces", "fs_write_xda",
 ]
 
 
@@ -114,6 +114,24 @@ def meshgen(kind, nx, ny, min_x, min_y, max_x, max_y, bcids, factor, loading, ul
     if rc:
         raise FemShellError(rc, "fs_meshgen failed")
     return dict(xyz=xyz, etype=etype, eptr=eptr, enodes=enodes, bc=bc, forces=F)
+
+
+def gather_plan(etype, eptr, enodes, n_nodes, mask=None, warp_vals=2816):
+    """host-only schedule of the row-gather assembly pass (fs_gather_plan); None when the mesh needs the coloured pass"""
+    lib = load_library()
+    etype, eptr, enodes = _i32(etype), _i64(eptr), _i32(enodes)
+    mk = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+    sizes = np.zeros(3, np.int64)
+    args = [C.c_int64(n_nodes), C.c_int64(etype.size), _p(etype), _p(eptr), _p(enodes), _p(mk), C.c_int(warp_vals)]
+    if lib.fs_gather_plan(*args, _p(sizes), None, None, None, None, None):
+        raise FemShellError(-1, "fs_gather_plan: bad arguments")
+    nptr = np.empty(n_nodes + 1, np.int32); nadj = np.empty(sizes[2], np.int32)
+    if not sizes[1]:
+        return None
+    chunks = np.empty((sizes[0], 4), np.int64); info = np.empty((sizes[0] * 32, 4), np.int32); nodes = np.empty((sizes[0] * 32, 4), np.int32)
+    if lib.fs_gather_plan(*args, _p(sizes), _p(chunks), _p(info), _p(nodes), _p(nptr), _p(nadj)):
+        raise FemShellError(-1, "fs_gather_plan failed")
+    return dict(chunks=chunks, info=info, nodes=nodes, nptr=nptr, nadj=nadj)
 
 
 def partition_plan(eptr, enodes, n_nodes, rank, world, dof_mode=DOF_FIRST_ENCOUNTER):

@@ -18,6 +18,7 @@
 
 #include "fs_context.hpp"
 #include "fs_elements.cuh"
+#include "fs_gather_plan.hpp"
 
 namespace fs {
 
@@ -650,111 +651,21 @@ int build_gather_schedule(fs_context *c)
     }
     FS_CUDA(c, cudaMemcpy(nptr.data(), c->d_nptr.p, sizeof(int32_t) * (n_own + 1), cudaMemcpyDeviceToHost));
 
-    struct Inc { int32_t row, gid, eidx; uint8_t type, I; };
-    std::vector<int32_t> cnt(n_own + 1, 0);
-    for (int64_t e = 0; e < nt; e++)
-        for (int k = 0; k < 3; k++) { int p = tri[3 * e + k] - own_lo; if (p >= 0 && p < n_own) cnt[p + 1]++; }
-    for (int64_t e = 0; e < nq; e++)
-        for (int k = 0; k < 4; k++) { int p = quad[4 * e + k] - own_lo; if (p >= 0 && p < n_own) cnt[p + 1]++; }
-    for (int64_t p = 0; p < n_own; p++) cnt[p + 1] += cnt[p];
-    std::vector<Inc> inc(cnt[n_own]);
-    std::vector<int32_t> fill(cnt.begin(), cnt.end() - 1);
-    for (int64_t e = 0; e < nt; e++)
-        for (int k = 0; k < 3; k++) { int p = tri[3 * e + k] - own_lo; if (p >= 0 && p < n_own) inc[fill[p]++] = {(int32_t)p, tgid[e], (int32_t)e, 0, (uint8_t)k}; }
-    for (int64_t e = 0; e < nq; e++)
-        for (int k = 0; k < 4; k++) { int p = quad[4 * e + k] - own_lo; if (p >= 0 && p < n_own) inc[fill[p]++] = {(int32_t)p, qgid[e], (int32_t)e, 1, (uint8_t)k}; }
-    // Phases.  All lanes emit block j (the element's j-th node column) in the same step, so two incidences of
-    // one row may share a step iff they never meet in a slot at the same j, i.e. no node sits at the same local
-    // index in both elements.  On a structured Quad-4 mesh the four elements around a node see every shared
-    // neighbour under different local indices -> one phase; meshGen's triangle pairs share their hypotenuse end
-    // node at the same index -> a few phases.  Greedy colouring in a fixed order (triangles first, then by
-    // element id) keeps the summation order of every CSR value a function of the mesh alone.
-    std::vector<uint8_t> phase(inc.size(), 0);
-    for (int64_t p = 0; p < n_own; p++) {
-        std::sort(inc.begin() + cnt[p], inc.begin() + cnt[p + 1], [](const Inc &a, const Inc &b) {
-            return a.type != b.type ? a.type < b.type : a.gid < b.gid;
-        });
-        for (int k = cnt[p]; k < cnt[p + 1]; k++) {
-            const int nen = inc[k].type ? 4 : 3;
-            const int32_t *ek = inc[k].type ? &quad[4 * (int64_t)inc[k].eidx] : &tri[3 * (int64_t)inc[k].eidx];
-            unsigned used = 0;
-            for (int m = cnt[p]; m < k; m++) {
-                if (inc[m].type != inc[k].type) continue;  // quads and triangles are emitted one after the other
-                const int32_t *em = inc[m].type ? &quad[4 * (int64_t)inc[m].eidx] : &tri[3 * (int64_t)inc[m].eidx];
-                bool clash = false;
-                for (int j = 0; j < nen; j++) clash |= ek[j] == em[j];
-                if (clash) used |= 1u << phase[m];
-            }
-            int ph = 0;
-            while (used & (1u << ph)) ph++;
-            if (ph > 31) {  // more than 32 mutually clashing elements at one node: leave this mesh to the coloured pass
-                c->gather_unavailable = true;
-                return FS_OK;
-            }
-            phase[k] = (uint8_t)ph;
-        }
+    GatherPlan plan;
+    if (!plan_gather(n_own, own_lo, nt, tri.data(), tgid.data(), tpos.data(), nq, quad.data(), qgid.data(), qpos.data(), nptr.data(),
+                     mask.data(), GATHER_WARP_VALS, plan)) {
+        c->gather_unavailable = true;  // a block row exceeds a warp: leave this mesh to the coloured pass
+        return FS_OK;
     }
-
-    std::vector<GatherChunk> chunks;
-    std::vector<int4> g_info, g_nodes;  // 32 entries per chunk
-    int64_t row = 0;
-    while (row < n_own) {
-        int64_t r1 = row, vals = 0;
-        int threads = 0, rounds = 0;
-        while (r1 < n_own) {
-            const int t2 = threads + (cnt[r1 + 1] - cnt[r1]);
-            const int64_t v2 = vals + 36 * (int64_t)(nptr[r1 + 1] - nptr[r1]);
-            if (t2 > 32 || v2 > GATHER_WARP_VALS || nptr[r1 + 1] - nptr[r1] > 255) break;
-            threads = t2;
-            vals = v2;
-            for (int k = cnt[r1]; k < cnt[r1 + 1]; k++) rounds = std::max(rounds, (int)phase[k] + 1);
-            r1++;
-        }
-        if (r1 == row) {  // a single row does not fit a warp: leave this mesh to the coloured pass
-            c->gather_unavailable = true;
-            return FS_OK;
-        }
-        GatherChunk ch;
-        ch.val_off = 36 * (long long)nptr[row];
-        ch.n_threads = threads;
-        ch.n_rounds = rounds;
-        ch.val_count = (int)vals;
-        ch.pad = 0;
-        const size_t base = g_info.size();
-        g_info.resize(base + 32, make_int4(0, 0, 0, 0));
-        g_nodes.resize(base + 32, make_int4(0, 0, 0, 0));
-        size_t at = base;
-        // quads first so that a mixed chunk splits into at most two divergent halves
-        for (int pass = 1; pass >= 0; pass--)
-            for (int64_t p = row; p < r1; p++)
-                for (int k = cnt[p]; k < cnt[p + 1]; k++)
-                    if (inc[k].type == pass) {
-                        const int nen = pass ? 4 : 3, I = inc[k].I;
-                        const int32_t *en = pass ? &quad[4 * (int64_t)inc[k].eidx] : &tri[3 * (int64_t)inc[k].eidx];
-                        const int32_t *ps = pass ? &qpos[16 * (int64_t)inc[k].eidx + 4 * I] : &tpos[9 * (int64_t)inc[k].eidx + 3 * I];
-                        int nd[4] = {0, 0, 0, 0};
-                        unsigned slots = 0, mbits = 0;
-                        for (int j = 0; j < nen; j++) {
-                            nd[j] = en[j];
-                            slots |= (unsigned)(ps[j] & 0xff) << (8 * j);
-                            mbits |= (unsigned)(mask[en[j]] & 0x3f) << (8 * j);
-                        }
-                        const unsigned soff = (unsigned)(36 * (nptr[p] - nptr[row]));
-                        const unsigned deg = (unsigned)(nptr[p + 1] - nptr[p]);
-                        g_info[at] = make_int4(I | (inc[k].type << 2) | ((int)phase[k] << 3) | (1 << 8), (int)(soff | (deg << 16)), (int)mbits, (int)slots);
-                        g_nodes[at] = make_int4(nd[0], nd[1], nd[2], nd[3]);
-                        at++;
-                    }
-        chunks.push_back(ch);
-        row = r1;
-    }
+    const std::vector<GatherChunk> &chunks = plan.chunks;
+    const std::vector<int32_t> &g_info = plan.info, &g_nodes = plan.nodes;
     c->n_g_chunks = (int64_t)chunks.size();
     FS_CUDA(c, c->d_g_chunks.alloc(chunks.size()));
-    FS_CUDA(c, c->d_g_info.alloc(g_info.size()));
-    FS_CUDA(c, c->d_g_nodes.alloc(g_nodes.size()));
+    FS_CUDA(c, c->d_g_info.alloc(g_info.size() / 4));
+    FS_CUDA(c, c->d_g_nodes.alloc(g_nodes.size() / 4));
     FS_CUDA(c, cudaMemcpy(c->d_g_chunks.p, chunks.data(), sizeof(GatherChunk) * chunks.size(), cudaMemcpyHostToDevice));
-    FS_CUDA(c, cudaMemcpy(c->d_g_info.p, g_info.data(), sizeof(int4) * g_info.size(), cudaMemcpyHostToDevice));
-    FS_CUDA(c, cudaMemcpy(c->d_g_nodes.p, g_nodes.data(), sizeof(int4) * g_nodes.size(), cudaMemcpyHostToDevice));
+    FS_CUDA(c, cudaMemcpy(c->d_g_info.p, g_info.data(), sizeof(int32_t) * g_info.size(), cudaMemcpyHostToDevice));
+    FS_CUDA(c, cudaMemcpy(c->d_g_nodes.p, g_nodes.data(), sizeof(int32_t) * g_nodes.size(), cudaMemcpyHostToDevice));
     constexpr int smem = GATHER_WARPS * GATHER_WARP_VALS * (int)sizeof(double);
     FS_CUDA(c, cudaFuncSetAttribute(k_assemble_gather<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     FS_CUDA(c, cudaFuncSetAttribute(k_assemble_gather<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

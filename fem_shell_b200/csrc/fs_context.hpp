@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/femshell_b200.h"
+#include "fs_gather_plan.hpp"
 #include "fs_mlpc.cuh"
 
 struct ncclComm;
@@ -61,15 +62,6 @@ struct CgState {
     long long max_its;
     int done;         // 1 -> all later kernels of the batch are no-ops
     int status;       // FS_OK / FS_ERR_NOT_CONVERGED / FS_ERR_BREAKDOWN
-};
-
-// one warp of the row-gather assembly: a run of block rows accumulated in shared memory (fs_assembly.cu)
-struct GatherChunk {
-    long long val_off;   // first CSR value of the run (36 * nptr[row0])
-    int val_count;       // 36 * (nptr[row1] - nptr[row0]) doubles staged in shared memory
-    int n_rounds;        // phases of the chunk's emit steps (build_gather_schedule)
-    int n_threads;       // valid entries among the chunk's 32 thread-table slots
-    int pad;
 };
 
 struct Peer {

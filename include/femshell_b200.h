@@ -236,6 +236,16 @@ int fs_partition_plan(int64_t n_nodes, int64_t n_elem, const int64_t *eptr, cons
                       int rank, int world, int64_t sizes[8], int32_t *local_to_global, int32_t *loc_elems,
                       int32_t *send_idx, int64_t *peer_table);
 
+/* host-only: the schedule of the row-gather assembly pass (fs_assemble, FS_ASM_GATHER) for a single-rank mesh given
+ * in dof-node numbering -- which (element, node row) pairs each warp forms, where they add their 6x6 blocks and in
+ * which conflict-free phase.  Test hook of fem_shell_b200/csrc/fs_gather_plan.cpp; needs no GPU.  Two-call protocol
+ * (NULL arrays -> sizes only): sizes = {n_chunks, available (0: a block row does not fit a warp, the context would use
+ * the coloured pass), n_blocks}; chunks rows = {val_off, val_count, n_phases, n_threads}; info / nodes = 32 entries of
+ * 4 ints per chunk (layout: fs_gather_plan.hpp); nptr_out / nadj_out = the node-block pattern the slots refer to. */
+int fs_gather_plan(int64_t n_nodes, int64_t n_elem, const int32_t *etype, const int64_t *eptr, const int32_t *enodes,
+                   const uint8_t *mask /* may be NULL */, int warp_vals, int64_t sizes[3], int64_t *chunks, int32_t *info,
+                   int32_t *nodes, int32_t *nptr_out, int32_t *nadj_out);
+
 /* ---- reference file formats and generator (host side) ------------------ */
 /* in-memory meshGen (src/meshgen/main_all.cpp:133-387), incl. the 6-significant-digit text
  * round trip of coordinates and load factor.  Two-call protocol: pass NULL arrays to get sizes. */

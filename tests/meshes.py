@@ -90,3 +90,45 @@ def elements_as_mesh(elems):
         eptr.append(len(enodes))
     return dict(xyz=np.array(xyz), etype=np.array(etype, np.int32), eptr=np.array(eptr, np.int64),
                 enodes=np.array(enodes, np.int32), bc=np.zeros((0, 3), np.int32))
+
+
+def umbrella(n_spokes=14, n_rings=4, cone=0.35, mixed=True):
+    """Unstructured shell around a hub: `n_spokes` triangles meet at node 0 (all with the hub as their FIRST local
+    node, so every pair of them clashes in the gather schedule's step 0), followed by rings of quads (or, with
+    `mixed`, alternating rings of quads and triangle pairs) on a shallow cone.  Outer ring clamped (id 1), a point
+    load and a moment at the hub.  High valence + identical local indices = worst case for the emit phases."""
+    xyz = [(0.0, 0.0, 0.0)]
+    ring = lambda r: [1 + (r - 1) * n_spokes + k for k in range(n_spokes)]
+    for r in range(1, n_rings + 1):
+        for k in range(n_spokes):
+            a = 2 * np.pi * (k + 0.13 * r) / n_spokes
+            rad = r * (1.0 + 0.07 * np.sin(3 * a))
+            xyz.append((rad * np.cos(a), rad * np.sin(a), cone * rad))
+    etype, enodes, eptr, bc = [], [], [0], []
+    r1 = ring(1)
+    for k in range(n_spokes):
+        etype.append(TRI3)
+        enodes.extend((0, r1[k], r1[(k + 1) % n_spokes]))
+        eptr.append(len(enodes))
+    for r in range(1, n_rings):
+        a, b = ring(r), ring(r + 1)
+        for k in range(n_spokes):
+            k1 = (k + 1) % n_spokes
+            if mixed and r % 2 == 0:
+                for tri in ((a[k], b[k], a[k1]), (a[k1], b[k], b[k1])):
+                    if r == n_rings - 1 and tri[2] == b[k1]:
+                        bc.append((len(etype), 1, 1))       # side b[k] -> b[k1] lies on the outer ring
+                    etype.append(TRI3)
+                    enodes.extend(tri)
+                    eptr.append(len(enodes))
+            else:
+                if r == n_rings - 1:
+                    bc.append((len(etype), 1, 1))           # side b[k] -> b[k1]
+                etype.append(QUAD4)
+                enodes.extend((a[k], b[k], b[k1], a[k1]))
+                eptr.append(len(enodes))
+    xyz = np.array(xyz) @ rotation(0.2, 0.4, -0.3).T
+    F = np.zeros((xyz.shape[0], 6))
+    F[0] = (0.3, -0.2, -5.0, 0.4, 0.1, 0.0)
+    return dict(xyz=xyz, etype=np.array(etype, np.int32), eptr=np.array(eptr, np.int64),
+                enodes=np.array(enodes, np.int32), bc=np.array(bc, np.int32).reshape(-1, 3), forces=F)

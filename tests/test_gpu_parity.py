@@ -96,6 +96,11 @@ CASES = {
     "tri_ur": lambda fsb: (fsb.meshgen("t", 9, 13, -1, 0, 4, 6, (0, 0, -1, 1), 2.0, 1, 0, "y"), 0.25, 3e4, 1.0),
     "c5_folded": lambda fsb: (meshes.folded_cantilever(), 0.3, 1e4, 0.25),
     "c5_skewed": lambda fsb: (meshes.folded_cantilever(skew=0.35), 0.3, 1e4, 0.25),
+    # unstructured: 14 triangles share the hub as their first local node (14 emit phases), mixed rings behind them
+    "umbrella_mixed": lambda fsb: (meshes.umbrella(mixed=True, n_rings=5), 0.3, 1e4, 0.25),
+    "umbrella_quads": lambda fsb: (meshes.umbrella(mixed=False, n_rings=4), 0.3, 1e4, 0.25),
+    # 40 elements at one node do not fit a warp of the row-gather pass: the context falls back to the coloured pass
+    "umbrella_hub40": lambda fsb: (meshes.umbrella(n_spokes=40, mixed=True, n_rings=3), 0.3, 1e4, 0.25),
 }
 
 
