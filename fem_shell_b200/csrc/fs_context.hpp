@@ -170,6 +170,7 @@ struct fs_context {
     unsigned long long sell_mask = 0;      // the kernel mask in use (superset of sell_detected)
     int sell_nz = 36, sell_kind = -1;
     int64_t sell_slices = 0, sell_slots = 0;
+    int sell_dmax_max = 0;                 // widest slice (blocks per row): sizes the shared memory of k_sell_fill_t
     fs::DevBuf<int32_t> d_sell_sptr, d_sell_adj;
     fs::DevBuf<double> d_sell_vals;
     fs::DevBuf<unsigned long long> d_sell_mask;

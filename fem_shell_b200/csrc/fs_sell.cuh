@@ -188,4 +188,78 @@ static __global__ void __launch_bounds__(256) k_sell_fill(int n_own, int n_slice
     }
 }
 
+// Same copy as k_sell_fill, but every byte moves coalesced: block = one slice (32 block rows, contiguous in the
+// parity array), the four warps stream the rows into shared memory (row stride odd -> the transposed reads below
+// are bank-conflict free), then lane = row writes whole 256-byte lines of the sliced-ELL layout.  The union
+// pattern of the blocks is measured on the way (what k_sell_detect does in a pass of its own), so a re-assembly
+// costs ONE read of the parity values instead of two scattered ones (profiles/r01h: detect 0.42 ms + fill 1.46 ms
+// per values pass on c2 before this kernel).
+constexpr int SELL_FILL_THREADS = 256;
+
+static __global__ void __launch_bounds__(SELL_FILL_THREADS) k_sell_fill_t(int n_own, int own_lo, unsigned long long mask,
+                                                                 const int32_t *__restrict__ nptr, const int32_t *__restrict__ nadj,
+                                                                 const double *__restrict__ full, const int32_t *__restrict__ sptr,
+                                                                 int32_t *__restrict__ adj, double *__restrict__ vals, int nz,
+                                                                 int write_adj, unsigned long long *mask_out)
+{
+    constexpr int NW = SELL_FILL_THREADS / 32;
+    extern __shared__ double sm_rows[];
+    __shared__ int s_ab[36];
+    const int s = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int s0 = sptr[s], dmax = sptr[s + 1] - s0;
+    const int S = (36 * dmax) | 1;
+    const int p = 32 * s + lane;
+    const bool live = p < n_own;
+    const int b0 = live ? nptr[p] : 0, deg = live ? nptr[p + 1] - b0 : 0, L = 6 * deg;
+    if (threadIdx.x < 36) {  // item -> (a, b) of the mask's set bits, row-major
+        const int a = threadIdx.x / 6, b = threadIdx.x % 6;
+        if (mask & sell_bit(a, b)) s_ab[sell_popcount(mask & (sell_bit(a, b) - 1))] = (a << 4) | b;
+    }
+    unsigned long long m = 0;
+#pragma unroll
+    for (int rr = 0; rr < 32 / NW; rr++) {  // the rows of a warp are independent: all their loads are in flight together
+        const int r = NW * rr + w;
+        const int rb0 = __shfl_sync(0xffffffffu, b0, r), rL = __shfl_sync(0xffffffffu, L, r);
+        const double2 *src2 = reinterpret_cast<const double2 *>(full + (size_t)36 * rb0);  // 288-byte multiples: aligned
+        double *dst = sm_rows + (size_t)r * S;
+        const int n2 = 3 * rL;  // double2 items of the row (36 * deg / 2)
+        for (int base = 0; base < n2; base += 6 * 32) {
+            double2 buf[6];
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                const int idx = base + 32 * i + lane;
+                buf[i] = idx < n2 ? __ldcs(src2 + idx) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                const int idx = base + 32 * i + lane;
+                if (idx < n2) {
+                    const int k = 2 * idx;  // k even, rL even: k and k+1 lie in the same scalar row a, b = k % 6 does not wrap
+                    dst[k] = buf[i].x;
+                    dst[k + 1] = buf[i].y;
+                    const int a = (k >= rL) + (k >= 2 * rL) + (k >= 3 * rL) + (k >= 4 * rL) + (k >= 5 * rL), b = k % 6;
+                    if (buf[i].x != 0.0) m |= sell_bit(a, b);
+                    if (buf[i].y != 0.0) m |= sell_bit(a, b + 1);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+    if (lane == 0 && (m & ~mask)) atomicOr(mask_out, m);  // only a pattern outside the mask needs reporting
+    __syncthreads();
+    const int self = own_lo + (live ? p : 0);
+    if (write_adj)
+        for (int slot = w; slot < dmax; slot += NW) adj[32 * (size_t)(s0 + slot) + lane] = slot < deg ? nadj[b0 + slot] : self;
+    const double *row = sm_rows + (size_t)lane * S;
+    double *base = vals + 32 * ((size_t)nz * s0) + lane;
+    const int n_lines = dmax * nz;  // one 256-byte line per (slot, item)
+#pragma unroll 4
+    for (int q = w; q < n_lines; q += NW) {
+        const int slot = q / nz, ab = s_ab[q - slot * nz];
+        const double v = slot < deg ? row[(ab >> 4) * L + 6 * slot + (ab & 15)] : 0.0;
+        __stcs(base + 32 * (size_t)q, v);
+    }
+}
+
 }  // namespace fs

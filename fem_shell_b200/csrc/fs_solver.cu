@@ -402,6 +402,30 @@ static void drop_cg_graph(fs_context *c)
     c->cg_graph_exec = nullptr;
 }
 
+// shared memory of k_sell_fill_t for the widest slice of this mesh, or 0 when a slice does not fit an SM
+static size_t sell_fill_smem(const fs_context *c)
+{
+    const size_t bytes = (size_t)32 * ((36 * (size_t)c->sell_dmax_max) | 1) * sizeof(double);
+    return bytes <= 200 * 1024 ? bytes : 0;
+}
+
+static int sell_fill(fs_context *c, unsigned long long mask, int nz, int write_adj)
+{
+    const int n_own = (int)c->n_own, n_slices = (int)c->sell_slices;
+    const size_t smem = sell_fill_smem(c);
+    if (smem) {
+        FS_CUDA(c, cudaFuncSetAttribute(k_sell_fill_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_sell_fill_t<<<n_slices, SELL_FILL_THREADS, smem, c->stream>>>(n_own, (int)c->own_lo, mask, c->d_nptr.p, c->d_nadj.p, c->d_vals.p,
+                                                                        c->d_sell_sptr.p, c->d_sell_adj.p, c->d_sell_vals.p, nz, write_adj,
+                                                                        c->d_sell_mask.p);
+    } else {
+        k_sell_fill<<<nblk(n_slices, 8), 256, 0, c->stream>>>(n_own, n_slices, (int)c->own_lo, mask, c->d_nptr.p, c->d_nadj.p, c->d_vals.p,
+                                                               c->d_sell_sptr.p, c->d_sell_adj.p, c->d_sell_vals.p, nz, write_adj);
+    }
+    FS_CUDA(c, cudaGetLastError());
+    return FS_OK;
+}
+
 int spmv_format_prepare(fs_context *c)
 {
     if (c->sell_checked) return FS_OK;
@@ -418,8 +442,21 @@ int spmv_format_prepare(fs_context *c)
     const int n_own = (int)c->n_own;
     if (c->d_sell_mask.n < 1) FS_CUDA(c, c->d_sell_mask.alloc(1));
     FS_CUDA(c, cudaMemsetAsync(c->d_sell_mask.p, 0, sizeof(unsigned long long), st));
-    k_sell_detect<<<c->sm_count * 8, 256, 0, st>>>(n_own, c->d_nptr.p, c->d_vals.p, c->d_sell_mask.p);
     unsigned long long m = 0;
+    // Re-assembly of a mesh that iterated on the compacted copy before: copy with the same mask in one pass and
+    // let the copy kernel report any entry outside it; only then fall back to detect -> decide -> fill.
+    if (was && c->sell_layout_ready && sell_fill_smem(c) && c->d_sell_vals.n >= (size_t)32 * c->sell_nz * c->sell_slots) {
+        int rc = sell_fill(c, old_mask, c->sell_nz, 0);
+        if (rc) return rc;
+        FS_CUDA(c, cudaMemcpyAsync(&m, c->d_sell_mask.p, sizeof m, cudaMemcpyDeviceToHost, st));
+        FS_CUDA(c, cudaStreamSynchronize(st));
+        if ((m & ~old_mask) == 0) {
+            c->sell_active = true;
+            return FS_OK;
+        }
+        FS_CUDA(c, cudaMemsetAsync(c->d_sell_mask.p, 0, sizeof(unsigned long long), st));
+    }
+    k_sell_detect<<<c->sm_count * 8, 256, 0, st>>>(n_own, c->d_nptr.p, c->d_vals.p, c->d_sell_mask.p);
     FS_CUDA(c, cudaMemcpyAsync(&m, c->d_sell_mask.p, sizeof m, cudaMemcpyDeviceToHost, st));
     FS_CUDA(c, cudaStreamSynchronize(st));
     c->sell_detected = m;
@@ -442,11 +479,20 @@ int spmv_format_prepare(fs_context *c)
         DevBuf<char> tmp;
         FS_CUDA(c, tmp.alloc(bytes));
         FS_CUDA(c, cub::DeviceScan::ExclusiveSum(tmp.p, bytes, dmax.p, c->d_sell_sptr.p, n_slices + 1, st));
-        int32_t total = 0;
+        DevBuf<int32_t> dmx;
+        FS_CUDA(c, dmx.alloc(1));
+        size_t bytes2 = 0;
+        FS_CUDA(c, cub::DeviceReduce::Max(nullptr, bytes2, dmax.p, dmx.p, n_slices, st));
+        DevBuf<char> tmp2;
+        FS_CUDA(c, tmp2.alloc(bytes2));
+        FS_CUDA(c, cub::DeviceReduce::Max(tmp2.p, bytes2, dmax.p, dmx.p, n_slices, st));
+        int32_t total = 0, widest = 0;
         FS_CUDA(c, cudaMemcpyAsync(&total, c->d_sell_sptr.p + n_slices, sizeof total, cudaMemcpyDeviceToHost, st));
+        FS_CUDA(c, cudaMemcpyAsync(&widest, dmx.p, sizeof widest, cudaMemcpyDeviceToHost, st));
         FS_CUDA(c, cudaStreamSynchronize(st));
         c->sell_slices = n_slices;
         c->sell_slots = total;
+        c->sell_dmax_max = widest;
         FS_CUDA(c, c->d_sell_adj.alloc((size_t)32 * total));
         c->sell_layout_ready = true;
         write_adj = 1;
@@ -454,9 +500,9 @@ int spmv_format_prepare(fs_context *c)
     const int nz = sell_popcount(mask);
     const size_t need = (size_t)32 * nz * c->sell_slots;
     if (c->d_sell_vals.n < need) FS_CUDA(c, c->d_sell_vals.alloc(need));
-    k_sell_fill<<<nblk(n_slices, 8), 256, 0, st>>>(n_own, n_slices, (int)c->own_lo, mask, c->d_nptr.p, c->d_nadj.p, c->d_vals.p,
-                                                   c->d_sell_sptr.p, c->d_sell_adj.p, c->d_sell_vals.p, nz, write_adj);
-    FS_CUDA(c, cudaGetLastError());
+    FS_CUDA(c, cudaMemsetAsync(c->d_sell_mask.p, 0, sizeof(unsigned long long), st));
+    int rc = sell_fill(c, mask, nz, write_adj);
+    if (rc) return rc;
     c->sell_active = true;
     c->sell_mask = mask;
     c->sell_nz = nz;
