@@ -359,7 +359,8 @@ k_dense_matvec(int n, const double *__restrict__ Minv, const double *__restrict_
 // set-up kernels
 // ---------------------------------------------------------------------------------------------
 // probing vector on a lattice: unit mode `mode` on every cell of colour col (index mod 3 per active dimension)
-__global__ void k_lat_set_probe(const __grid_constant__ LatGeom g, int c0, int c1, int c2, int mode, double *__restrict__ e)
+// mode2 >= 0: a second unit mode from the OTHER decoupled class rides along (see ml_probe_pairs)
+__global__ void k_lat_set_probe(const __grid_constant__ LatGeom g, int c0, int c1, int c2, int mode, int mode2, double *__restrict__ e)
 {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= g.n) return;
@@ -367,14 +368,19 @@ __global__ void k_lat_set_probe(const __grid_constant__ LatGeom g, int c0, int c
     lat_unindex(g, a, k);
     const bool hit = (!g.active[0] || k[0] % 3 == c0) && (!g.active[1] || k[1] % 3 == c1) && (!g.active[2] || k[2] % 3 == c2);
     double v[6] = {0, 0, 0, 0, 0, 0};
-    if (hit) v[mode] = 1.0;
+    if (hit) {
+        v[mode] = 1.0;
+        if (mode2 >= 0) v[mode2] = 1.0;
+    }
     store6(e + 6 * (size_t)a, v);
 }
 
 // y = -(P^T A P) e for the probing vector above: column `mode` of the block coupling each cell to its one
 // neighbour of colour col
-__global__ void k_lat_collect(const __grid_constant__ LatGeom g, int c0, int c1, int c2, int mode, const double *__restrict__ y,
-                              double *__restrict__ A)
+// With a paired probe (mode2 >= 0) row i of the response belongs to the column of the mode in ITS class (bit i of
+// class_a set: the class of `mode`); its entry in the other column is a structural zero and stays zero.
+__global__ void k_lat_collect(const __grid_constant__ LatGeom g, int c0, int c1, int c2, int mode, int mode2, unsigned class_a,
+                              const double *__restrict__ y, double *__restrict__ A)
 {
     const int64_t n6 = 6 * (int64_t)g.n;
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -389,7 +395,8 @@ __global__ void k_lat_collect(const __grid_constant__ LatGeom g, int c0, int c1,
         if (kk < 0 || kk >= g.np[d]) return;
     }
     const int s = lat_stencil_slot(g, o);
-    A[(size_t)(6 * s + mode) * n6 + t] = -y[t];
+    const int column = (mode2 < 0 || ((class_a >> (int)(t - 6 * (int64_t)a)) & 1u)) ? mode : mode2;
+    A[(size_t)(6 * s + column) * n6 + t] = -y[t];
 }
 
 // generalised inverse of a symmetric positive semi-definite 6x6 block: Gauss-Jordan with diagonal pivoting; pivots
@@ -819,6 +826,27 @@ static int lat_lambda(fs_context *c, int l, double *lam)
     return FS_OK;
 }
 
+// Probing pairs.  On a shell lying in a coordinate plane the in-plane unknowns (two translations and the rotation
+// about the normal) and the out-of-plane ones (deflection and the two tilts) never couple -- that is the block
+// pattern the compacted SpMV format was detected from (fs_sell.cuh), the rigid-body modes about cell centres IN
+// the plane keep it, and so does every coarse stencil.  One in-plane and one out-of-plane unit mode can then be
+// probed with the same vector and separated by the class of the responding row: 3 probes per colour instead of 6,
+// with bit-identical stencils.
+static void ml_probe_pairs(const fs_context *c, int *n, int a[6], int b[6], unsigned *class_a)
+{
+    if (!c->sell_active || c->sell_kind < 0 || c->sell_kind > 2) return;
+    static const int in_plane[3][3] = {{0, 1, 5}, {0, 2, 4}, {1, 2, 3}}, out_plane[3][3] = {{2, 3, 4}, {1, 3, 5}, {0, 4, 5}};
+    const int normal = c->sell_kind == 0 ? 2 : (c->sell_kind == 1 ? 1 : 0);
+    if (c->bbox_hi[normal] != c->bbox_lo[normal]) return;  // the lattice centres must lie in the plane of the shell
+    *n = 3;
+    *class_a = 0;
+    for (int k = 0; k < 3; k++) {
+        a[k] = in_plane[c->sell_kind][k];
+        b[k] = out_plane[c->sell_kind][k];
+        *class_a |= 1u << a[k];
+    }
+}
+
 int ml_prepare(fs_context *c)
 {
     if (!c->ml_geom_ready) {
@@ -847,11 +875,15 @@ int ml_prepare(fs_context *c)
         // stencil of this level by probing the level below through the cycle's own transfer operators
         FS_CUDA(c, cudaMemsetAsync(L.A.p, 0, sizeof(double) * (size_t)g.ns * 6 * n6, st));
         const int nc0 = g.active[0] ? 3 : 1, nc1 = g.active[1] ? 3 : 1, nc2 = g.active[2] ? 3 : 1;
+        int n_probe = 6, probe_a[6] = {0, 1, 2, 3, 4, 5}, probe_b[6] = {-1, -1, -1, -1, -1, -1};
+        unsigned class_a = 0;
+        ml_probe_pairs(c, &n_probe, probe_a, probe_b, &class_a);
         for (int c2 = 0; c2 < nc2; c2++)
             for (int c1 = 0; c1 < nc1; c1++)
                 for (int c0 = 0; c0 < nc0; c0++)
-                    for (int mode = 0; mode < 6; mode++) {
-                        k_lat_set_probe<<<nblk(g.n, 256), 256, 0, st>>>(g, c0, c1, c2, mode, L.xb.p);
+                    for (int pi = 0; pi < n_probe; pi++) {
+                        const int mode = probe_a[pi], mode2 = probe_b[pi];
+                        k_lat_set_probe<<<nblk(g.n, 256), 256, 0, st>>>(g, c0, c1, c2, mode, mode2, L.xb.p);
                         if (l == 0) {
                             rc = fine_prolong_chain(c, L.xb.p, c->d_z.p, false, 0);
                             if (rc) return rc;
@@ -861,7 +893,7 @@ int ml_prepare(fs_context *c)
                             lat_prolong_chain(c, l - 1, L.xb.p, m.lat[l - 1].x.p, false, 0);
                             lat_restrict_chain(c, l - 1, nullptr, m.lat[l - 1].x.p, 0);
                         }
-                        k_lat_collect<<<nblk(n6, 256), 256, 0, st>>>(g, c0, c1, c2, mode, L.b.p, L.A.p);
+                        k_lat_collect<<<nblk(n6, 256), 256, 0, st>>>(g, c0, c1, c2, mode, mode2, class_a, L.b.p, L.A.p);
                     }
         FS_CUDA(c, cudaGetLastError());
         if (L.dense) {
