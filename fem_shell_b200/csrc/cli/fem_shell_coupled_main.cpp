@@ -64,7 +64,8 @@ int main(int argc, char **argv)
         fs_solve_opts &o = es.solver_options();
         o.rtol = rtol;
         o.max_its = max_it;
-        o.pc = pc == "pbjacobi" ? FS_PC_BJACOBI6 : (pc == "none" ? FS_PC_NONE : FS_PC_JACOBI);
+        o.pc = pc == "pbjacobi" ? FS_PC_BJACOBI6 : (pc == "none" ? FS_PC_NONE : (pc == "mg" ? FS_PC_MLRBM : FS_PC_JACOBI));
+        if (o.pc == FS_PC_MLRBM) o.norm_type = FS_NORM_UNPRECONDITIONED;
         es.init();
         int64_t n_if = 0;
         es.check(fs_interface_nodes(es.context(), &n_if, nullptr));

@@ -2,7 +2,7 @@
 // (main: fs.cpp:14-185, flags: fs.cpp:194-267) on top of the B200 library.
 //
 //   fem-shell -nu <v> -e <v> -t <v> -mesh <file.xda> [-out <name>] [-d 1]
-//             [-ksp_type cg] [-pc_type jacobi|pbjacobi|none] [-ksp_rtol r] [-ksp_max_it n]
+//             [-ksp_type cg] [-pc_type jacobi|pbjacobi|none|mg] [-ksp_rtol r] [-ksp_max_it n]
 //             [-ksp_norm_type preconditioned|unpreconditioned] [-dof_order libmesh|node] [-device k]
 //
 // Flags after the reference's own six are the PETSc options the reference passes through to KSP
@@ -96,8 +96,9 @@ int main(int argc, char **argv)
         fs_solve_opts &o = es.solver_options();
         o.rtol = a.rtol;
         o.max_its = a.max_it;
-        o.pc = a.pc == "pbjacobi" ? FS_PC_BJACOBI6 : (a.pc == "none" ? FS_PC_NONE : FS_PC_JACOBI);
-        o.norm_type = a.norm == "unpreconditioned" ? FS_NORM_UNPRECONDITIONED : FS_NORM_PRECONDITIONED;
+        o.pc = a.pc == "pbjacobi" ? FS_PC_BJACOBI6 : (a.pc == "none" ? FS_PC_NONE : (a.pc == "mg" ? FS_PC_MLRBM : FS_PC_JACOBI));
+        // the multilevel cycle is not a fixed diagonal scaling: only the true residual norm is defined for it
+        o.norm_type = (a.norm == "unpreconditioned" || o.pc == FS_PC_MLRBM) ? FS_NORM_UNPRECONDITIONED : FS_NORM_PRECONDITIONED;
         es.init();
         int64_t n_dofnodes = 0, n_blocks = 0;
         fs_get_sizes(es.context(), &n_dofnodes, &n_blocks, nullptr, nullptr, nullptr);

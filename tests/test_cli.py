@@ -64,14 +64,15 @@ def test_fem_shell_cli_reproduces_thesis_values(fso, ref_meshes, tmp_path):
             f.write("%d\n1.0\n" % mesh.n_nodes)
             for row in F:
                 f.write(" ".join(repr(float(v)) for v in row) + "\n")
-        r = subprocess.run([os.path.join(BIN, "fem-shell")] + flags + ["-mesh", base + ".xda", "-out", base, "-pc_type", "pbjacobi",
-                            "-ksp_max_it", "100000"], capture_output=True, text=True, timeout=300)
-        assert r.returncode == 0, r.stdout[-2000:] + r.stderr
-        assert "Read command-line arguments.......OK" in r.stdout and "All done :)" in r.stdout
-        u = _solution_rows(r.stdout)
-        assert u.shape == (mesh.n_nodes, 6)
-        for node, var, gold in checks:
-            assert float("%.6g" % u[node, var]) == pytest.approx(gold, rel=2e-6)
+        for pc in ("pbjacobi", "mg"):   # the reference's documented block Jacobi, and the multilevel cycle
+            r = subprocess.run([os.path.join(BIN, "fem-shell")] + flags + ["-mesh", base + ".xda", "-out", base, "-pc_type", pc,
+                                "-ksp_max_it", "100000"], capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr
+            assert "Read command-line arguments.......OK" in r.stdout and "All done :)" in r.stdout
+            u = _solution_rows(r.stdout)
+            assert u.shape == (mesh.n_nodes, 6)
+            for node, var, gold in checks:
+                assert float("%.6g" % u[node, var]) == pytest.approx(gold, rel=2e-6)
         assert os.path.exists(base + ".vtk")
         vtk = open(base + ".vtk").read()
         assert "POINTS %d double" % mesh.n_nodes in vtk and "SCALARS tz double 1" in vtk
