@@ -3,6 +3,8 @@
 
 #include <algorithm>
 
+#include "../../include/femshell_b200.h"
+
 namespace fs {
 
 bool plan_gather(int64_t n_own, int own_lo, int64_t nt, const int32_t *tri, const int32_t *tgid, const int32_t *tpos, int64_t nq,
@@ -122,15 +124,15 @@ extern "C" int fs_gather_plan(int64_t n_nodes, int64_t n_elem, const int32_t *et
                               const uint8_t *mask, int warp_vals, int64_t sizes[3], int64_t *chunks, int32_t *info, int32_t *nodes,
                               int32_t *nptr_out, int32_t *nadj_out)
 {
-    if (n_nodes <= 0 || n_elem <= 0 || !etype || !eptr || !enodes || !sizes || warp_vals <= 0) return -1;
+    if (n_nodes <= 0 || n_elem <= 0 || !etype || !eptr || !enodes || !sizes || warp_vals <= 0) return FS_ERR_ARG;
     std::vector<std::vector<int32_t>> adj(n_nodes);
     std::vector<int32_t> tri, quad, tgid, qgid;
     for (int64_t e = 0; e < n_elem; e++) {
         const int nen = (int)(eptr[e + 1] - eptr[e]);
-        if ((etype[e] == 3 && nen != 3) || (etype[e] == 5 && nen != 4) || (etype[e] != 3 && etype[e] != 5)) return -1;
+        if ((etype[e] == FS_TRI3 && nen != 3) || (etype[e] == FS_QUAD4 && nen != 4) || (etype[e] != FS_TRI3 && etype[e] != FS_QUAD4)) return FS_ERR_ARG;
         const int32_t *en = enodes + eptr[e];
         for (int i = 0; i < nen; i++) {
-            if (en[i] < 0 || en[i] >= n_nodes) return -1;
+            if (en[i] < 0 || en[i] >= n_nodes) return FS_ERR_ARG;
             for (int j = 0; j < nen; j++) adj[en[i]].push_back(en[j]);
             (nen == 3 ? tri : quad).push_back(en[i]);
         }
@@ -167,7 +169,7 @@ extern "C" int fs_gather_plan(int64_t n_nodes, int64_t n_elem, const int32_t *et
     sizes[2] = (int64_t)nadj.size();
     if (nptr_out) std::copy(nptr.begin(), nptr.end(), nptr_out);
     if (nadj_out) std::copy(nadj.begin(), nadj.end(), nadj_out);
-    if (!ok) return 0;
+    if (!ok) return FS_OK;
     if (chunks)
         for (size_t i = 0; i < plan.chunks.size(); i++) {
             chunks[4 * i + 0] = plan.chunks[i].val_off;
@@ -177,5 +179,5 @@ extern "C" int fs_gather_plan(int64_t n_nodes, int64_t n_elem, const int32_t *et
         }
     if (info) std::copy(plan.info.begin(), plan.info.end(), info);
     if (nodes) std::copy(plan.nodes.begin(), plan.nodes.end(), nodes);
-    return 0;
+    return FS_OK;
 }
