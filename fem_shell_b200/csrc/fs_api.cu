@@ -41,6 +41,8 @@ int fs_create(fs_context **out, int device)
     c->device = device;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) != cudaSuccess ||
         cudaMallocHost((void **)&c->h_state, sizeof(CgState)) != cudaSuccess) {
         delete c;
         return FS_ERR_CUDA;
@@ -67,6 +69,11 @@ int fs_destroy(fs_context *c)
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamDestroy(c->copy_stream);
+    }
     cudaStream_t st = c->stream;
     delete c;  // frees the device buffers
     if (st) cudaStreamDestroy(st);
@@ -517,8 +524,28 @@ int fs_solve_host(fs_context *c, const double *F, int reassemble, const fs_solve
                   fs_solve_info *info)
 {
     FS_CHECK_CTX(c);
-    if (F) FS_TRY(fs_set_nodal_loads(c, F));
-    if (reassemble || !c->assembled) FS_TRY(fs_assemble(c, nullptr));
+    if (F && (reassemble || !c->assembled) && c->pattern_ready) {
+        // the loads travel host -> device on the copy stream WHILE the values pass runs (the two are independent:
+        // the element loop needs no loads, fs.cpp:1211-1221 vs :1222-1226); the rhs is formed once both are done
+        FS_CUDA(c, cudaSetDevice(c->device));
+        FS_CUDA(c, cudaEventRecord(c->ev_copy, c->stream));  // earlier work on the context stream may still read the staging buffer
+        FS_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_copy, 0));
+        FS_CUDA(c, cudaMemcpyAsync(c->d_stage.p, F + 6 * c->span_lo, sizeof(double) * 6 * c->span_n, cudaMemcpyHostToDevice, c->copy_stream));
+        FS_CUDA(c, cudaEventRecord(c->ev_copy, c->copy_stream));
+        int rca = fs_assemble(c, nullptr);
+        if (rca) {
+            cudaStreamSynchronize(c->copy_stream);  // F is borrowed for the duration of the call only
+            return rca;
+        }
+        FS_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
+        k_loads_from_stage<<<nblk(6 * c->n_own, 256), 256, 0, c->stream>>>(c->n_own, c->d_node_of_own.p, c->span_lo, c->d_stage.p, c->d_F.p);
+        FS_CUDA(c, cudaGetLastError());
+        c->loads_set = true;
+        FS_TRY(build_rhs(c, 1.0));
+    } else {
+        if (F) FS_TRY(fs_set_nodal_loads(c, F));
+        if (reassemble || !c->assembled) FS_TRY(fs_assemble(c, nullptr));
+    }
     int rc = fs_solve(c, opts, info);
     if (rc != FS_OK && rc != FS_ERR_NOT_CONVERGED) return rc;
     if (!sols) return rc;  // the caller fetches its own rows with fs_get_solution_owned

@@ -100,6 +100,8 @@ struct fs_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t copy_stream = nullptr;    // host -> device load copies that overlap the values pass (fs_solve_host)
+    cudaEvent_t ev_copy = nullptr;
     std::string err;
 
     // distributed

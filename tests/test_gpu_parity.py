@@ -287,6 +287,23 @@ def test_owned_rows_of_the_solution(fso, fsb):
     s.close()
 
 
+def test_solve_host_takes_new_loads_with_every_reassembly(fso, fsb):
+    """the plugin call of the coupling loop (fsp.cpp:271-274): new loads in, values pass, solve, displacements out --
+    the load copy overlaps the values pass on a second stream, so stale or half-copied loads would show here"""
+    m, nu, E, t = CASES["quad24"](fsb)
+    om = as_fso_mesh(fso, m)
+    s = gpu_system(fsb, m, nu, E, t)
+    rng = np.random.default_rng(5)
+    U = np.empty((om.n_nodes, 6))
+    for k in range(4):
+        F = np.ascontiguousarray(m["forces"] * (1.0 + k) + rng.standard_normal(m["forces"].shape) * (k % 2))
+        info = s.solve_host(F, U, reassemble=(k != 2), rtol=1e-13, max_its=400000, pc=fsb.PC_BJACOBI6, warm_start=(k > 1))
+        assert info.status == 0
+        uo = fso.direct_solve(om, fso.assemble(om, F, nu, E, t))
+        assert np.linalg.norm(U - uo) <= 1e-8 * np.linalg.norm(uo), k
+    s.close()
+
+
 def test_max_its_and_error_paths(fso, fsb):
     m, nu, E, t = CASES["quad24"](fsb)
     s = gpu_system(fsb, m, nu, E, t, loads=m["forces"])
