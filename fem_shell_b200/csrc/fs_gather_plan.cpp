@@ -2,10 +2,30 @@
 #include "fs_gather_plan.hpp"
 
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <thread>
 
 #include "../../include/femshell_b200.h"
 
 namespace fs {
+
+// fn(begin, end) on contiguous pieces of [0, n); the pieces are independent (rows of the matrix / chunks of the table)
+template <class F>
+static void parallel_ranges(int64_t n, F fn)
+{
+    const unsigned hw = std::thread::hardware_concurrency();
+    int64_t T = std::max<int64_t>(1, std::min<int64_t>({(int64_t)(hw ? hw : 1), (int64_t)8, n / 65536}));
+    if (const char *forced = getenv("FS_PLAN_THREADS"))  // tests: the plan must not depend on the number of threads
+        T = std::max<int64_t>(1, std::min<int64_t>({(int64_t)atoi(forced), (int64_t)64, std::max<int64_t>(n, 1)}));
+    if (T == 1) {
+        fn((int64_t)0, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int64_t t = 0; t < T; t++) pool.emplace_back(fn, n * t / T, n * (t + 1) / T);
+    for (std::thread &th : pool) th.join();
+}
 
 bool plan_gather(int64_t n_own, int own_lo, int64_t nt, const int32_t *tri, const int32_t *tgid, const int32_t *tpos, int64_t nq,
                  const int32_t *quad, const int32_t *qgid, const int32_t *qpos, const int32_t *nptr, const uint8_t *mask,
@@ -31,33 +51,40 @@ bool plan_gather(int64_t n_own, int own_lo, int64_t nt, const int32_t *tri, cons
     // node at the same index -> a few phases.  Greedy colouring in a fixed order (triangles first, then by
     // element id) keeps the summation order of every CSR value a function of the mesh alone.
     std::vector<uint8_t> phase(inc.size(), 0);
-    for (int64_t p = 0; p < n_own; p++) {
-        std::sort(inc.begin() + cnt[p], inc.begin() + cnt[p + 1], [](const Inc &a, const Inc &b) {
-            return a.type != b.type ? a.type < b.type : a.gid < b.gid;
-        });
-        for (int k = cnt[p]; k < cnt[p + 1]; k++) {
-            const int nen = inc[k].type ? 4 : 3;
-            const int32_t *ek = inc[k].type ? &quad[4 * (int64_t)inc[k].eidx] : &tri[3 * (int64_t)inc[k].eidx];
-            unsigned used = 0;
-            for (int m = cnt[p]; m < k; m++) {
-                if (inc[m].type != inc[k].type) continue;  // quads and triangles are emitted one after the other
-                const int32_t *em = inc[m].type ? &quad[4 * (int64_t)inc[m].eidx] : &tri[3 * (int64_t)inc[m].eidx];
-                bool clash = false;
-                for (int j = 0; j < nen; j++) clash |= ek[j] == em[j];
-                if (clash) used |= 1u << phase[m];
+    std::atomic<bool> too_many(false);
+    parallel_ranges(n_own, [&](int64_t p0, int64_t p1) {
+        for (int64_t p = p0; p < p1; p++) {
+            std::sort(inc.begin() + cnt[p], inc.begin() + cnt[p + 1], [](const Inc &a, const Inc &b) {
+                return a.type != b.type ? a.type < b.type : a.gid < b.gid;
+            });
+            for (int k = cnt[p]; k < cnt[p + 1]; k++) {
+                const int nen = inc[k].type ? 4 : 3;
+                const int32_t *ek = inc[k].type ? &quad[4 * (int64_t)inc[k].eidx] : &tri[3 * (int64_t)inc[k].eidx];
+                unsigned used = 0;
+                for (int m = cnt[p]; m < k; m++) {
+                    if (inc[m].type != inc[k].type) continue;  // quads and triangles are emitted one after the other
+                    const int32_t *em = inc[m].type ? &quad[4 * (int64_t)inc[m].eidx] : &tri[3 * (int64_t)inc[m].eidx];
+                    bool clash = false;
+                    for (int j = 0; j < nen; j++) clash |= ek[j] == em[j];
+                    if (clash) used |= 1u << phase[m];
+                }
+                int ph = 0;
+                while (ph < 32 && ((used >> ph) & 1u)) ph++;
+                if (ph > 31) {  // more than 32 mutually clashing elements at one node
+                    too_many = true;
+                    ph = 31;
+                }
+                phase[k] = (uint8_t)ph;
             }
-            int ph = 0;
-            while (ph < 32 && ((used >> ph) & 1u)) ph++;
-            if (ph > 31) {  // more than 32 mutually clashing elements at one node: leave this mesh to the coloured pass
-                return false;
-            }
-            phase[k] = (uint8_t)ph;
         }
-    }
+    });
+    if (too_many) return false;
 
+    // packing: a sequential scan over the rows (cheap); the table is then filled chunk by chunk in parallel
     std::vector<GatherChunk> &chunks = plan.chunks;
     std::vector<int32_t> &g_info = plan.info, &g_nodes = plan.nodes;  // 32 entries of 4 ints per chunk
     chunks.clear(); g_info.clear(); g_nodes.clear();
+    std::vector<int64_t> first_row;
     int64_t row = 0;
     while (row < n_own) {
         int64_t r1 = row, vals = 0;
@@ -71,45 +98,48 @@ bool plan_gather(int64_t n_own, int own_lo, int64_t nt, const int32_t *tri, cons
             for (int k = cnt[r1]; k < cnt[r1 + 1]; k++) rounds = std::max(rounds, (int)phase[k] + 1);
             r1++;
         }
-        if (r1 == row) {  // a single row does not fit a warp: leave this mesh to the coloured pass
-            return false;
-        }
+        if (r1 == row) return false;  // a single row does not fit a warp: leave this mesh to the coloured pass
         GatherChunk ch;
         ch.val_off = 36 * (long long)nptr[row];
         ch.n_threads = threads;
         ch.n_rounds = rounds;
         ch.val_count = (int)vals;
         ch.pad = 0;
-        size_t at = g_info.size();
-        g_info.resize(at + 4 * 32, 0);
-        g_nodes.resize(at + 4 * 32, 0);
-        // quads first so that a mixed chunk splits into at most two divergent halves
-        for (int pass = 1; pass >= 0; pass--)
-            for (int64_t p = row; p < r1; p++)
-                for (int k = cnt[p]; k < cnt[p + 1]; k++)
-                    if (inc[k].type == pass) {
-                        const int nen = pass ? 4 : 3, I = inc[k].I;
-                        const int32_t *en = pass ? &quad[4 * (int64_t)inc[k].eidx] : &tri[3 * (int64_t)inc[k].eidx];
-                        const int32_t *ps = pass ? &qpos[16 * (int64_t)inc[k].eidx + 4 * I] : &tpos[9 * (int64_t)inc[k].eidx + 3 * I];
-                        int nd[4] = {0, 0, 0, 0};
-                        unsigned slots = 0, mbits = 0;
-                        for (int j = 0; j < nen; j++) {
-                            nd[j] = en[j];
-                            slots |= (unsigned)(ps[j] & 0xff) << (8 * j);
-                            mbits |= (unsigned)(mask[en[j]] & 0x3f) << (8 * j);
-                        }
-                        const unsigned soff = (unsigned)(36 * (nptr[p] - nptr[row]));
-                        const unsigned deg = (unsigned)(nptr[p + 1] - nptr[p]);
-                        g_info[at] = I | (inc[k].type << 2) | ((int)phase[k] << 3) | (1 << 8);
-                        g_info[at + 1] = (int)(soff | (deg << 16));
-                        g_info[at + 2] = (int)mbits;
-                        g_info[at + 3] = (int)slots;
-                        for (int j = 0; j < 4; j++) g_nodes[at + j] = nd[j];
-                        at += 4;
-                    }
         chunks.push_back(ch);
+        first_row.push_back(row);
         row = r1;
     }
+    first_row.push_back(n_own);
+    g_info.assign(chunks.size() * 4 * 32, 0);
+    g_nodes.assign(chunks.size() * 4 * 32, 0);
+    parallel_ranges((int64_t)chunks.size(), [&](int64_t c0, int64_t c1) {
+        for (int64_t ci = c0; ci < c1; ci++) {
+            const int64_t row0 = first_row[ci], row1 = first_row[ci + 1];
+            size_t at = (size_t)ci * 4 * 32;
+            // quads first so that a mixed chunk splits into at most two divergent halves
+            for (int pass = 1; pass >= 0; pass--)
+                for (int64_t p = row0; p < row1; p++)
+                    for (int k = cnt[p]; k < cnt[p + 1]; k++)
+                        if (inc[k].type == pass) {
+                            const int nen = pass ? 4 : 3, I = inc[k].I;
+                            const int32_t *en = pass ? &quad[4 * (int64_t)inc[k].eidx] : &tri[3 * (int64_t)inc[k].eidx];
+                            const int32_t *ps = pass ? &qpos[16 * (int64_t)inc[k].eidx + 4 * I] : &tpos[9 * (int64_t)inc[k].eidx + 3 * I];
+                            unsigned slots = 0, mbits = 0;
+                            for (int j = 0; j < nen; j++) {
+                                g_nodes[at + j] = en[j];
+                                slots |= (unsigned)(ps[j] & 0xff) << (8 * j);
+                                mbits |= (unsigned)(mask[en[j]] & 0x3f) << (8 * j);
+                            }
+                            const unsigned soff = (unsigned)(36 * (nptr[p] - nptr[row0]));
+                            const unsigned deg = (unsigned)(nptr[p + 1] - nptr[p]);
+                            g_info[at] = I | (inc[k].type << 2) | ((int)phase[k] << 3) | (1 << 8);
+                            g_info[at + 1] = (int)(soff | (deg << 16));
+                            g_info[at + 2] = (int)mbits;
+                            g_info[at + 3] = (int)slots;
+                            at += 4;
+                        }
+        }
+    });
     return true;
 }
 

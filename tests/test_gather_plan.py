@@ -120,3 +120,20 @@ def test_dirichlet_bits_travel_with_the_entries():
         if (info[k, 0] >> 8) & 1:
             for j in range(4):
                 assert (int(info[k, 2]) >> (8 * j)) & 0xff == mask[nodes[k, j]]
+
+
+def test_plan_does_not_depend_on_the_number_of_host_threads(monkeypatch):
+    """rows and chunks are planned on several host threads for large meshes; the schedule is a function of the mesh alone"""
+    for m in (structured("t", 60, 45), meshes.umbrella(mixed=True, n_rings=5), structured("q", 70, 51)):
+        plans = []
+        for threads in ("1", "3", "7"):
+            monkeypatch.setenv("FS_PLAN_THREADS", threads)
+            plans.append(fsb.gather_plan(m["etype"], m["eptr"], m["enodes"], m["xyz"].shape[0]))
+        for other in plans[1:]:
+            for key in plans[0]:
+                assert np.array_equal(plans[0][key], other[key]), key
+    monkeypatch.setenv("FS_PLAN_THREADS", "5")
+    m = MESHES["folded_mixed"]()
+    check_plan(m, fsb.gather_plan(m["etype"], m["eptr"], m["enodes"], m["xyz"].shape[0]))
+    big = meshes.umbrella(n_spokes=40, mixed=True, n_rings=3)
+    assert fsb.gather_plan(big["etype"], big["eptr"], big["enodes"], big["xyz"].shape[0]) is None
