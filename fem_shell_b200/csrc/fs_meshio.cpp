@@ -11,8 +11,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <fstream>
-#include <sstream>
 #include <string>
 #include <vector>
 
@@ -27,16 +25,89 @@ double g6(double v)
     return strtod(buf, nullptr);
 }
 
-// next non-empty line with any "# comment" tail removed
-bool next_line(std::istream &in, std::string &line)
-{
-    while (std::getline(in, line)) {
-        size_t h = line.find('#');
-        if (h != std::string::npos) line.resize(h);
-        if (line.find_first_not_of(" \t\r\n") != std::string::npos) return true;
+// ---------------------------------------------------------------------------------------------
+// Whole-file text cursor.  The 96 M-DOF mesh of BASELINE config 3 is a 1.3 GB XDA file; getline + stringstream
+// parse it at ~45 MB/s, this cursor at several hundred (one read, no per-line allocation, hand-rolled integers).
+// ---------------------------------------------------------------------------------------------
+class TextFile {
+public:
+    ~TextFile() { free(buf_); }
+    bool load(const char *path)
+    {
+        FILE *f = fopen(path, "rb");
+        if (!f) return false;
+        bool ok = fseek(f, 0, SEEK_END) == 0;
+        const long long size = ok ? ftell(f) : -1;
+        ok = ok && size >= 0 && fseek(f, 0, SEEK_SET) == 0;
+        if (ok) {
+            buf_ = (char *)malloc((size_t)size + 1);
+            ok = buf_ && fread(buf_, 1, (size_t)size, f) == (size_t)size;
+        }
+        fclose(f);
+        if (!ok) return false;
+        buf_[size] = '\0';  // strtod may look one character past the last token
+        cur_ = buf_;
+        end_ = buf_ + size;
+        return true;
     }
-    return false;
+    const char *begin() const { return buf_; }
+    const char *end() const { return end_; }
+    // the next line as it stands (std::getline)
+    bool raw_line(const char *&b, const char *&e)
+    {
+        if (cur_ >= end_) return false;
+        b = cur_;
+        const char *nl = (const char *)memchr(cur_, '\n', (size_t)(end_ - cur_));
+        e = nl ? nl : end_;
+        cur_ = nl ? nl + 1 : end_;
+        return true;
+    }
+    // the next line that holds something besides blanks once its "# comment" tail is cut off
+    bool next_line(const char *&b, const char *&e)
+    {
+        while (raw_line(b, e)) {
+            const char *h = (const char *)memchr(b, '#', (size_t)(e - b));
+            if (h) e = h;
+            for (const char *p = b; p < e; p++)
+                if (*p != ' ' && *p != '\t' && *p != '\r') return true;
+        }
+        return false;
+    }
+
+private:
+    char *buf_ = nullptr;
+    const char *cur_ = nullptr, *end_ = nullptr;
+};
+
+inline bool is_blank(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; }
+
+// next whitespace-separated token of [b, e) as an integer; advances b past it
+bool parse_int(const char *&b, const char *e, long long &out)
+{
+    while (b < e && is_blank(*b)) b++;
+    if (b >= e) return false;
+    bool neg = false;
+    if (*b == '-' || *b == '+') neg = *b++ == '-';
+    if (b >= e || *b < '0' || *b > '9') return false;
+    long long v = 0;
+    while (b < e && *b >= '0' && *b <= '9') v = v * 10 + (*b++ - '0');
+    out = neg ? -v : v;
+    return true;
 }
+
+// next token as a double (strtod: the buffer is NUL-terminated and a number never spans a line break)
+bool parse_double(const char *&b, const char *e, double &out)
+{
+    while (b < e && is_blank(*b)) b++;
+    if (b >= e) return false;
+    char *stop = nullptr;
+    const double v = strtod(b, &stop);
+    if (stop == b || stop > e) return false;
+    b = stop;
+    out = v;
+    return true;
+}
+
 
 }  // namespace
 
@@ -158,50 +229,48 @@ int fs_read_xda(const char *path, int64_t *n_nodes_o, int64_t *n_elem_o, int64_t
                 double *xyz, int32_t *etype, int64_t *eptr, int32_t *enodes, int32_t *bc)
 {
     if (!path) return FS_ERR_ARG;
-    std::ifstream in(path);
-    if (!in) return FS_ERR_IO;
-    std::string line;
-    if (!std::getline(in, line) || line.compare(0, 7, "libMesh") != 0) return FS_ERR_IO;
-    int64_t n_elem = 0, n_nodes = 0;
-    if (!next_line(in, line)) return FS_ERR_IO;
-    n_elem = strtoll(line.c_str(), nullptr, 10);
-    if (!next_line(in, line)) return FS_ERR_IO;
-    n_nodes = strtoll(line.c_str(), nullptr, 10);
+    TextFile f;
+    if (!f.load(path)) return FS_ERR_IO;
+    const char *b, *e;
+    if (!f.raw_line(b, e) || e - b < 7 || memcmp(b, "libMesh", 7) != 0) return FS_ERR_IO;
+    long long n_elem = 0, n_nodes = 0, v = 0;
+    if (!f.next_line(b, e) || !parse_int(b, e, n_elem)) return FS_ERR_IO;
+    if (!f.next_line(b, e) || !parse_int(b, e, n_nodes)) return FS_ERR_IO;
     for (int i = 0; i < 4; i++)  // bc / subdomain / processor / p-level specification lines
-        if (!std::getline(in, line)) return FS_ERR_IO;
-    if (!next_line(in, line)) return FS_ERR_IO;  // n_elem at level 0
+        if (!f.raw_line(b, e)) return FS_ERR_IO;
+    if (!f.next_line(b, e)) return FS_ERR_IO;  // n_elem at level 0
     if (n_elem <= 0 || n_nodes <= 0) return FS_ERR_IO;
     int64_t n_en = 0;
     if (eptr) eptr[0] = 0;
-    for (int64_t e = 0; e < n_elem; e++) {
-        if (!next_line(in, line)) return FS_ERR_IO;
-        std::istringstream ss(line);
-        int t;
-        ss >> t;
-        int nen = (t == FS_TRI3) ? 3 : (t == FS_QUAD4 ? 4 : 0);
+    for (int64_t el = 0; el < n_elem; el++) {
+        if (!f.next_line(b, e)) return FS_ERR_IO;
+        long long t;
+        if (!parse_int(b, e, t)) return FS_ERR_IO;
+        const int nen = (t == FS_TRI3) ? 3 : (t == FS_QUAD4 ? 4 : 0);
         if (!nen) return FS_ERR_ARG;  // only the two element types fem-shell handles (fs.cpp:315,342)
         for (int k = 0; k < nen; k++) {
-            long long id;
-            if (!(ss >> id)) return FS_ERR_IO;
-            if (enodes) enodes[n_en + k] = (int32_t)id;
+            if (!parse_int(b, e, v)) return FS_ERR_IO;
+            if (enodes) enodes[n_en + k] = (int32_t)v;
         }
-        if (etype) etype[e] = t;
+        if (etype) etype[el] = (int32_t)t;
         n_en += nen;
-        if (eptr) eptr[e + 1] = n_en;
+        if (eptr) eptr[el + 1] = n_en;
     }
     for (int64_t i = 0; i < n_nodes; i++) {
-        if (!next_line(in, line)) return FS_ERR_IO;
-        double a, b, c;
-        if (sscanf(line.c_str(), "%lf %lf %lf", &a, &b, &c) != 3) return FS_ERR_IO;
-        if (xyz) { xyz[3 * i] = a; xyz[3 * i + 1] = b; xyz[3 * i + 2] = c; }
+        if (!f.next_line(b, e)) return FS_ERR_IO;
+        double c[3];
+        for (int k = 0; k < 3; k++)
+            if (!parse_double(b, e, c[k])) return FS_ERR_IO;
+        if (xyz) { xyz[3 * i] = c[0]; xyz[3 * i + 1] = c[1]; xyz[3 * i + 2] = c[2]; }
     }
-    int64_t n_bc = 0;
-    if (next_line(in, line)) n_bc = strtoll(line.c_str(), nullptr, 10);
+    long long n_bc = 0;
+    if (f.next_line(b, e)) parse_int(b, e, n_bc);
     for (int64_t i = 0; i < n_bc; i++) {
-        if (!next_line(in, line)) return FS_ERR_IO;
-        int a, b, c;
-        if (sscanf(line.c_str(), "%d %d %d", &a, &b, &c) != 3) return FS_ERR_IO;
-        if (bc) { bc[3 * i] = a; bc[3 * i + 1] = b; bc[3 * i + 2] = c; }
+        if (!f.next_line(b, e)) return FS_ERR_IO;
+        long long t[3];
+        for (int k = 0; k < 3; k++)
+            if (!parse_int(b, e, t[k])) return FS_ERR_IO;
+        if (bc) { bc[3 * i] = (int32_t)t[0]; bc[3 * i + 1] = (int32_t)t[1]; bc[3 * i + 2] = (int32_t)t[2]; }
     }
     if (n_nodes_o) *n_nodes_o = n_nodes;
     if (n_elem_o) *n_elem_o = n_elem;
@@ -214,17 +283,20 @@ int fs_read_forces(const char *path, int64_t n_nodes, double *forces)
 {
     if (!path || !forces || n_nodes <= 0) return FS_ERR_ARG;
     memset(forces, 0, sizeof(double) * 6 * n_nodes);
-    std::ifstream in(path);
-    if (!in) return FS_ERR_IO;  // the reference silently runs without loads (fs.cpp:52); callers decide
+    TextFile f;
+    if (!f.load(path)) return FS_ERR_IO;  // the reference silently runs without loads (fs.cpp:52); callers decide
+    // fs.cpp:52-66 reads with operator>>: whitespace-separated tokens, no comment syntax; the first failed extraction
+    // leaves this and every later zero-initialised DenseVector entry untouched
+    const char *b = f.begin(), *e = f.end();
     long long n = 0;
     double factor = 1.0;
-    in >> n;
-    in >> factor;
-    // fs.cpp:59-66: a failed extraction leaves the zero-initialised DenseVector entries untouched
+    if (!parse_int(b, e, n)) return FS_OK;
+    if (!parse_double(b, e, factor)) return FS_OK;
     for (long long i = 0; i < n && i < n_nodes; i++)
         for (int j = 0; j < 6; j++) {
             double v;
-            if (in >> v) forces[6 * i + j] = v * factor;
+            if (!parse_double(b, e, v)) return FS_OK;
+            forces[6 * i + j] = v * factor;
         }
     return FS_OK;
 }
@@ -239,16 +311,51 @@ int fs_write_xda(const char *path, int64_t n_nodes, const double *xyz, int64_t n
     fprintf(f, ".        # boundary condition specification file\nn/a      # subdomain id specification file\n");
     fprintf(f, "n/a      # processor id specification file\nn/a      # p-level specification file\n");
     fprintf(f, "%lld      # n_elem at level 0, [ type (n0 ... nN-1) ]\n", (long long)n_elem);
+    // element and boundary lines are integers only: formatted by hand into a block buffer (fprintf per value is the
+    // bottleneck of a 32 M-element file); coordinates keep "%g", the reference generator's 6-digit text (main_all.cpp:261)
+    std::vector<char> buf(1 << 20);
+    size_t at = 0;
+    bool ok = true;
+    auto flush = [&]() {
+        ok = ok && fwrite(buf.data(), 1, at, f) == at;
+        at = 0;
+    };
+    auto put_int = [&](long long v) {
+        char tmp[24];
+        int n = 0;
+        const bool neg = v < 0;
+        unsigned long long u = neg ? 0ull - (unsigned long long)v : (unsigned long long)v;
+        do tmp[n++] = (char)('0' + u % 10); while (u /= 10);
+        if (neg) buf[at++] = '-';
+        while (n) buf[at++] = tmp[--n];
+    };
     for (int64_t e = 0; e < n_elem; e++) {
-        fprintf(f, "%d", etype[e]);
-        for (int64_t k = eptr[e]; k < eptr[e + 1]; k++) fprintf(f, " %d", enodes[k]);
-        fputc('\n', f);
+        if (at + 256 > buf.size()) flush();
+        put_int(etype[e]);
+        for (int64_t k = eptr[e]; k < eptr[e + 1]; k++) {
+            if (at + 64 > buf.size()) flush();
+            buf[at++] = ' ';
+            put_int(enodes[k]);
+        }
+        buf[at++] = '\n';
     }
-    for (int64_t i = 0; i < n_nodes; i++) fprintf(f, "%g %g %g\n", xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    for (int64_t i = 0; i < n_nodes; i++) {
+        if (at + 256 > buf.size()) flush();
+        at += (size_t)snprintf(buf.data() + at, 200, "%g %g %g\n", xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    }
+    flush();
     fprintf(f, "%lld        # number of boundary conditions\n", (long long)n_bc);
-    for (int64_t i = 0; i < n_bc; i++) fprintf(f, "%d %d %d\n", bc[3 * i], bc[3 * i + 1], bc[3 * i + 2]);
-    fclose(f);
-    return FS_OK;
+    for (int64_t i = 0; i < n_bc; i++) {
+        if (at + 256 > buf.size()) flush();
+        for (int k = 0; k < 3; k++) {
+            if (k) buf[at++] = ' ';
+            put_int(bc[3 * i + k]);
+        }
+        buf[at++] = '\n';
+    }
+    flush();
+    ok = fclose(f) == 0 && ok;
+    return ok ? FS_OK : FS_ERR_IO;
 }
 
 }  // extern "C"

@@ -91,3 +91,39 @@ def test_cxx_xda_and_force_readers(fso, ref_meshes, tmp_path):
     assert F[3].tolist() == [0] * 6 and F[2].tolist() == [2.5, 0, 0, 0, 0, 1.25]
     with pytest.raises(fsb.FemShellError):
         fsb.read_xda(str(tmp_path / "missing.xda"))
+
+
+def test_text_readers_tolerate_crlf_comments_and_short_files(tmp_path):
+    """the whole-file cursor behind fs_read_xda / fs_read_forces: CRLF line ends, comment-only and blank lines, no trailing
+    newline; a load file that ends early leaves the remaining entries zero like the reference's failed stream extraction
+    (fs.cpp:59-66)"""
+    xda = tmp_path / "edge.xda"
+    xda.write_bytes(b"libMesh-0.7.0+\r\n2   # elems\r\n\r\n5 # nodes\r\n.  # bc file\r\nn/a\r\nn/a # p\r\nn/a\r\n2 # level 0\r\n"
+                    b"3 0 1 2\r\n# a comment line\r\n5 1 3 4 2 # quad\r\n0 0 0\r\n1 0 0\r\n0 1 0\r\n1 1 0.5\r\n2e0 1 -.25\r\n1 # nbc\r\n0 2 1")
+    r = fsb.read_xda(str(xda))
+    assert r["etype"].tolist() == [3, 5] and r["eptr"].tolist() == [0, 3, 7] and r["enodes"].tolist() == [0, 1, 2, 1, 3, 4, 2]
+    assert r["bc"].tolist() == [[0, 2, 1]]
+    assert np.array_equal(r["xyz"], np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0.5], [2, 1, -0.25]], float))
+    ff = tmp_path / "edge_f"
+    ff.write_text("5\n2.0\n1 2 3 4 5 6\n7 8 9 10 11 12\n1 1\n")
+    F = fsb.read_forces(str(ff), 5)
+    assert np.array_equal(F, np.array([[2, 4, 6, 8, 10, 12], [14, 16, 18, 20, 22, 24], [2, 2, 0, 0, 0, 0], [0] * 6, [0] * 6], float))
+    with pytest.raises(fsb.FemShellError):
+        fsb.read_xda(str(tmp_path / "missing.xda"))
+    bad = tmp_path / "bad.xda"
+    bad.write_text("libMesh-0.7.0+\n1\n3\n.\nn/a\nn/a\nn/a\n1\n10 0 1 2 3 4 5 6 7\n")   # HEX8: not an element fem-shell handles
+    with pytest.raises(fsb.FemShellError):
+        fsb.read_xda(str(bad))
+
+
+def test_xda_writer_round_trip_and_reference_text(tmp_path):
+    m = fsb.meshgen("t", 7, 5, -1.5, 0.25, 3.0, 2.0, (0, 1, 20, 21), 3.0, 2, 1)
+    p = str(tmp_path / "rt.xda")
+    fsb.write_xda(p, m["xyz"], m["etype"], m["eptr"], m["enodes"], m["bc"])
+    r = fsb.read_xda(p)
+    for k in ("xyz", "etype", "eptr", "enodes"):
+        assert np.array_equal(r[k], m[k]), k
+    assert np.array_equal(r["bc"].reshape(-1, 3), m["bc"].reshape(-1, 3))
+    lines = open(p).read().splitlines()
+    assert lines[0] == "libMesh-0.7.0+" and lines[8] == "3 " + " ".join(str(v) for v in m["enodes"][:3])
+    assert lines[8 + m["etype"].size] == "%g %g %g" % tuple(m["xyz"][0])
