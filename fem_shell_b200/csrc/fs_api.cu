@@ -273,8 +273,8 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
     c->iface_nodes.clear();
     for (int64_t i = 0; i < n_nodes; i++)
         if (is_if[i]) c->iface_nodes.push_back((int32_t)i);
-    c->sols.assign(6 * n_nodes, 0.0);
-    c->pre_sols.assign(6 * n_nodes, 0.0);
+    c->sols.clear();  // coupled-step state (fsp.cpp:77-87): sized by the first fs_step, not by every mesh
+    c->pre_sols.clear();
 
     // ---- node-block partition of the DOF order (fs_partition.cpp) ----
     PartitionPlan plan;
@@ -574,6 +574,14 @@ static void axis_components(int dims, char dead_axis, int comp[3])
     }
 }
 
+// sols / preSols of the coupling loop (fsp.cpp:77-87), zero until the first step like the reference's new[]-and-fill
+static void coupled_state(fs_context *c)
+{
+    const size_t n = (size_t)6 * c->n_nodes;
+    if (c->sols.size() != n) c->sols.assign(n, 0.0);
+    if (c->pre_sols.size() != n) c->pre_sols.assign(n, 0.0);
+}
+
 int fs_step(fs_context *c, int dims, char dead_axis, const double *forces_in, const fs_solve_opts *opts,
             double *displ_out, fs_solve_info *info)
 {
@@ -584,6 +592,7 @@ int fs_step(fs_context *c, int dims, char dead_axis, const double *forces_in, co
     if (!c->assembled) FS_TRY(fs_assemble(c, nullptr));  // K is constant across coupling iterations
     int rc = fs_solve(c, opts, info);
     if (rc != FS_OK && rc != FS_ERR_NOT_CONVERGED) return rc;
+    coupled_state(c);
     FS_TRY(fs_get_solution(c, c->sols.data()));
     int comp[3];
     axis_components(dims, dead_axis, comp);
@@ -600,6 +609,7 @@ int fs_commit_step(fs_context *c, int dims, char dead_axis)
     if (dims != 2 && dims != 3) return fail(c, FS_ERR_ARG, "dims must be 2 or 3");
     int comp[3];
     axis_components(dims, dead_axis, comp);
+    coupled_state(c);
     for (int32_t id : c->iface_nodes)  // fsp.cpp:347-368
         for (int d = 0; d < dims; d++) c->pre_sols[6 * (int64_t)id + comp[d]] = c->sols[6 * (int64_t)id + comp[d]];
     return FS_OK;
