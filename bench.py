@@ -34,6 +34,20 @@ METRIC = "CG DOF-iterations/s"
 UNIT = "DOF-iterations/s"
 
 
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: from here on file descriptor 1 is stderr for everything else that writes to
+    it (NCCL prints its version banner to stdout when the box sets NCCL_DEBUG); returns the descriptor of the real stdout"""
+    sys.stdout.flush()
+    fd = os.dup(1)
+    os.dup2(2, 1)
+    return fd
+
+
+def emit_line(fd, line):
+    sys.stdout.flush()
+    os.write(fd, (json.dumps(line) + "\n").encode())
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -157,6 +171,7 @@ def run_ours(args):
     import torch.distributed as dist
     import fem_shell_b200 as fsb
 
+    json_fd = claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -164,8 +179,6 @@ def run_ours(args):
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
     torch.cuda.set_device(local_rank)
     nccl_id = None
-    # stdout carries exactly one JSON line: whatever NCCL_DEBUG level the box sets (its version banner included) goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         ids = [fsb.FemShell.unique_id() if rank == 0 else None]
@@ -385,7 +398,7 @@ def run_ours(args):
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
     }
-    print(json.dumps(line))
+    emit_line(json_fd, line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -39,6 +39,16 @@ def test_reference_arm_other_ranks_exit_quietly():
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 
+def test_stdout_carries_only_the_json_line():
+    """whatever a library prints to file descriptor 1 after claim_stdout() lands on stderr"""
+    code = ("import bench, os; fd = bench.claim_stdout(); print('banner from a library'); os.write(1, b'raw write\\n'); "
+            "bench.emit_line(fd, {'metric': 'x', 'value': 1})")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, cwd=ROOT)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == '{"metric": "x", "value": 1}\n'
+    assert "banner from a library" in r.stderr and "raw write" in r.stderr
+
+
 @pytest.mark.gpu
 def test_our_arm_line_on_a_small_plate():
     d = run_bench("--nodes", "200", "--steps", "2", "--warmup", "3", "--iters", "20", "--cpu-iters", "3", "--tts", "on")
