@@ -27,6 +27,10 @@
  * Individual stiffness entries, CSR ordering and the det() side effects on
  * non-rectangular quads are "parity unpinned": no reference output exists for
  * them in this container (libMesh/PETSc cannot be built here).
+ * fso_recover_resultants restates formulas the thesis prints but the reference
+ * never coded (doc/shellelements.tex:524, :1394-1403); it is pinned to
+ * closed-form constant-strain / constant-curvature / rigid-body fields in
+ * tests/test_oracle_resultants.py.
  *
  * Plain C99, doubles, element-id order, no reassociation tricks.
  */
