@@ -132,3 +132,47 @@ def umbrella(n_spokes=14, n_rings=4, cone=0.35, mixed=True):
     F[0] = (0.3, -0.2, -5.0, 0.4, 0.1, 0.0)
     return dict(xyz=xyz, etype=np.array(etype, np.int32), eptr=np.array(eptr, np.int64),
                 enodes=np.array(enodes, np.int32), bc=np.array(bc, np.int32).reshape(-1, 3), forces=F)
+
+
+def delaunay_patch(n_points=400, seed=7, quad_fraction=0.3):
+    """Irregular planar mesh: Delaunay triangulation of seeded random points, a fraction of edge-adjacent triangle pairs
+    merged into quads (convex ones only).  Valence 3..10, arbitrary local node indices -- an unstructured input for the
+    host-side schedules.  No boundary records, no loads."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(seed)
+    pts = rng.uniform(0.0, 10.0, (n_points, 2))
+    tri = Delaunay(pts).simplices.astype(np.int32)
+    # counter-clockwise triangles
+    a, b, c = pts[tri[:, 0]], pts[tri[:, 1]], pts[tri[:, 2]]
+    cw = (b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (b[:, 1] - a[:, 1]) * (c[:, 0] - a[:, 0]) < 0
+    tri[cw] = tri[cw][:, [0, 2, 1]]
+    edge_owner, used, quads = {}, np.zeros(len(tri), bool), []
+    for t, (i, j, k) in enumerate(tri):
+        for e in ((i, j), (j, k), (k, i)):
+            edge_owner[e] = t
+    for t, (i, j, k) in enumerate(tri):
+        if used[t] or rng.uniform() > quad_fraction:
+            continue
+        for (p, q, r) in ((i, j, k), (j, k, i), (k, i, j)):      # edge p->q, opposite node r
+            o = edge_owner.get((q, p))
+            if o is None or used[o] or o == t:
+                continue
+            s = [v for v in tri[o] if v != p and v != q][0]
+            quad = [r, p, s, q]                                  # counter-clockwise around the merged pair
+            P = pts[quad]
+            cross = [(P[(m + 1) % 4, 0] - P[m, 0]) * (P[(m + 2) % 4, 1] - P[(m + 1) % 4, 1])
+                     - (P[(m + 1) % 4, 1] - P[m, 1]) * (P[(m + 2) % 4, 0] - P[(m + 1) % 4, 0]) for m in range(4)]
+            if min(cross) <= 1e-9:
+                continue
+            used[t] = used[o] = True
+            quads.append(quad)
+            break
+    etype, enodes, eptr = [], [], [0]
+    for t in range(len(tri)):
+        if not used[t]:
+            etype.append(TRI3); enodes.extend(int(v) for v in tri[t]); eptr.append(len(enodes))
+    for qd in quads:
+        etype.append(QUAD4); enodes.extend(int(v) for v in qd); eptr.append(len(enodes))
+    xyz = np.column_stack([pts, np.zeros(n_points)])
+    return dict(xyz=xyz, etype=np.array(etype, np.int32), eptr=np.array(eptr, np.int64), enodes=np.array(enodes, np.int32),
+                bc=np.zeros((0, 3), np.int32), forces=np.zeros((n_points, 6)))

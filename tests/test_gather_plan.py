@@ -22,6 +22,8 @@ MESHES = {
     "folded_mixed": lambda: meshes.folded_cantilever(skew=0.35),
     "umbrella_mixed": lambda: meshes.umbrella(mixed=True, n_rings=5),
     "umbrella_quads": lambda: meshes.umbrella(mixed=False, n_rings=4),
+    "delaunay_mixed": lambda: meshes.delaunay_patch(400, seed=7, quad_fraction=0.3),
+    "delaunay_tris": lambda: meshes.delaunay_patch(300, seed=11, quad_fraction=0.0),
 }
 
 
