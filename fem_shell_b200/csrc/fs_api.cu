@@ -204,7 +204,8 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
         return fail(c, FS_ERR_ARG, "empty mesh or null array");
     if (n_nodes >= (int64_t)1 << 31 || n_elem >= (int64_t)1 << 31) return fail(c, FS_ERR_ARG, "mesh too large for 32-bit ids");
     FS_CUDA(c, cudaSetDevice(c->device));
-    FS_TRY(peer_window_teardown(c));
+    // every argument check comes BEFORE the first collective step: a bad mesh on one rank must not leave the others
+    // waiting in a barrier
     for (int64_t e = 0; e < n_elem; e++) {
         int nen = (int)(eptr[e + 1] - eptr[e]);
         if ((etype[e] == FS_TRI3 && nen != 3) || (etype[e] == FS_QUAD4 && nen != 4) ||
@@ -213,6 +214,12 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
         for (int64_t k = eptr[e]; k < eptr[e + 1]; k++)
             if (enodes[k] < 0 || enodes[k] >= n_nodes) return fail(c, FS_ERR_ARG, "node id out of range in element " + std::to_string(e));
     }
+    for (int64_t i = 0; i < n_bc; i++) {
+        const int32_t e = bc[3 * i], sd = bc[3 * i + 1];
+        if (e < 0 || e >= n_elem) return fail(c, FS_ERR_ARG, "boundary record " + std::to_string(i) + ": element out of range");
+        if (sd < 0 || sd >= (int)(eptr[e + 1] - eptr[e])) return fail(c, FS_ERR_ARG, "boundary record " + std::to_string(i) + ": side out of range");
+    }
+    FS_TRY(peer_window_teardown(c));
     c->n_nodes = n_nodes;
     c->n_elem = n_elem;
     c->pattern_ready = c->assembled = c->loads_set = c->rhs_ready = c->have_solution = false;
@@ -259,9 +266,7 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
     std::vector<uint8_t> is_if(n_nodes, 0);
     for (int64_t i = 0; i < n_bc; i++) {
         const int32_t e = bc[3 * i], s = bc[3 * i + 1], id = bc[3 * i + 2];
-        if (e < 0 || e >= n_elem) return fail(c, FS_ERR_ARG, "boundary record " + std::to_string(i) + ": element out of range");
         const int nen = (int)(eptr[e + 1] - eptr[e]);
-        if (s < 0 || s >= nen) return fail(c, FS_ERR_ARG, "boundary record " + std::to_string(i) + ": side out of range");
         const int32_t n0 = enodes[eptr[e] + s], n1 = enodes[eptr[e] + (s + 1) % nen];
         uint8_t m = 0;
         if (id == 0 || id == 20) m = 0x07;
@@ -438,7 +443,7 @@ static void default_opts(fs_solve_opts &o)
     o.rtol = 1e-12;   // libMesh default TOLERANCE^2 (fs.cpp:130-133 leave it untouched)
     o.max_its = 5000;
     o.pc = FS_PC_JACOBI;
-    o.norm_type = FS_NORM_UNPRECONDITIONED;
+    o.norm_type = FS_NORM_PRECONDITIONED;  // KSPCG's default norm, i.e. what the reference's solve tests
     o.warm_start = 1;
     o.check_every = 0;
 }

@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 
 #include "fs_context.hpp"
 #include "fs_elements.cuh"
@@ -353,6 +354,11 @@ int build_pattern(fs_context *c, const std::vector<int32_t> &tri, const std::vec
     return FS_OK;
 }
 
+// The material / quirk constants live in ONE __constant__ object per device (c_el); every pass that uploads and
+// then reads it holds this lock until its kernels have finished, so that contexts with different materials driven
+// from different host threads cannot assemble with each other's D matrices.
+static std::mutex g_elconst_mutex;
+
 int upload_element_constants(fs_context *c)
 {
     // fs.cpp:273-294 initMaterialMatrices
@@ -677,6 +683,7 @@ int build_gather_schedule(fs_context *c)
 int assemble_values(fs_context *c, float *ms)
 {
     cudaStream_t st = c->stream;
+    std::lock_guard<std::mutex> lock(g_elconst_mutex);  // both branches below synchronise the stream before returning
     int rc = upload_element_constants(c);
     if (rc) return rc;
     if (c->asm_mode == FS_ASM_GATHER) {
@@ -791,6 +798,7 @@ __global__ void k_debug_elements(const int32_t *__restrict__ conn, const int32_t
 
 int debug_element_matrices(fs_context *c, double *out_host)
 {
+    std::lock_guard<std::mutex> lock(g_elconst_mutex);
     int rc = upload_element_constants(c);
     if (rc) return rc;
     DevBuf<double> out;
@@ -953,6 +961,7 @@ k_recover_resultants(const int32_t *__restrict__ conn, const int32_t *__restrict
 // d_out: 6*n_elem doubles, zero-filled by the caller; d_x: solution in the local vector layout with valid halos
 int recover_resultants(fs_context *c, const double *d_x, double *d_out)
 {
+    std::lock_guard<std::mutex> lock(g_elconst_mutex);
     int rc = upload_element_constants(c);
     if (rc) return rc;
     if (c->n_tri)
@@ -962,6 +971,7 @@ int recover_resultants(fs_context *c, const double *d_x, double *d_out)
         k_recover_resultants<4><<<nblk(c->n_quad, 128), 128, 0, c->stream>>>(c->d_quad.p, c->d_quad_gid.p, c->n_quad, c->d_xyz.p, d_x,
                                                                               (int)c->own_lo, (int)c->n_own, d_out);
     FS_CUDA(c, cudaGetLastError());
+    FS_CUDA(c, cudaStreamSynchronize(c->stream));  // the constants may change once the lock is released
     return FS_OK;
 }
 

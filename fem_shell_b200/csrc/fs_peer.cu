@@ -110,56 +110,67 @@ int peer_window_setup(fs_context *c)
                 ok = 0;
             }
         }
+    // ---- device-side description: everything that can fail locally happens BEFORE the one collective decision ----
+    PeerWin h;
+    memset(&h, 0, sizeof h);
+    h.rank = me;
+    h.world = W;
+    h.spin_limit = 20000000000LL;  // ~10 s of SM clocks
+    std::string why;
+    std::vector<int32_t> push_peer(c->send_total), push_dst(c->send_total);
+    if (ok) {
+        for (int r = 0; r < W; r++) {
+            char *b = (char *)(r == me ? base : pb[r]);
+            h.mbox[r] = (unsigned long long *)b;
+            h.peer_p[r] = (double *)(b + MBOX_WORDS * 8);
+        }
+        for (const Peer &pr : c->peers) {
+            if (pr.recv_count > 0) h.recv_rank[h.n_recv++] = pr.rank;
+            if (pr.send_count > 0) h.send_rank[h.n_send++] = pr.rank;
+        }
+        for (const Peer &pr : c->peers) {
+            const int64_t off = meta[pr.rank].recv_off_from[me];
+            if (pr.send_count > 0 && off < 0) {  // the neighbour does not expect values from this rank
+                ok = 0;
+                why = "halo plans of neighbouring ranks disagree";
+                break;
+            }
+            for (int64_t k = 0; k < pr.send_count; k++) {
+                push_peer[pr.send_off + k] = pr.rank;
+                push_dst[pr.send_off + k] = (int32_t)(off + k);
+            }
+        }
+    }
+    if (ok) {
+        bool up = c->d_pw.alloc(1) == cudaSuccess && c->d_push_peer.alloc(push_peer.size()) == cudaSuccess &&
+                  c->d_push_dst.alloc(push_dst.size()) == cudaSuccess &&
+                  cudaMemcpy(c->d_pw.p, &h, sizeof h, cudaMemcpyHostToDevice) == cudaSuccess;
+        if (up && !push_peer.empty())
+            up = cudaMemcpy(c->d_push_peer.p, push_peer.data(), sizeof(int32_t) * push_peer.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+                 cudaMemcpy(c->d_push_dst.p, push_dst.data(), sizeof(int32_t) * push_dst.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+        if (!up) {
+            cudaGetLastError();
+            ok = 0;
+            why = "device allocation of the peer tables failed";
+        }
+    }
     // every rank must take the same path; the all-reduce is also the barrier "all mailboxes are zeroed"
     int all_ok = ok;
     int rc = nccl_barrier(c, &all_ok);
     if (rc != FS_OK || !all_ok) {
         for (int r = 0; r < W; r++)
             if (pb[r]) cudaIpcCloseMemHandle(pb[r]);
-        if (rc == FS_OK) rc = nccl_barrier(c, nullptr);
+        if (rc == FS_OK) rc = nccl_barrier(c, nullptr);  // nobody frees a window another rank still has mapped
         if (base) cudaFree(base);
+        c->d_pw.release();
+        c->d_push_peer.release();
+        c->d_push_dst.release();
         if (rc != FS_OK) return rc;
-        if (c->comm_pref == FS_COMM_PEER) return fail(c, FS_ERR_COMM, "peer windows unavailable (cudaIpc / P2P mapping failed on some rank)");
+        if (!why.empty()) return fail(c, FS_ERR_STATE, "peer windows: " + why);
+        if (c->comm_pref == FS_COMM_PEER) return fail(c, FS_ERR_COMM, "peer windows unavailable (cudaIpc / P2P mapping or set-up failed on some rank)");
         return FS_OK;  // AUTO: stay on the NCCL path
     }
 
-    // ---- device-side description ----
-    PeerWin h;
-    memset(&h, 0, sizeof h);
-    h.rank = me;
-    h.world = W;
-    h.spin_limit = 20000000000LL;  // ~10 s of SM clocks
-    for (int r = 0; r < W; r++) {
-        char *b = (char *)(r == me ? base : pb[r]);
-        h.mbox[r] = (unsigned long long *)b;
-        h.peer_p[r] = (double *)(b + MBOX_WORDS * 8);
-    }
-    for (const Peer &pr : c->peers) {
-        if (pr.recv_count > 0) h.recv_rank[h.n_recv++] = pr.rank;
-        if (pr.send_count > 0) h.send_rank[h.n_send++] = pr.rank;
-    }
-    std::vector<int32_t> push_peer(c->send_total), push_dst(c->send_total);
-    for (const Peer &pr : c->peers)
-        for (int64_t k = 0; k < pr.send_count; k++) {
-            const int64_t off = meta[pr.rank].recv_off_from[me];
-            if (off < 0) {
-                // the neighbour does not expect values from this rank: plans disagree
-                for (int r = 0; r < W; r++)
-                    if (pb[r]) cudaIpcCloseMemHandle(pb[r]);
-                cudaFree(base);
-                return fail(c, FS_ERR_STATE, "halo plans of neighbouring ranks disagree");
-            }
-            push_peer[pr.send_off + k] = pr.rank;
-            push_dst[pr.send_off + k] = (int32_t)(off + k);
-        }
-    FS_CUDA(c, c->d_pw.alloc(1));
-    FS_CUDA(c, c->d_push_peer.alloc(push_peer.size()));
-    FS_CUDA(c, c->d_push_dst.alloc(push_dst.size()));
-    FS_CUDA(c, cudaMemcpy(c->d_pw.p, &h, sizeof h, cudaMemcpyHostToDevice));
-    if (!push_peer.empty()) {
-        FS_CUDA(c, cudaMemcpy(c->d_push_peer.p, push_peer.data(), sizeof(int32_t) * push_peer.size(), cudaMemcpyHostToDevice));
-        FS_CUDA(c, cudaMemcpy(c->d_push_dst.p, push_dst.data(), sizeof(int32_t) * push_dst.size(), cudaMemcpyHostToDevice));
-    }
     c->win_base = base;
     for (int r = 0; r < W; r++) c->peer_base[r] = pb[r];
     c->d_p.view((double *)((char *)base + MBOX_WORDS * 8), 6 * (size_t)c->n_local);

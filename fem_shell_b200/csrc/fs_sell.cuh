@@ -60,16 +60,27 @@ __host__ __device__ constexpr bool sell_uses_col(unsigned long long mask, int b)
 // q = A p on the compacted matrix (+ partial p.q).  Lane = block row; slots of a slice are walked in
 // column order, two at a time so that 2*NZ value loads are in flight per lane.
 // ---------------------------------------------------------------------------------------------
-template <unsigned long long MASK, bool WITH_DOT, int BLOCK, int MINB, int UNROLL = 2>
+// PEER = the halo segments of x are written by the neighbouring GPUs while this kernel is already resident (it
+// spins on their stamps first, fs_peer.cuh).  x is then NOT read-only for the kernel's lifetime: no __restrict__ /
+// ld.global.nc on it, and halo blocks are loaded with ld.global.cg (L2 is the point of coherence for NVLink
+// writes; an L1 line could predate them).  Owned blocks of x are only written by earlier kernels of this stream.
+template <bool PEER>
+__device__ __forceinline__ double2 ld_x2(const double2 *p, bool halo)
+{
+    if (PEER) return halo ? __ldcg(p) : *p;
+    return __ldg(p);
+}
+
+template <unsigned long long MASK, bool WITH_DOT, int BLOCK, int MINB, bool PEER = false, int UNROLL = 2>
 __global__ void __launch_bounds__(BLOCK, MINB)
-k_spmv_sell(int n_own, int n_slices, const int32_t *__restrict__ sptr, const int32_t *__restrict__ adj,
-            const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y_own,
-            const double *__restrict__ x_own, double *partials, unsigned int *counter, CgState *state,
+k_spmv_sell(int n_own, int own_lo, int n_slices, const int32_t *__restrict__ sptr, const int32_t *__restrict__ adj,
+            const double *__restrict__ vals, const double *x, double *__restrict__ y_own,
+            const double *x_own, double *partials, unsigned int *counter, CgState *state,
             double *red, int fin_mode, PeerWin *pw)
 {
     constexpr int NZ = sell_popcount(MASK);
     if (WITH_DOT ? state->done : (state && state->done)) return;  // without the dot product: checked only when a state is passed
-    if (WITH_DOT && pw && !peer_halo_wait(pw)) {  // the neighbours' boundary values of x must have landed
+    if (PEER && !peer_halo_wait(pw)) {  // the neighbours' boundary values of x must have landed
         if (blockIdx.x == 0 && threadIdx.x == 0) peer_fail(state);
         return;
     }
@@ -84,12 +95,14 @@ k_spmv_sell(int n_own, int n_slices, const int32_t *__restrict__ sptr, const int
         double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll UNROLL
         for (int slot = 0; slot < dmax; slot++) {
-            const double2 *xp = reinterpret_cast<const double2 *>(x + 6 * (size_t)aj[32 * slot]);
+            const int col = aj[32 * slot];
+            const bool halo = PEER && (unsigned)(col - own_lo) >= (unsigned)n_own;
+            const double2 *xp = reinterpret_cast<const double2 *>(x + 6 * (size_t)col);
             double xv[6];
 #pragma unroll
             for (int h = 0; h < 3; h++)
                 if (sell_uses_col(MASK, 2 * h) || sell_uses_col(MASK, 2 * h + 1)) {
-                    const double2 t = xp[h];
+                    const double2 t = ld_x2<PEER>(xp + h, halo);
                     xv[2 * h] = t.x;
                     xv[2 * h + 1] = t.y;
                 }

@@ -14,6 +14,8 @@
 // partial sums, then a one-thread finalise kernel.
 #include <cub/cub.cuh>
 
+#include <cmath>
+
 #include "fs_context.hpp"
 #include "fs_cg_device.cuh"
 #include "fs_nccl.hpp"
@@ -49,15 +51,15 @@ __global__ void k_finalize(CgState *s, const double *red, int which)
 constexpr int SPMV_BLOCK = 128;
 constexpr int SPMV_MIN_BLOCKS = 8;
 
-template <bool WITH_DOT, int BLOCK>
+template <bool WITH_DOT, int BLOCK, bool PEER = false>
 __global__ void __launch_bounds__(BLOCK, SPMV_MIN_BLOCKS)
-k_spmv(int n_own, const int32_t *__restrict__ nptr, const int32_t *__restrict__ nadj,
-       const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y_own,
-       const double *__restrict__ x_own, double *partials, unsigned int *counter, CgState *state,
+k_spmv(int n_own, int own_lo, const int32_t *__restrict__ nptr, const int32_t *__restrict__ nadj,
+       const double *__restrict__ vals, const double *x, double *__restrict__ y_own,
+       const double *x_own, double *partials, unsigned int *counter, CgState *state,
        double *red, int fin_mode, PeerWin *pw)
 {
     if (WITH_DOT ? state->done : (state && state->done)) return;  // without the dot product: checked only when a state is passed
-    if (WITH_DOT && pw && !peer_halo_wait(pw)) {  // the neighbours' boundary values of x must have landed
+    if (PEER && !peer_halo_wait(pw)) {  // the neighbours' boundary values of x must have landed (ld_x2: fs_sell.cuh)
         if (blockIdx.x == 0 && threadIdx.x == 0) peer_fail(state);
         return;
     }
@@ -74,7 +76,8 @@ k_spmv(int n_own, const int32_t *__restrict__ nptr, const int32_t *__restrict__ 
         for (int l = lane; l < L2; l += 32) {
             const int j = l / 3, h = l - 3 * j;
             const int col = nadj[b0 + j];
-            const double2 xv = *reinterpret_cast<const double2 *>(x + 6 * (size_t)col + 2 * h);
+            const double2 xv = ld_x2<PEER>(reinterpret_cast<const double2 *>(x + 6 * (size_t)col + 2 * h),
+                                           PEER && (unsigned)(col - own_lo) >= (unsigned)n_own);
             double2 v[6];
 #pragma unroll
             for (int a = 0; a < 6; a++) v[a] = __ldcs(base + (size_t)a * L2 + l);
@@ -350,8 +353,11 @@ __global__ void k_extract_minv(int n_own, int own_lo, const int32_t *__restrict_
     if (slot < 0) { *bad = 1; return; }
     const double *blk = vals + (size_t)36 * b0 + 6 * slot;
     const int L = 6 * deg;
-    if (pc == 1) {
-        for (int a = 0; a < 6; a++) minv[6 * (size_t)p + a] = 1.0 / blk[(size_t)a * L + a];
+    if (pc == 1) {  // PCJacobi: a zero diagonal entry is replaced by 1 (PETSc's PCSetUp_Jacobi does the same)
+        for (int a = 0; a < 6; a++) {
+            const double d = blk[(size_t)a * L + a];
+            minv[6 * (size_t)p + a] = d != 0.0 ? 1.0 / d : 1.0;
+        }
         return;
     }
     double M[6][12];
@@ -386,7 +392,7 @@ int solver_query_occupancy(fs_context *c)
     c->spmv_blocks_per_sm = std::max(1, nb);
     FS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_update<1, 0, 256>, 256, 0));
     c->vec_blocks_per_sm = std::max(1, nb);
-    FS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_spmv_sell<SELL_MASK_XY, true, SELL_BLOCK, SELL_MINB>, SELL_BLOCK, 0));
+    FS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_spmv_sell<SELL_MASK_XY, true, SELL_BLOCK, SELL_MINB, false>, SELL_BLOCK, 0));
     c->sell_blocks_per_sm = std::max(1, nb);
     return FS_OK;
 }
@@ -516,9 +522,14 @@ static void launch_sell(fs_context *c, const double *x, double *y_own, const dou
 {
     const int64_t want = (c->sell_slices + SELL_BLOCK / 32 - 1) / (SELL_BLOCK / 32);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->sm_count * c->sell_blocks_per_sm));
-    k_spmv_sell<MASK, WITH_DOT, SELL_BLOCK, SELL_MINB><<<grid, SELL_BLOCK, 0, c->stream>>>(
-        (int)c->n_own, (int)c->sell_slices, c->d_sell_sptr.p, c->d_sell_adj.p, c->d_sell_vals.p, x, y_own, x_own,
-        c->d_partials.p, c->d_counter.p, state, red, fin_mode, pw);
+    if (WITH_DOT && pw)
+        k_spmv_sell<MASK, WITH_DOT, SELL_BLOCK, SELL_MINB, WITH_DOT><<<grid, SELL_BLOCK, 0, c->stream>>>(
+            (int)c->n_own, (int)c->own_lo, (int)c->sell_slices, c->d_sell_sptr.p, c->d_sell_adj.p, c->d_sell_vals.p, x, y_own, x_own,
+            c->d_partials.p, c->d_counter.p, state, red, fin_mode, pw);
+    else
+        k_spmv_sell<MASK, WITH_DOT, SELL_BLOCK, SELL_MINB, false><<<grid, SELL_BLOCK, 0, c->stream>>>(
+            (int)c->n_own, (int)c->own_lo, (int)c->sell_slices, c->d_sell_sptr.p, c->d_sell_adj.p, c->d_sell_vals.p, x, y_own, x_own,
+            c->d_partials.p, c->d_counter.p, state, red, fin_mode, pw);
 }
 
 int solver_prepare(fs_context *c, int pc)
@@ -613,9 +624,14 @@ static void launch_spmv(fs_context *c, const double *x, double *y_own, const dou
         else launch_sell<SELL_MASK_YZ, WITH_DOT>(c, x, y_own, x_own, red, fin_mode, pw, state);
         return;
     }
-    k_spmv<WITH_DOT, SPMV_BLOCK><<<spmv_grid(c), SPMV_BLOCK, 0, c->stream>>>(
-        (int)c->n_own, c->d_nptr.p, c->d_nadj.p, c->d_vals.p, x, y_own, x_own, c->d_partials.p, c->d_counter.p,
-        state, red, fin_mode, pw);
+    if (WITH_DOT && pw)
+        k_spmv<WITH_DOT, SPMV_BLOCK, WITH_DOT><<<spmv_grid(c), SPMV_BLOCK, 0, c->stream>>>(
+            (int)c->n_own, (int)c->own_lo, c->d_nptr.p, c->d_nadj.p, c->d_vals.p, x, y_own, x_own, c->d_partials.p, c->d_counter.p,
+            state, red, fin_mode, pw);
+    else
+        k_spmv<WITH_DOT, SPMV_BLOCK, false><<<spmv_grid(c), SPMV_BLOCK, 0, c->stream>>>(
+            (int)c->n_own, (int)c->own_lo, c->d_nptr.p, c->d_nadj.p, c->d_vals.p, x, y_own, x_own, c->d_partials.p, c->d_counter.p,
+            state, red, fin_mode, pw);
 }
 
 int spmv_once(fs_context *c, const double *d_in, double *d_out, bool check_done)
@@ -756,7 +772,8 @@ static int run_pcg(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
     FS_CUDA(c, cudaStreamSynchronize(st));
     const CgState &s = *c->h_state;
     if (s.nrm2 < 0.0) FS_CUDA(c, cudaMemsetAsync(c->d_x.p, 0, sizeof(double) * 6 * c->n_local, st));
-    c->have_solution = true;
+    // a later warm start (the default, fsp.cpp:271) must not begin from the iterate of a broken-down or timed-out solve
+    c->have_solution = (s.status == FS_OK || s.status == FS_ERR_NOT_CONVERGED) && std::isfinite(s.nrm2) && std::isfinite(s.rz);
     if (info) {
         info->iterations = s.iter;
         info->rel_residual = s.nrm2 < 0.0 ? 0.0 : sqrt(s.nrm2 / s.bnorm2);

@@ -16,7 +16,9 @@
  * the duration of the call; every function returns 0 (FS_OK) or a negative
  * fs_status and leaves a message retrievable with fs_last_error(); no C++
  * exception crosses this boundary.  One context = one GPU = one CUDA stream;
- * calls on one context must be serialised by the caller.  There is no CPU
+ * calls on one context must be serialised by the caller; different contexts
+ * may be driven from different host threads (the passes that use the
+ * per-device element constants serialise themselves).  There is no CPU
  * fallback: without a CUDA device fs_create fails.
  */
 #ifndef FEMSHELL_B200_H
@@ -150,7 +152,10 @@ int fs_build_rhs(fs_context *ctx, double scale);
  * the block-CSR matrix, rhs.  The sparsity pattern and the element colouring are built on the
  * first call and kept.  *ms (optional) receives the device time of the values pass. */
 int fs_assemble(fs_context *ctx, float *ms);
-/* replaces LinearImplicitSystem::solve -> KSPSolve (fs.cpp:138) for an already assembled system */
+/* replaces LinearImplicitSystem::solve -> KSPSolve (fs.cpp:138) for an already assembled system.
+ * opts == NULL: the reference's defaults as far as they apply to CG -- rtol 1e-12, 5000 iterations, Jacobi,
+ * PRECONDITIONED norm (KSPCG's default), warm start.  A solve that ends in FS_ERR_BREAKDOWN / FS_ERR_COMM leaves no
+ * solution behind: fs_get_solution then fails and the next solve starts from zero. */
 int fs_solve(fs_context *ctx, const fs_solve_opts *opts, fs_solve_info *info);
 /* replaces build_solution_vector (fs.cpp:140-141): sols[6*node_id+var]; every rank gets the full vector */
 int fs_get_solution(fs_context *ctx, double *sols);
