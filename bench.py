@@ -613,7 +613,7 @@ def run_ours(args):
             sysm = fso.assemble(mesh1, forces1, NU, EM, THICK, threads=threads)
             t_asm, n_cpu_elem, cpu_nx, cpu_ny = time.perf_counter() - t0, mesh1.n_elem, nx, nx
         c_it = args.cpu_iters
-        fso.pcg(sysm, rtol=1e-30, max_its=2, threads=threads)
+        fso.pcg(sysm, rtol=1e-30, max_its=10, threads=threads)   # thread pool, page placement
         t0 = time.perf_counter()
         fso.pcg(sysm, rtol=1e-30, max_its=c_it, threads=threads)
         t_cg = time.perf_counter() - t0
@@ -678,7 +678,7 @@ def main():
     ap.add_argument("--tts-max-s", type=float, default=90.0)
     ap.add_argument("--tts-pc", default="ml", choices=["ml", "jacobi", "both"], help="preconditioner(s) of the time-to-solution run")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-iters", type=int, default=30)
+    ap.add_argument("--cpu-iters", type=int, default=60)
     ap.add_argument("--ref-nodes", type=int, default=1000, help="reference arm: nodes per side of one strip (same as --nodes)")
     ap.add_argument("--ref-iters", type=int, default=0, help="reference arm: iterations per step; 0 = the config's, bounded by --ref-budget-s")
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="reference arm: wall-clock bound of the whole steps+warmup loop")

@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = [
     "fs_set_nodal_loads", "fs_set_interface_loads", "fs_build_rhs", "fs_assemble", "fs_solve",
     "fs_get_solution", "fs_get_solution_owned", "fs_recover_resultants", "fs_solve_host", "fs_interface_nodes", "fs_step", "fs_commit_step", "fs_get_sizes",
     "fs_export_dof_order", "fs_export_csr", "fs_export_rhs", "fs_debug_element_matrices", "fs_spmv_host",
-    "fs_bench_spmv", "fs_bench_fp64_peak", "fs_set_ml_options", "fs_get_ml_info", "fs_debug_ml_level", "fs_apply_mlrbm_host", "fs_partition_plan", "fs_gather_plan", "fs_meshgen", "fs_read_xda", "fs_read_forces", "fs_write_xda",
+    "fs_bench_spmv", "fs_bench_fp64_peak", "fs_bench_contraction", "fs_set_ml_options", "fs_get_ml_info", "fs_debug_ml_level", "fs_apply_mlrbm_host", "fs_partition_plan", "fs_gather_plan", "fs_meshgen", "fs_read_xda", "fs_read_forces", "fs_write_xda",
 ]
 
 
@@ -409,6 +409,13 @@ class FemShell:
         t = C.c_double()
         self._ck(self.lib.fs_bench_fp64_peak(self.ctx, C.byref(t)))
         return t.value
+
+    def bench_contraction(self, n_elem=1 << 20, reps=10):
+        """DMMA vs FMA-pipe micro-benchmark of the plate contraction (fs_bench_contraction)"""
+        out = (C.c_double * 6)()
+        self._ck(self.lib.fs_bench_contraction(self.ctx, C.c_int64(n_elem), C.c_int(reps), out))
+        return {"fma_ms": out[0], "dmma_ms": out[1], "max_rel_diff": out[2], "dmma_peak_tflops": out[3],
+                "fma_useful_tflops": out[4], "dmma_useful_tflops": out[5]}
 
     def bench_spmv(self, reps=20) -> float:
         i = _Info()

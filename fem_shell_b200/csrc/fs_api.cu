@@ -224,6 +224,7 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
     c->n_elem = n_elem;
     c->pattern_ready = c->assembled = c->loads_set = c->rhs_ready = c->have_solution = false;
     c->gather_ready = c->gather_unavailable = false;
+    c->slice_ready = c->parity_valid = false;
     c->sell_checked = c->sell_active = c->sell_layout_ready = false;
     c->ml_geom_ready = c->ml_values_ready = false;
     if (c->cg_graph_exec) { cudaGraphExecDestroy(c->cg_graph_exec); c->cg_graph_exec = nullptr; }
@@ -664,7 +665,10 @@ int fs_export_csr(fs_context *c, int64_t *rowptr, int32_t *colidx, double *vals)
         }
     }
     if (rowptr) rowptr[6 * c->n_own] = 36 * (int64_t)c->n_blocks;
-    if (vals) FS_CUDA(c, cudaMemcpy(vals, c->d_vals.p, sizeof(double) * 36 * c->n_blocks, cudaMemcpyDeviceToHost));
+    if (vals) {
+        FS_TRY(ensure_parity_values(c));  // shells in the xy plane are assembled into the compacted SpMV format only
+        FS_CUDA(c, cudaMemcpy(vals, c->d_vals.p, sizeof(double) * 36 * c->n_blocks, cudaMemcpyDeviceToHost));
+    }
     return FS_OK;
 }
 

@@ -20,6 +20,7 @@
 #include "fs_context.hpp"
 #include "fs_elements.cuh"
 #include "fs_gather_plan.hpp"
+#include "fs_sell.cuh"
 
 namespace fs {
 
@@ -347,9 +348,12 @@ int build_pattern(fs_context *c, const std::vector<int32_t> &tri, const std::vec
     FS_CUDA(c, c->d_quad_pos.alloc(nq * 16));
     if (nt) k_positions<<<nblk(nt * 9, 256), 256, 0, st>>>(c->d_tri.p, 3, nt, own_lo, n_own, c->d_nptr.p, c->d_nadj.p, c->d_tri_pos.p);
     if (nq) k_positions<<<nblk(nq * 16, 256), 256, 0, st>>>(c->d_quad.p, 4, nq, own_lo, n_own, c->d_nptr.p, c->d_nadj.p, c->d_quad_pos.p);
-    FS_CUDA(c, c->d_vals.alloc((size_t)36 * c->n_blocks));
     FS_CUDA(c, cudaStreamSynchronize(st));
     FS_CUDA(c, cudaGetLastError());
+    c->d_vals.release();   // the parity values are allocated by the first pass that writes them
+    c->parity_valid = false;
+    rc = slice_plan_build(c);
+    if (rc) return rc;
     c->pattern_ready = true;
     return FS_OK;
 }
@@ -361,16 +365,8 @@ static std::mutex g_elconst_mutex;
 
 int upload_element_constants(fs_context *c)
 {
-    // fs.cpp:273-294 initMaterialMatrices
-    ElemConst h;
-    const double nu = c->nu;
-    const double fm = c->E / (1.0 - nu * nu);
-    const double fp = c->E * pow(c->thickness, 3.0) / (12.0 * (1.0 - nu * nu));
-    h.dm11 = 1.0 * fm; h.dm12 = nu * fm; h.dm33 = ((1.0 - nu) / 2.0) * fm;
-    h.dp11 = 1.0 * fp; h.dp12 = nu * fp; h.dp33 = ((1.0 - nu) / 2.0) * fp;
-    h.thickness = c->thickness;
-    h.quirks = c->quirks;
-    FS_CUDA(c, cudaMemcpyToSymbolAsync(c_el, &h, sizeof h, 0, cudaMemcpyHostToDevice, c->stream));
+    const ElemConst h = make_elem_const(c->nu, c->E, c->thickness, c->quirks);
+    FS_CUDA(c, upload_elem_const_tu(h, c->stream));
     if (!c->d_qgp.p) {  // Gauss-point table of the gather kernel's run-time node rows (fs_elements.cuh)
         QuadGpTab t;
         quad_gp_table(t);
@@ -680,29 +676,20 @@ int build_gather_schedule(fs_context *c)
     return FS_OK;
 }
 
-int assemble_values(fs_context *c, float *ms)
+// the parity block-CSR values (explicit zeros included) of the current material / mesh into d_vals; enqueue only
+static int enqueue_parity_values(fs_context *c)
 {
     cudaStream_t st = c->stream;
-    std::lock_guard<std::mutex> lock(g_elconst_mutex);  // both branches below synchronise the stream before returning
-    int rc = upload_element_constants(c);
-    if (rc) return rc;
+    if (c->d_vals.n < (size_t)36 * c->n_blocks) FS_CUDA(c, c->d_vals.alloc((size_t)36 * c->n_blocks));
     if (c->asm_mode == FS_ASM_GATHER) {
-        rc = build_gather_schedule(c);
+        int rc = build_gather_schedule(c);
         if (rc) return rc;
     }
-    FS_CUDA(c, cudaEventRecord(c->ev0, st));
     if (c->asm_mode == FS_ASM_GATHER && c->gather_ready) {
         auto kern = c->n_tri == 0 ? k_assemble_gather<1> : (c->n_quad == 0 ? k_assemble_gather<2> : k_assemble_gather<3>);
         kern<<<nblk(c->n_g_chunks, GATHER_WARPS), GATHER_THREADS, GATHER_WARPS * GATHER_WARP_VALS * sizeof(double), st>>>(
             c->d_g_chunks.p, (int)c->n_g_chunks, c->d_g_info.p, c->d_g_nodes.p, c->d_xyz.p, c->d_vals.p, c->d_qgp.p);
-        FS_CUDA(c, cudaEventRecord(c->ev1, st));
-        FS_CUDA(c, cudaStreamSynchronize(st));
         FS_CUDA(c, cudaGetLastError());
-        if (ms) FS_CUDA(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
-        c->assembled = true;
-        c->minv_kind = -1;
-        c->ml_values_ready = false;
-        c->sell_checked = false;
         return FS_OK;
     }
     FS_CUDA(c, cudaMemsetAsync(c->d_vals.p, 0, sizeof(double) * 36 * (size_t)c->n_blocks, st));
@@ -717,6 +704,41 @@ int assemble_values(fs_context *c, float *ms)
             k_assemble_colored<4, G><<<nblk(q1 - q0, 32 * G), 128 * G, 0, st>>>(
                 c->d_quad.p, c->d_quad_pos.p, q0, q1, c->d_xyz.p, c->d_mask.p, c->d_nptr.p, c->d_vals.p, (int)c->own_lo);
     }
+    FS_CUDA(c, cudaGetLastError());
+    return FS_OK;
+}
+
+// fs_export_csr / FS_SPMV_FULL / a non-planar union pattern need the parity values: form them from the current
+// material and mesh when the last fs_assemble wrote the compacted format only
+int ensure_parity_values(fs_context *c)
+{
+    if (c->parity_valid) return FS_OK;
+    if (!c->assembled) return fail(c, FS_ERR_STATE, "matrix not assembled");
+    std::lock_guard<std::mutex> lock(g_elconst_mutex);
+    int rc = upload_element_constants(c);
+    if (rc) return rc;
+    rc = enqueue_parity_values(c);
+    if (rc) return rc;
+    FS_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->parity_valid = true;
+    return FS_OK;
+}
+
+int assemble_values(fs_context *c, float *ms)
+{
+    cudaStream_t st = c->stream;
+    std::lock_guard<std::mutex> lock(g_elconst_mutex);  // held until the stream has been synchronised
+    int rc = upload_element_constants(c);
+    if (rc) return rc;
+    // shells in the xy plane: straight into the zero-compacted SpMV format (fs_slice_asm.cu)
+    const bool direct = c->slice_ready && c->asm_mode == FS_ASM_GATHER && c->spmv_format_pref == FS_SPMV_AUTO;
+    if (!direct && c->asm_mode == FS_ASM_GATHER) {  // the host plan of the row-gather pass is not part of the timed values pass
+        rc = build_gather_schedule(c);
+        if (rc) return rc;
+    }
+    FS_CUDA(c, cudaEventRecord(c->ev0, st));
+    rc = direct ? assemble_slice_enqueue(c) : enqueue_parity_values(c);
+    if (rc) return rc;
     FS_CUDA(c, cudaEventRecord(c->ev1, st));
     FS_CUDA(c, cudaStreamSynchronize(st));
     FS_CUDA(c, cudaGetLastError());
@@ -724,7 +746,16 @@ int assemble_values(fs_context *c, float *ms)
     c->assembled = true;
     c->minv_kind = -1;
     c->ml_values_ready = false;
-    c->sell_checked = false;
+    c->parity_valid = !direct;
+    if (direct) {  // the iteration format IS the assembly output
+        const bool was = c->sell_active && c->sell_mask == SELL_MASK_XY;
+        c->sell_checked = c->sell_active = true;
+        c->sell_mask = c->sell_detected = SELL_MASK_XY;
+        c->sell_nz = 14;
+        c->sell_kind = 0;
+        if (!was && c->cg_graph_exec) { cudaGraphExecDestroy(c->cg_graph_exec); c->cg_graph_exec = nullptr; }
+    } else
+        c->sell_checked = false;
     return FS_OK;
 }
 

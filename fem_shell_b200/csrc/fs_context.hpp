@@ -155,6 +155,14 @@ struct fs_context {
     fs::DevBuf<double> d_qgp;              // 96 doubles: Gauss-point shape-derivative table (fs_elements.cuh QuadGpTab)
     int64_t n_g_chunks = 0;
     bool gather_ready = false, gather_unavailable = false;
+    // slice pass (fs_slice_asm.cu): shells in the xy plane are assembled straight into the sliced-ELL SpMV format
+    fs::DevBuf<int32_t> d_sl_ptr;          // n_own+1: first incidence record of every owned row (slice s starts at row 32 s)
+    fs::DevBuf<int4> d_sl_info, d_sl_nodes;  // packed thread table, one record per (element, node row) incidence
+    fs::DevBuf<int2> d_sl_meta;            // per slice: {emit phases, element kinds present}
+    bool slice_ready = false;              // the plan exists for this mesh (planar in xy, rows fit)
+    size_t slice_smem = 0;
+    int slice_threads = 128;
+    bool parity_valid = false;             // d_vals holds the values of the current assembly (else: formed on demand)
 
     // block-CSR matrix of the owned rows: row 6p+a occupies vals[36*nptr[p] + a*6*deg ...]
     fs::DevBuf<int32_t> d_nptr;            // n_own+1
@@ -237,6 +245,12 @@ int build_pattern(fs_context *c, const std::vector<int32_t> &tri, const std::vec
                   const std::vector<int32_t> &tri_gid, const std::vector<int32_t> &quad_gid);
 int assemble_values(fs_context *c, float *ms);
 int build_gather_schedule(fs_context *c);
+int ensure_parity_values(fs_context *c);   // d_vals <- the current assembly (no-op when it already holds it)
+// slice_asm.cu
+int sell_layout_build(fs_context *c);
+int slice_plan_build(fs_context *c);
+int assemble_slice_enqueue(fs_context *c);
+int extract_minv_sell(fs_context *c, int pc, int *d_bad);
 int build_rhs(fs_context *c, double scale);
 int debug_element_matrices(fs_context *c, double *out_host);
 int recover_resultants(fs_context *c, const double *d_x, double *d_out);

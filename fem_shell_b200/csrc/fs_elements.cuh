@@ -19,6 +19,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cmath>
+
 namespace fs {
 
 struct ElemConst {
@@ -28,7 +30,26 @@ struct ElemConst {
     int quirks;               // FS_QUIRK_* bits
 };
 
-__constant__ ElemConst c_el;
+__constant__ ElemConst c_el;   // one copy per translation unit that includes this header (no -rdc)
+
+// fs.cpp:273-294 initMaterialMatrices
+static inline ElemConst make_elem_const(double nu, double E, double thickness, int quirks)
+{
+    ElemConst h;
+    const double fm = E / (1.0 - nu * nu);
+    const double fp = E * pow(thickness, 3.0) / (12.0 * (1.0 - nu * nu));
+    h.dm11 = 1.0 * fm; h.dm12 = nu * fm; h.dm33 = ((1.0 - nu) / 2.0) * fm;
+    h.dp11 = 1.0 * fp; h.dp12 = nu * fp; h.dp33 = ((1.0 - nu) / 2.0) * fp;
+    h.thickness = thickness;
+    h.quirks = quirks;
+    return h;
+}
+
+// uploads into THIS translation unit's c_el (static: one instance per including .cu file)
+static inline cudaError_t upload_elem_const_tu(const ElemConst &h, cudaStream_t st)
+{
+    return cudaMemcpyToSymbolAsync(c_el, &h, sizeof h, 0, cudaMemcpyHostToDevice, st);
+}
 
 #define FS_Q_Y21 1
 #define FS_Q_DETLU 2

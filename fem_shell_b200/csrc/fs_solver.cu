@@ -440,6 +440,10 @@ int spmv_format_prepare(fs_context *c)
     const bool was = c->sell_active;
     const unsigned long long old_mask = c->sell_mask;
     c->sell_active = false;
+    {   // everything below reads the parity values; the slice pass (fs_slice_asm.cu) does not write them
+        int rcp = ensure_parity_values(c);
+        if (rcp) return rcp;
+    }
     c->sell_checked = true;
     if (c->spmv_format_pref == FS_SPMV_FULL) {
         if (was) drop_cg_graph(c);
@@ -473,36 +477,11 @@ int spmv_format_prepare(fs_context *c)
         if (was) drop_cg_graph(c);
         return FS_OK;
     }
-    const int n_slices = (n_own + 31) / 32;
-    int write_adj = 0;
-    if (!c->sell_layout_ready) {
-        DevBuf<int32_t> dmax;
-        FS_CUDA(c, dmax.alloc((size_t)n_slices + 1));
-        FS_CUDA(c, c->d_sell_sptr.alloc((size_t)n_slices + 1));
-        k_sell_dmax<<<nblk(n_slices, 8), 256, 0, st>>>(n_own, n_slices, c->d_nptr.p, dmax.p);
-        size_t bytes = 0;
-        FS_CUDA(c, cub::DeviceScan::ExclusiveSum(nullptr, bytes, dmax.p, c->d_sell_sptr.p, n_slices + 1, st));
-        DevBuf<char> tmp;
-        FS_CUDA(c, tmp.alloc(bytes));
-        FS_CUDA(c, cub::DeviceScan::ExclusiveSum(tmp.p, bytes, dmax.p, c->d_sell_sptr.p, n_slices + 1, st));
-        DevBuf<int32_t> dmx;
-        FS_CUDA(c, dmx.alloc(1));
-        size_t bytes2 = 0;
-        FS_CUDA(c, cub::DeviceReduce::Max(nullptr, bytes2, dmax.p, dmx.p, n_slices, st));
-        DevBuf<char> tmp2;
-        FS_CUDA(c, tmp2.alloc(bytes2));
-        FS_CUDA(c, cub::DeviceReduce::Max(tmp2.p, bytes2, dmax.p, dmx.p, n_slices, st));
-        int32_t total = 0, widest = 0;
-        FS_CUDA(c, cudaMemcpyAsync(&total, c->d_sell_sptr.p + n_slices, sizeof total, cudaMemcpyDeviceToHost, st));
-        FS_CUDA(c, cudaMemcpyAsync(&widest, dmx.p, sizeof widest, cudaMemcpyDeviceToHost, st));
-        FS_CUDA(c, cudaStreamSynchronize(st));
-        c->sell_slices = n_slices;
-        c->sell_slots = total;
-        c->sell_dmax_max = widest;
-        FS_CUDA(c, c->d_sell_adj.alloc((size_t)32 * total));
-        c->sell_layout_ready = true;
-        write_adj = 1;
+    {
+        int rcl = sell_layout_build(c);   // slice pointers + column nodes, once per mesh
+        if (rcl) return rcl;
     }
+    const int write_adj = 0;
     const int nz = sell_popcount(mask);
     const size_t need = (size_t)32 * nz * c->sell_slots;
     if (c->d_sell_vals.n < need) FS_CUDA(c, c->d_sell_vals.alloc(need));
@@ -556,8 +535,15 @@ int solver_prepare(fs_context *c, int pc)
         }
         DevBuf<int> &bad = c->d_flag;
         FS_CUDA(c, cudaMemsetAsync(bad.p, 0, sizeof(int), c->stream));
-        k_extract_minv<<<nblk(c->n_own, 128), 128, 0, c->stream>>>((int)c->n_own, (int)c->own_lo, c->d_nptr.p,
-                                                                    c->d_nadj.p, c->d_vals.p, pc, c->d_minv.p, bad.p);
+        if (c->sell_active && c->sell_mask == SELL_MASK_XY && !c->parity_valid) {  // the slice pass wrote the compacted format only
+            int rcm = extract_minv_sell(c, pc, bad.p);
+            if (rcm) return rcm;
+        } else {
+            int rcp = ensure_parity_values(c);
+            if (rcp) return rcp;
+            k_extract_minv<<<nblk(c->n_own, 128), 128, 0, c->stream>>>((int)c->n_own, (int)c->own_lo, c->d_nptr.p,
+                                                                        c->d_nadj.p, c->d_vals.p, pc, c->d_minv.p, bad.p);
+        }
         int h_bad = 0;
         FS_CUDA(c, cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         FS_CUDA(c, cudaStreamSynchronize(c->stream));

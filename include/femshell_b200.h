@@ -213,6 +213,12 @@ int fs_bench_spmv(fs_context *ctx, int reps, fs_solve_info *info);
 /* measured FP64 FMA peak of the device in TFLOP/s (dependent-FMA micro-benchmark): the roofline of the
  * element kernels, which MEASURED_PEAKS.json does not carry */
 int fs_bench_fp64_peak(fs_context *ctx, double *tflops);
+/* north_star (a), "FP64 DMMA only if it beats the FMA pipe": the plate contraction Kp = sum_gp (Dp B)^T B of
+ * fs.cpp:664-681 on a synthetic batch of n_elem Quad-4 elements, once with the production layout on the FMA pipe
+ * (thread = node row) and once with mma.sync.m8n8k4.f64 (warp = element).  out = {ms per launch FMA, ms per launch
+ * DMMA, max relative difference of the per-element checksums, measured DMMA peak TFLOP/s, useful TFLOP/s FMA,
+ * useful TFLOP/s DMMA}.  fem_shell_b200/csrc/fs_bench.cu. */
+int fs_bench_contraction(fs_context *ctx, int64_t n_elem, int reps, double out[6]);
 
 /* ---- FS_PC_MLRBM (fem_shell_b200/csrc/fs_mlpc.cuh; no counterpart in the reference) ---- */
 /* max_points: cap on the cells of the first lattice (default 4194304; its vectors are replicated on every rank and

@@ -12,9 +12,12 @@ Reference anchors: assemble_elasticity fs.cpp:1160-1233, equation_systems.solve(
 On the residual bar.  Floating-point evaluation of b - K u itself carries an error of up to gamma_n |K||u| per row
 (Higham, Accuracy and Stability, eq. 3.13; n = 54 terms per interior row).  On these plates |K||u| / |b| is about 1e10
 (bending stiffness D/h^2 ~ 1e10 against nodal loads q h^2 ~ 3e-2), so NO double-precision solver -- PETSc included --
-can show a true relative residual of 1e-8 there: the measurable floor is ~1e-7.  The tests therefore assert
+can show a true relative residual of 1e-8 there.  The tests therefore assert
     ||b - K_oracle u|| <= rtol ||b|| + 2 n eps || |K_oracle| |u| ||
-with both terms evaluated by the oracle, and print the raw numbers.
+with both terms evaluated by the oracle, and print the raw numbers.  Measured on c2 (profiles/r02a_fullsize.txt): the
+worst-case bound is 1.0e-3 ||b||; the multilevel-PCG solution evaluates to 1.05e-5 (the statistical rounding level of
+the product), the 464 846-iteration Jacobi-PCG solution to 7.8e-4 (rounding-level high-frequency components that
+464 846 recurrence updates leave in u) -- while the two displacement fields agree to 8.1e-10 relative L2.
 """
 import numpy as np
 import pytest
@@ -150,9 +153,9 @@ def test_c2_jacobi_solution_solves_the_oracle_system_and_agrees_with_multilevel(
     u, info = solve_and_check(c2, c2.fsb.PC_JACOBI, 1e-8, 2000000, check_every=4096)
     d = np.linalg.norm(u - c2.u_ml) / np.linalg.norm(u)
     print("Jacobi-PCG needed %d iterations on c2; ||u_jacobi - u_multilevel|| / ||u|| = %.3e" % (info.iterations, d))
-    # two Krylov solves stopped at the same residual tolerance agree to cond-limited accuracy, not to the
-    # tolerance itself; the bound asserted is the measured one with head-room (see profiles/r02*_fullsize.txt)
-    assert d <= 1e-6
+    # north_star: "displacements within 1e-8 relative L2 at the same CG tolerance" (measured 8.1e-10,
+    # profiles/r02a_fullsize.txt)
+    assert d <= 1e-8
 
 
 def test_tri1000_solutions_solve_the_oracle_system(tri1000):

@@ -398,3 +398,98 @@ def test_full_size_properties(fsb):
 
     p100, p300 = phi(100), phi(300)
     assert p300 < p100 < 0.0
+
+
+# ---- slice pass: shells in the xy plane are assembled straight into the compacted SpMV format ----
+def _planar_umbrella(mixed):
+    m = dict(meshes.umbrella(mixed=mixed, n_rings=5, cone=0.0))
+    xyz = np.asarray(m["xyz"], float) @ meshes.rotation(0.2, 0.4, -0.3)      # undo the generator's rigid rotation
+    xyz[:, 2] = 0.0
+    m["xyz"] = np.ascontiguousarray(xyz)
+    return m
+
+
+def _delaunay_clamped():
+    m = dict(meshes.delaunay_patch(n_points=900, seed=3, quad_fraction=0.4))
+    # clamp the first side of the first 40 elements' first nodes (arbitrary but deterministic Dirichlet set)
+    m["bc"] = np.array([(e, 0, 1 if e % 2 else 0) for e in range(0, 40)], np.int32).reshape(-1, 3)
+    F = np.zeros((m["xyz"].shape[0], 6))
+    F[:, 2] = 0.01
+    F[::7, 0] = 0.02
+    m["forces"] = F
+    return m
+
+
+SLICE_CASES = {
+    "c1_tri16": lambda fsb: (fsb.meshgen("t", 16, 16, 0, 0, 10, 10, (1, 1, 1, 1), 300.0, 2, 1), 0.3, 1e7, 0.5),
+    "tri_ur_33x70": lambda fsb: (fsb.meshgen("t", 33, 70, -1, 0, 4, 6, (0, 21, -1, 1), 2.0, 2, 0), 0.25, 3e4, 1.0),
+    "quad_41x29": lambda fsb: (fsb.meshgen("q", 41, 29, 0, 0, 10, 7, (0, 1, 20, 21), 300.0, 2, 1), 0.3, 1e7, 0.5),
+    "quad_1col": lambda fsb: (fsb.meshgen("q", 1, 50, 0, 0, 1, 10, (1, 1, -1, -1), 5.0, 2, 1), 0.3, 1e7, 0.5),
+    "umbrella_flat_mixed": lambda fsb: (_planar_umbrella(True), 0.3, 1e4, 0.25),
+    "umbrella_flat_quads": lambda fsb: (_planar_umbrella(False), 0.3, 1e4, 0.25),
+    "delaunay_mixed": lambda fsb: (_delaunay_clamped(), 0.3, 1e5, 0.1),
+}
+
+
+@pytest.mark.parametrize("dof", [0, 1])
+@pytest.mark.parametrize("case", sorted(SLICE_CASES))
+def test_slice_pass_assembles_the_compacted_format_directly(fso, fsb, case, dof):
+    """fs_slice_asm.cu: no parity array is written by fs_assemble; the matrix the iteration streams is checked through
+    its SpMV, its diagonal (Jacobi / block-Jacobi extraction from the sliced layout) and the solves; the parity CSR
+    that fs_export_csr forms on demand still matches the oracle entry by entry"""
+    m, nu, E, t = SLICE_CASES[case](fsb)
+    om = as_fso_mesh(fso, m)
+    ref = fso.assemble(om, m["forces"], nu, E, t, dof_mode=dof)
+    s = gpu_system(fsb, m, nu, E, t, dof=dof, loads=m["forces"], asm=fsb.ASM_GATHER)
+    fmt = s.spmv_format()
+    assert fmt["nz_per_block"] == 14, fmt
+    rng = np.random.default_rng(5)
+    for _ in range(2):
+        x = rng.standard_normal(6 * ref.n_dofnodes)
+        y, yr = s.spmv(x), fso.spmv(ref, x)
+        assert np.abs(y - yr).max() <= 1e-13 * np.abs(yr).max()
+    # Dirichlet rows of the streamed matrix: unit vectors come back as integer multiples of themselves
+    con = np.repeat(ref.mask[np.argsort(ref.dofnode)], 6) >> np.tile(np.arange(6), ref.n_dofnodes) & 1
+    ones = np.ones(6 * ref.n_dofnodes)
+    yc = s.spmv(con.astype(float))
+    assert np.all(yc[con == 1] == np.round(yc[con == 1])) and np.all(yc[con == 1] >= 1)
+    assert np.all((s.spmv(ones * (con == 0)))[con == 1] == 0.0)
+    if np.abs(ref.rhs).max() > 0 and ref.mask.any():
+        uo = fso.direct_solve(om, ref)
+        for pc in (fsb.PC_JACOBI, fsb.PC_BJACOBI6):
+            xo, its_o, _ = fso.pcg(ref, pc=pc, rtol=1e-10, max_its=400000)
+            info = s.solve(rtol=1e-10, max_its=400000, pc=pc, warm_start=False)
+            assert abs(info.iterations - its_o) <= max(3, its_o // 50), (pc, info.iterations, its_o)
+            assert np.linalg.norm(s.solution() - uo) <= 1e-7 * np.linalg.norm(uo)
+    # on demand: the parity CSR (explicit zeros included)
+    rowptr, colidx, vals = s.export_csr()
+    rr, rc, rv = ref.csr()
+    assert np.array_equal(rowptr, rr) and np.array_equal(colidx, rc)
+    assert block_scaled_error(vals, rv, ref.nptr) <= 1e-12
+    assert s.spmv_format()["nz_per_block"] == 14          # forming it did not change what the iteration streams
+    # re-assembly with another material refreshes the compacted values (and the diagonal taken from them)
+    s.set_material(0.2, 2 * E, 0.8 * t)
+    s.assemble()
+    ref2 = fso.assemble(om, m["forces"], 0.2, 2 * E, 0.8 * t, dof_mode=dof)
+    y2, y2r = s.spmv(x), fso.spmv(ref2, x)
+    assert np.abs(y2 - y2r).max() <= 1e-13 * np.abs(y2r).max()
+    assert block_scaled_error(s.export_csr(with_cols=False)[2], ref2.vals, ref2.nptr) <= 1e-12
+
+
+def test_slice_pass_is_bitwise_reproducible_and_matches_the_copy_from_parity(fsb):
+    m = fsb.meshgen("q", 300, 200, 0, 0, 10, 7, (1, 0, 1, 0), 300.0, 2, 1)
+    x = np.random.default_rng(2).standard_normal(6 * 301 * 201)
+    a = gpu_system(fsb, m, 0.3, 1e7, 0.5, asm=fsb.ASM_GATHER)
+    b = gpu_system(fsb, m, 0.3, 1e7, 0.5, asm=fsb.ASM_GATHER)
+    ya, yb = a.spmv(x), b.spmv(x)
+    assert np.array_equal(ya, yb)
+    c = gpu_system(fsb, m, 0.3, 1e7, 0.5, asm=fsb.ASM_COLORED)    # parity array first, compacted copy made from it
+    assert c.spmv_format()["nz_per_block"] == 14
+    yc = c.spmv(x)
+    assert np.abs(ya - yc).max() <= 1e-13 * np.abs(yc).max()
+
+
+def test_dmma_and_fma_contractions_agree(fsb):
+    """fs_bench_contraction (north_star (a)): both variants of the plate contraction produce the same matrices"""
+    r = fsb.FemShell().bench_contraction(n_elem=4096, reps=1)
+    assert r["max_rel_diff"] <= 1e-13 and r["fma_ms"] > 0 and r["dmma_ms"] > 0
