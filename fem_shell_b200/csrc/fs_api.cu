@@ -13,6 +13,7 @@
 #include "fs_context.hpp"
 #include "fs_nccl.hpp"
 #include "fs_partition.hpp"
+#include "fs_host_par.hpp"
 
 using namespace fs;
 
@@ -204,15 +205,27 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
         return fail(c, FS_ERR_ARG, "empty mesh or null array");
     if (n_nodes >= (int64_t)1 << 31 || n_elem >= (int64_t)1 << 31) return fail(c, FS_ERR_ARG, "mesh too large for 32-bit ids");
     FS_CUDA(c, cudaSetDevice(c->device));
+    PhaseTimer tm("fs_set_mesh");
     // every argument check comes BEFORE the first collective step: a bad mesh on one rank must not leave the others
     // waiting in a barrier
-    for (int64_t e = 0; e < n_elem; e++) {
-        int nen = (int)(eptr[e + 1] - eptr[e]);
-        if ((etype[e] == FS_TRI3 && nen != 3) || (etype[e] == FS_QUAD4 && nen != 4) ||
-            (etype[e] != FS_TRI3 && etype[e] != FS_QUAD4))
-            return fail(c, FS_ERR_ARG, "element " + std::to_string(e) + ": only TRI3 (3) and QUAD4 (5) are supported");
-        for (int64_t k = eptr[e]; k < eptr[e + 1]; k++)
-            if (enodes[k] < 0 || enodes[k] >= n_nodes) return fail(c, FS_ERR_ARG, "node id out of range in element " + std::to_string(e));
+    const int ht = host_threads(c->world);
+    {
+        std::vector<int64_t> bad_type(ht, -1), bad_node(ht, -1);
+        parallel_chunks(n_elem, ht, [&](int t, int64_t e0, int64_t e1) {
+            for (int64_t e = e0; e < e1; e++) {
+                const int nen = (int)(eptr[e + 1] - eptr[e]);
+                if ((etype[e] == FS_TRI3 && nen != 3) || (etype[e] == FS_QUAD4 && nen != 4) || (etype[e] != FS_TRI3 && etype[e] != FS_QUAD4)) {
+                    if (bad_type[t] < 0) bad_type[t] = e;
+                    continue;
+                }
+                for (int64_t k = eptr[e]; k < eptr[e + 1]; k++)
+                    if ((enodes[k] < 0 || enodes[k] >= n_nodes) && bad_node[t] < 0) bad_node[t] = e;
+            }
+        });
+        for (int t = 0; t < ht; t++) {
+            if (bad_type[t] >= 0) return fail(c, FS_ERR_ARG, "element " + std::to_string(bad_type[t]) + ": only TRI3 (3) and QUAD4 (5) are supported");
+            if (bad_node[t] >= 0) return fail(c, FS_ERR_ARG, "node id out of range in element " + std::to_string(bad_node[t]));
+        }
     }
     for (int64_t i = 0; i < n_bc; i++) {
         const int32_t e = bc[3 * i], sd = bc[3 * i + 1];
@@ -229,39 +242,55 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
     c->ml_geom_ready = c->ml_values_ready = false;
     if (c->cg_graph_exec) { cudaGraphExecDestroy(c->cg_graph_exec); c->cg_graph_exec = nullptr; }
 
+    tm.lap("validate + teardown");
     // ---- DOF order (a12) ----
     const int64_t n_g = compute_dof_order(c->dof_mode, n_nodes, n_elem, eptr, enodes, c->dofnode);
     c->n_dofnodes_global = n_g;
-    c->node_of_dof.assign(n_g, -1);
-    for (int64_t i = 0; i < n_nodes; i++)
-        if (c->dofnode[i] >= 0) c->node_of_dof[c->dofnode[i]] = (int32_t)i;
+    c->node_of_dof.resize(n_g);
+    parallel_chunks(n_nodes, ht, [&](int, int64_t i0, int64_t i1) {
+        for (int64_t i = i0; i < i1; i++)
+            if (c->dofnode[i] >= 0) c->node_of_dof[c->dofnode[i]] = (int32_t)i;   // a permutation: distinct targets
+    });
 
-    // bounding box of the nodes that carry DOFs (lattice of the multilevel preconditioner, fs_mlpc.cuh)
+    tm.lap("dof order");
+    // bounding box of the nodes that carry DOFs and largest element extent per axis (lattice of the multilevel
+    // preconditioner, fs_mlpc.cuh: the cells of the first lattice are three element extents wide)
     {
-        bool first = true;
-        for (int64_t i = 0; i < n_nodes; i++) {
-            if (c->dofnode[i] < 0) continue;
-            for (int d = 0; d < 3; d++) {
-                const double v = xyz[3 * i + d];
-                if (first || v < c->bbox_lo[d]) c->bbox_lo[d] = v;
-                if (first || v > c->bbox_hi[d]) c->bbox_hi[d] = v;
-            }
-            first = false;
-        }
-        // largest element extent per axis: the cells of the first lattice are three of these wide
-        for (int d = 0; d < 3; d++) c->ml_h[d] = 0.0;
-        for (int64_t e = 0; e < n_elem; e++)
-            for (int d = 0; d < 3; d++) {
-                double lo = xyz[3 * (int64_t)enodes[eptr[e]] + d], hi = lo;
-                for (int64_t k = eptr[e] + 1; k < eptr[e + 1]; k++) {
-                    const double v = xyz[3 * (int64_t)enodes[k] + d];
-                    lo = std::min(lo, v);
-                    hi = std::max(hi, v);
+        const double inf = 1e300;
+        std::vector<double> lo(3 * ht, inf), hi(3 * ht, -inf), hmax(3 * ht, 0.0);
+        parallel_chunks(n_nodes, ht, [&](int t, int64_t i0, int64_t i1) {
+            for (int64_t i = i0; i < i1; i++) {
+                if (c->dofnode[i] < 0) continue;
+                for (int d = 0; d < 3; d++) {
+                    const double v = xyz[3 * i + d];
+                    lo[3 * t + d] = std::min(lo[3 * t + d], v);
+                    hi[3 * t + d] = std::max(hi[3 * t + d], v);
                 }
-                c->ml_h[d] = std::max(c->ml_h[d], hi - lo);
             }
+        });
+        parallel_chunks(n_elem, ht, [&](int t, int64_t e0, int64_t e1) {
+            for (int64_t e = e0; e < e1; e++)
+                for (int d = 0; d < 3; d++) {
+                    double l = xyz[3 * (int64_t)enodes[eptr[e]] + d], h = l;
+                    for (int64_t k = eptr[e] + 1; k < eptr[e + 1]; k++) {
+                        const double v = xyz[3 * (int64_t)enodes[k] + d];
+                        l = std::min(l, v);
+                        h = std::max(h, v);
+                    }
+                    hmax[3 * t + d] = std::max(hmax[3 * t + d], h - l);
+                }
+        });
+        for (int d = 0; d < 3; d++) {
+            c->bbox_lo[d] = inf; c->bbox_hi[d] = -inf; c->ml_h[d] = 0.0;
+            for (int t = 0; t < ht; t++) {
+                c->bbox_lo[d] = std::min(c->bbox_lo[d], lo[3 * t + d]);
+                c->bbox_hi[d] = std::max(c->bbox_hi[d], hi[3 * t + d]);
+                c->ml_h[d] = std::max(c->ml_h[d], hmax[3 * t + d]);
+            }
+            if (c->bbox_lo[d] > c->bbox_hi[d]) c->bbox_lo[d] = c->bbox_hi[d] = 0.0;
+        }
     }
-
+    tm.lap("bbox + element extents");
     // ---- Dirichlet bits (fs.cpp:90-120) and coupling interface (fsp.cpp:55-71) ----
     c->node_mask.assign(n_nodes, 0);
     std::vector<uint8_t> is_if(n_nodes, 0);
@@ -282,9 +311,10 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
     c->sols.clear();  // coupled-step state (fsp.cpp:77-87): sized by the first fs_step, not by every mesh
     c->pre_sols.clear();
 
+    tm.lap("dirichlet + interface");
     // ---- node-block partition of the DOF order (fs_partition.cpp) ----
     PartitionPlan plan;
-    if (plan_partition(c->dofnode, n_g, n_elem, eptr, enodes, c->rank, c->world, plan) != FS_OK)
+    if (plan_partition(c->dofnode, n_g, n_elem, eptr, enodes, c->rank, c->world, plan, ht) != FS_OK)
         return fail(c, FS_ERR_ARG, "fewer nodes than ranks");
     c->own_begin = plan.own_begin;
     c->own_end = plan.own_end;
@@ -292,8 +322,11 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
     c->own_lo = plan.own_lo;
     c->local_to_global = plan.local_to_global;
     c->n_local = (int64_t)c->local_to_global.size();
-    std::vector<int32_t> g2l(n_g, -1);
-    for (int64_t l = 0; l < c->n_local; l++) g2l[c->local_to_global[l]] = (int32_t)l;
+    std::vector<int32_t> g2l;
+    if (c->world > 1) {   // one rank: local == global
+        g2l.assign(n_g, -1);
+        for (int64_t l = 0; l < c->n_local; l++) g2l[c->local_to_global[l]] = (int32_t)l;
+    }
     const std::vector<int32_t> &loc_elems = plan.loc_elems;
     const std::vector<int32_t> &send_idx = plan.send_idx;
     c->peers.clear();
@@ -310,35 +343,63 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
     if (!send_idx.empty())
         FS_CUDA(c, cudaMemcpy(c->d_send_idx.p, send_idx.data(), sizeof(int32_t) * send_idx.size(), cudaMemcpyHostToDevice));
 
+    tm.lap("partition plan");
     // ---- device mesh in local numbering ----
     std::vector<double> lxyz(3 * c->n_local);
     std::vector<uint8_t> lmask(c->n_local);
-    for (int64_t l = 0; l < c->n_local; l++) {
-        int32_t node = c->node_of_dof[c->local_to_global[l]];
-        lxyz[3 * l + 0] = xyz[3 * (int64_t)node + 0];
-        lxyz[3 * l + 1] = xyz[3 * (int64_t)node + 1];
-        lxyz[3 * l + 2] = xyz[3 * (int64_t)node + 2];
-        lmask[l] = c->node_mask[node];
-    }
+    parallel_chunks(c->n_local, ht, [&](int, int64_t l0, int64_t l1) {
+        for (int64_t l = l0; l < l1; l++) {
+            const int32_t node = c->node_of_dof[c->local_to_global[l]];
+            lxyz[3 * l + 0] = xyz[3 * (int64_t)node + 0];
+            lxyz[3 * l + 1] = xyz[3 * (int64_t)node + 1];
+            lxyz[3 * l + 2] = xyz[3 * (int64_t)node + 2];
+            lmask[l] = c->node_mask[node];
+        }
+    });
     FS_CUDA(c, c->d_xyz.alloc(3 * c->n_local));
     FS_CUDA(c, c->d_mask.alloc(c->n_local));
     FS_CUDA(c, cudaMemcpy(c->d_xyz.p, lxyz.data(), sizeof(double) * 3 * c->n_local, cudaMemcpyHostToDevice));
     FS_CUDA(c, cudaMemcpy(c->d_mask.p, lmask.data(), c->n_local, cudaMemcpyHostToDevice));
 
+    tm.lap("local xyz/mask + upload");
+    // local connectivity in local node ids, triangles and quads apart, element order kept: count per chunk, then fill
     std::vector<int32_t> tri, quad, tri_gid, quad_gid;
-    for (int32_t e : loc_elems) {
-        const int nen = (int)(eptr[e + 1] - eptr[e]);
-        auto &dst = (nen == 3) ? tri : quad;
-        for (int k = 0; k < nen; k++) dst.push_back(g2l[c->dofnode[enodes[eptr[e] + k]]]);
-        ((nen == 3) ? tri_gid : quad_gid).push_back(e);
+    {
+        const int64_t nle = (int64_t)loc_elems.size();
+        std::vector<int64_t> ct(ht + 1, 0), cq(ht + 1, 0);
+        const int used = parallel_chunks(nle, ht, [&](int t, int64_t i0, int64_t i1) {
+            int64_t a = 0, b = 0;
+            for (int64_t i = i0; i < i1; i++) (eptr[loc_elems[i] + 1] - eptr[loc_elems[i]] == 3 ? a : b)++;
+            ct[t + 1] = a;
+            cq[t + 1] = b;
+        });
+        for (int t = 0; t < used; t++) { ct[t + 1] += ct[t]; cq[t + 1] += cq[t]; }
+        c->n_tri = ct[used];
+        c->n_quad = cq[used];
+        tri.resize(3 * c->n_tri); tri_gid.resize(c->n_tri);
+        quad.resize(4 * c->n_quad); quad_gid.resize(c->n_quad);
+        const bool one = c->world == 1;
+        parallel_chunks(nle, ht, [&](int t, int64_t i0, int64_t i1) {
+            int64_t a = ct[t], b = cq[t];
+            for (int64_t i = i0; i < i1; i++) {
+                const int32_t e = loc_elems[i];
+                const int nen = (int)(eptr[e + 1] - eptr[e]);
+                int32_t *dst = nen == 3 ? &tri[3 * a] : &quad[4 * b];
+                for (int k = 0; k < nen; k++) {
+                    const int32_t g = c->dofnode[enodes[eptr[e] + k]];
+                    dst[k] = one ? g : g2l[g];
+                }
+                if (nen == 3) tri_gid[a++] = e;
+                else quad_gid[b++] = e;
+            }
+        });
     }
-    c->n_tri = (int64_t)tri_gid.size();
-    c->n_quad = (int64_t)quad_gid.size();
 
+    tm.lap("local connectivity");
     // node ids of the owned dof-nodes and the node-id span they cover (load staging)
     std::vector<int32_t> node_of_own(c->n_own);
     int64_t lo = n_nodes, hi = -1;
-    for (int64_t p = 0; p < c->n_own; p++) {
+    for (int64_t p = 0; p < c->n_own; p++) {   // cheap: one pass over the owned nodes
         int32_t node = c->node_of_dof[c->own_begin + p];
         node_of_own[p] = node;
         lo = std::min<int64_t>(lo, node);
@@ -351,13 +412,21 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
     FS_CUDA(c, c->d_stage.alloc(6 * c->span_n));
     FS_CUDA(c, c->d_F.alloc(6 * c->n_own));
     FS_CUDA(c, cudaMemset(c->d_F.p, 0, sizeof(double) * 6 * c->n_own));
-    for (DevBuf<double> *v : {&c->d_b, &c->d_x, &c->d_r, &c->d_p, &c->d_q, &c->d_z}) {
-        FS_CUDA(c, v->alloc(6 * c->n_local));
-        FS_CUDA(c, cudaMemset(v->p, 0, sizeof(double) * 6 * c->n_local));
+    {   // the six CG vectors share one allocation (cudaMalloc is the expensive part of this step)
+        const size_t len = ((size_t)6 * c->n_local + 31) & ~(size_t)31;   // 256-byte aligned pieces
+        for (DevBuf<double> *v : {&c->d_b, &c->d_x, &c->d_r, &c->d_p, &c->d_q, &c->d_z}) v->release();
+        FS_CUDA(c, c->d_vecpool.alloc(6 * len));
+        FS_CUDA(c, cudaMemsetAsync(c->d_vecpool.p, 0, sizeof(double) * 6 * len, c->stream));
+        int k = 0;
+        for (DevBuf<double> *v : {&c->d_b, &c->d_x, &c->d_r, &c->d_p, &c->d_q, &c->d_z}) v->view(c->d_vecpool.p + len * (k++), 6 * (size_t)c->n_local);
     }
     c->d_full.release();
+    tm.lap("vectors");
     FS_TRY(peer_window_setup(c));
-    return build_pattern(c, tri, quad, tri_gid, quad_gid);
+    tm.lap("peer window");
+    const int rcb = build_pattern(c, tri, quad, tri_gid, quad_gid);
+    tm.lap("build_pattern (device)");
+    return rcb;
 }
 
 // ---------------------------------------------------------------------------------------------

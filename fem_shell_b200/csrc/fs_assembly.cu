@@ -272,6 +272,7 @@ int build_pattern(fs_context *c, const std::vector<int32_t> &tri, const std::vec
     const int64_t nt = c->n_tri, nq = c->n_quad;
     const int own_lo = (int)c->own_lo, n_own = (int)c->n_own;
     cudaStream_t st = c->stream;
+    PhaseTimer tm("build_pattern");
     FS_CUDA(c, c->d_tri.alloc(nt * 3));
     FS_CUDA(c, c->d_quad.alloc(nq * 4));
     FS_CUDA(c, c->d_tri_gid.alloc(nt));
@@ -317,7 +318,35 @@ int build_pattern(fs_context *c, const std::vector<int32_t> &tri, const std::vec
     FS_CUDA(c, cudaStreamSynchronize(st));
     cand.release();
 
-    // ---- colouring ----
+    tm.lap("adjacency");
+    // the element colouring is only needed by the coloured scatter pass: ensure_coloring() builds it on first use
+    c->n_colors = 0;
+    c->colored = false;
+    // ---- scatter slots ----
+    FS_CUDA(c, c->d_tri_pos.alloc(nt * 9));
+    FS_CUDA(c, c->d_quad_pos.alloc(nq * 16));
+    if (nt) k_positions<<<nblk(nt * 9, 256), 256, 0, st>>>(c->d_tri.p, 3, nt, own_lo, n_own, c->d_nptr.p, c->d_nadj.p, c->d_tri_pos.p);
+    if (nq) k_positions<<<nblk(nq * 16, 256), 256, 0, st>>>(c->d_quad.p, 4, nq, own_lo, n_own, c->d_nptr.p, c->d_nadj.p, c->d_quad_pos.p);
+    FS_CUDA(c, cudaStreamSynchronize(st));
+    FS_CUDA(c, cudaGetLastError());
+    c->d_vals.release();   // the parity values are allocated by the first pass that writes them
+    c->parity_valid = false;
+    tm.lap("positions");
+    rc = slice_plan_build(c);
+    if (rc) return rc;
+    tm.lap("slice plan");
+    c->pattern_ready = true;
+    return FS_OK;
+}
+
+// Element colouring + colour-sorted element arrays for k_assemble_colored (once per mesh, on first use).  The
+// thread tables of the other two passes hold node ids and slots, not element indices, so they stay valid.
+int ensure_coloring(fs_context *c)
+{
+    if (c->colored) return FS_OK;
+    const int64_t nt = c->n_tri, nq = c->n_quad;
+    const int own_lo = (int)c->own_lo, n_own = (int)c->n_own;
+    cudaStream_t st = c->stream;
     DevBuf<unsigned long long> node_best, node_used;
     DevBuf<int32_t> tcol, qcol;
     FS_CUDA(c, node_best.alloc(c->n_local));
@@ -325,7 +354,7 @@ int build_pattern(fs_context *c, const std::vector<int32_t> &tri, const std::vec
     FS_CUDA(c, tcol.alloc(nt));
     FS_CUDA(c, qcol.alloc(nq));
     FS_CUDA(c, cudaMemsetAsync(node_used.p, 0, sizeof(unsigned long long) * c->n_local, st));
-    rc = color_family(c, c->d_tri.p, c->d_tri_gid.p, 3, nt, tcol.p, node_best.p, node_used.p, c->n_local);
+    int rc = color_family(c, c->d_tri.p, c->d_tri_gid.p, 3, nt, tcol.p, node_best.p, node_used.p, c->n_local);
     if (rc) return rc;
     rc = color_family(c, c->d_quad.p, c->d_quad_gid.p, 4, nq, qcol.p, node_best.p, node_used.p, c->n_local);
     if (rc) return rc;
@@ -342,19 +371,11 @@ int build_pattern(fs_context *c, const std::vector<int32_t> &tri, const std::vec
     if (rc) return rc;
     rc = sort_family_by_color(c, c->d_quad, c->d_quad_gid, 4, nq, qcol.p, c->n_colors, c->quad_color_off);
     if (rc) return rc;
-
-    // ---- scatter slots ----
-    FS_CUDA(c, c->d_tri_pos.alloc(nt * 9));
-    FS_CUDA(c, c->d_quad_pos.alloc(nq * 16));
     if (nt) k_positions<<<nblk(nt * 9, 256), 256, 0, st>>>(c->d_tri.p, 3, nt, own_lo, n_own, c->d_nptr.p, c->d_nadj.p, c->d_tri_pos.p);
     if (nq) k_positions<<<nblk(nq * 16, 256), 256, 0, st>>>(c->d_quad.p, 4, nq, own_lo, n_own, c->d_nptr.p, c->d_nadj.p, c->d_quad_pos.p);
     FS_CUDA(c, cudaStreamSynchronize(st));
     FS_CUDA(c, cudaGetLastError());
-    c->d_vals.release();   // the parity values are allocated by the first pass that writes them
-    c->parity_valid = false;
-    rc = slice_plan_build(c);
-    if (rc) return rc;
-    c->pattern_ready = true;
+    c->colored = true;
     return FS_OK;
 }
 
@@ -691,6 +712,10 @@ static int enqueue_parity_values(fs_context *c)
             c->d_g_chunks.p, (int)c->n_g_chunks, c->d_g_info.p, c->d_g_nodes.p, c->d_xyz.p, c->d_vals.p, c->d_qgp.p);
         FS_CUDA(c, cudaGetLastError());
         return FS_OK;
+    }
+    {
+        int rc = ensure_coloring(c);
+        if (rc) return rc;
     }
     FS_CUDA(c, cudaMemsetAsync(c->d_vals.p, 0, sizeof(double) * 36 * (size_t)c->n_blocks, st));
     constexpr int G = 2;

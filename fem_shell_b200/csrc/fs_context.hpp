@@ -4,6 +4,8 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -149,6 +151,7 @@ struct fs_context {
     fs::DevBuf<int32_t> d_tri_gid, d_quad_gid;  // original element id (debug / determinism)
     std::vector<int64_t> tri_color_off, quad_color_off;  // n_colors+1 offsets
     int64_t n_colors = 0;
+    bool colored = false;                  // colouring + colour-sorted element arrays exist (built by the first coloured pass)
     // row-gather assembly schedule (fs_assembly.cu, build_gather_schedule)
     fs::DevBuf<fs::GatherChunk> d_g_chunks;
     fs::DevBuf<int4> d_g_info, d_g_nodes;  // packed thread table: {meta, row info, Dirichlet bits, slots}, node ids
@@ -191,6 +194,7 @@ struct fs_context {
     fs::DevBuf<double> d_stage;            // 6*span_n node-ordered staging for loads / solution
     fs::DevBuf<int32_t> d_node_of_own;     // n_own: mesh node id of owned dof-node p
     fs::DevBuf<double> d_full;             // 6*n_nodes gather buffer (multi-rank solution)
+    fs::DevBuf<double> d_vecpool;          // one allocation behind the six vectors below
     fs::DevBuf<double> d_b, d_x, d_r, d_p, d_q, d_z;
     fs::DevBuf<double> d_minv;             // 6*n_own (Jacobi) or 36*n_own (block)
     int minv_kind = -1;
@@ -224,6 +228,27 @@ struct fs_context {
 
 namespace fs {
 
+// FS_TIMING=1: phase timings of the set-up paths on stderr (host wall clock; the caller synchronises where it matters)
+struct PhaseTimer {
+    bool on;
+    double t0;
+    const char *what;
+    static double now()
+    {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec + 1e-9 * ts.tv_nsec;
+    }
+    explicit PhaseTimer(const char *w) : on(getenv("FS_TIMING") != nullptr), t0(0.0), what(w) { if (on) t0 = now(); }
+    void lap(const char *phase)
+    {
+        if (!on) return;
+        const double t = now();
+        fprintf(stderr, "[fs timing] %s / %-28s %8.2f ms\n", what, phase, 1e3 * (t - t0));
+        t0 = t;
+    }
+};
+
 inline int fail(fs_context *c, int code, const std::string &msg)
 {
     if (c) c->err = msg;
@@ -245,6 +270,7 @@ int build_pattern(fs_context *c, const std::vector<int32_t> &tri, const std::vec
                   const std::vector<int32_t> &tri_gid, const std::vector<int32_t> &quad_gid);
 int assemble_values(fs_context *c, float *ms);
 int build_gather_schedule(fs_context *c);
+int ensure_coloring(fs_context *c);
 int ensure_parity_values(fs_context *c);   // d_vals <- the current assembly (no-op when it already holds it)
 // slice_asm.cu
 int sell_layout_build(fs_context *c);

@@ -1,5 +1,6 @@
 // fs_partition.cpp -- see fs_partition.hpp
 #include "fs_partition.hpp"
+#include "fs_host_par.hpp"
 
 #include <algorithm>
 #include <cstring>
@@ -34,36 +35,62 @@ int owner_of(int64_t g, int64_t n_g, int world)
 }
 
 int plan_partition(const std::vector<int32_t> &dofnode, int64_t n_g, int64_t n_elem, const int64_t *eptr,
-                   const int32_t *enodes, int R, int W, PartitionPlan &p)
+                   const int32_t *enodes, int R, int W, PartitionPlan &p, int threads)
 {
     if (W < 1 || R < 0 || R >= W || n_g < W) return FS_ERR_ARG;
     p = PartitionPlan();
     p.n_global = n_g;
     p.own_begin = (int64_t)R * n_g / W;
     p.own_end = (int64_t)(R + 1) * n_g / W;
+    if (W == 1) {  // everything is local: no scan of the mesh
+        p.loc_elems.resize(n_elem);
+        p.local_to_global.resize(n_g);
+        parallel_chunks(n_elem, threads, [&](int, int64_t e0, int64_t e1) { for (int64_t e = e0; e < e1; e++) p.loc_elems[e] = (int32_t)e; });
+        parallel_chunks(n_g, threads, [&](int, int64_t g0, int64_t g1) { for (int64_t g = g0; g < g1; g++) p.local_to_global[g] = (int32_t)g; });
+        p.own_lo = 0;
+        return FS_OK;
+    }
 
-    // local elements = elements touching an owned node; local nodes = their nodes + owned nodes
+    // local elements = elements touching an owned node; local nodes = their nodes + owned nodes.  The scan over the
+    // replicated mesh runs on a few threads, each with its own lists; concatenated in element order afterwards, so
+    // the plan does not depend on the number of threads.
     std::vector<uint8_t> is_local(n_g, 0);
     for (int64_t g = p.own_begin; g < p.own_end; g++) is_local[g] = 1;
+    const int T_max = std::max(1, threads);
+    std::vector<std::vector<int32_t>> part_elems(T_max);
+    std::vector<std::vector<std::vector<int32_t>>> part_send(T_max, std::vector<std::vector<int32_t>>(W));
+    const int64_t ob = p.own_begin, oe = p.own_end;
+    parallel_chunks(n_elem, threads, [&](int t, int64_t e0, int64_t e1) {
+        std::vector<int32_t> &mine_elems = part_elems[t];
+        std::vector<std::vector<int32_t>> &send = part_send[t];
+        for (int64_t e = e0; e < e1; e++) {
+            const int nen = (int)(eptr[e + 1] - eptr[e]);
+            const int32_t *en = enodes + eptr[e];
+            bool mine = false, all_mine = true;
+            for (int k = 0; k < nen; k++) {
+                const int64_t g = dofnode[en[k]];
+                const bool own = g >= ob && g < oe;
+                mine = mine || own;
+                all_mine = all_mine && own;
+            }
+            if (!mine) continue;
+            mine_elems.push_back((int32_t)e);
+            if (all_mine) continue;  // interior element: nothing to mark, nothing to send
+            int owners[4];
+            for (int k = 0; k < nen; k++) owners[k] = owner_of(dofnode[en[k]], n_g, W);
+            for (int k = 0; k < nen; k++) {
+                const int32_t g = dofnode[en[k]];
+                __atomic_store_n(&is_local[g], (uint8_t)1, __ATOMIC_RELAXED);  // several threads may mark the same node
+                if (owners[k] == R)
+                    for (int l = 0; l < nen; l++)
+                        if (owners[l] != R) send[owners[l]].push_back(g);  // peer owners[l] needs my node g
+            }
+        }
+    });
     std::vector<std::vector<int32_t>> send(W);
-    for (int64_t e = 0; e < n_elem; e++) {
-        bool mine = false;
-        int owners[4];
-        const int nen = (int)(eptr[e + 1] - eptr[e]);
-        for (int k = 0; k < nen; k++) {
-            const int64_t g = dofnode[enodes[eptr[e] + k]];
-            owners[k] = (W == 1) ? 0 : owner_of(g, n_g, W);
-            mine = mine || owners[k] == R;
-        }
-        if (!mine) continue;
-        p.loc_elems.push_back((int32_t)e);
-        for (int k = 0; k < nen; k++) {
-            const int32_t g = dofnode[enodes[eptr[e] + k]];
-            is_local[g] = 1;
-            if (owners[k] == R)
-                for (int l = 0; l < nen; l++)
-                    if (owners[l] != R) send[owners[l]].push_back(g);  // peer owners[l] needs my node g
-        }
+    for (int t = 0; t < T_max; t++) {
+        p.loc_elems.insert(p.loc_elems.end(), part_elems[t].begin(), part_elems[t].end());
+        for (int r = 0; r < W; r++) send[r].insert(send[r].end(), part_send[t][r].begin(), part_send[t][r].end());
     }
     for (int64_t g = 0; g < n_g; g++)
         if (is_local[g]) p.local_to_global.push_back((int32_t)g);

@@ -35,6 +35,6 @@ int owner_of(int64_t g, int64_t n_g, int world);
 // Every rank derives its own plan from the replicated mesh; the send list of rank a to rank b and the
 // recv segment of rank b from rank a are the same set in the same (global) order by construction.
 int plan_partition(const std::vector<int32_t> &dofnode, int64_t n_g, int64_t n_elem, const int64_t *eptr,
-                   const int32_t *enodes, int rank, int world, PartitionPlan &plan);
+                   const int32_t *enodes, int rank, int world, PartitionPlan &plan, int threads = 1);
 
 }  // namespace fs

@@ -188,7 +188,8 @@ int fs_step(fs_context *ctx, int dims, char dead_axis, const double *forces_in, 
 int fs_commit_step(fs_context *ctx, int dims, char dead_axis);
 
 /* ---- parity / inspection ------------------------------------------------ */
-/* sizes of the (rank-local) system: numbered nodes, 6x6 blocks, owned node range */
+/* sizes of the (rank-local) system: numbered nodes, 6x6 blocks, element colours (0 until a coloured pass has
+ * run: the colouring is built on first use), owned node range */
 int fs_get_sizes(fs_context *ctx, int64_t *n_dofnodes, int64_t *n_blocks, int64_t *n_colors,
                  int64_t *own_begin, int64_t *own_end);
 /* node -> position in the DOF order (-1 for nodes no element references), n_nodes entries */

@@ -458,6 +458,11 @@ def test_slice_pass_assembles_the_compacted_format_directly(fso, fsb, case, dof)
         uo = fso.direct_solve(om, ref)
         for pc in (fsb.PC_JACOBI, fsb.PC_BJACOBI6):
             xo, its_o, _ = fso.pcg(ref, pc=pc, rtol=1e-10, max_its=400000)
+            if its_o < 0:      # K is not positive definite for this support (drilling term, fs.cpp:1036-1051): both CGs break down
+                with pytest.raises(fsb.FemShellError) as ei:
+                    s.solve(rtol=1e-10, max_its=400000, pc=pc, warm_start=False)
+                assert ei.value.code == fsb.FS_ERR_BREAKDOWN
+                continue
             info = s.solve(rtol=1e-10, max_its=400000, pc=pc, warm_start=False)
             assert abs(info.iterations - its_o) <= max(3, its_o // 50), (pc, info.iterations, its_o)
             assert np.linalg.norm(s.solution() - uo) <= 1e-7 * np.linalg.norm(uo)
