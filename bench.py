@@ -321,7 +321,7 @@ def run_c3(args, fsb, torch, dist, rank, world, local_rank, comm, peak):
         "rel_residual": info.rel_residual, "converged": info.status == 0,
         "time_to_solution_s": t_asm + t_solve,
         "spmv_ms_per_gpu": spmv_ms, "spmv_gbs_per_gpu": spmv_b / (spmv_ms * 1e-3) / 1e9, "spmv_frac_of_hbm_peak": spmv_b / (spmv_ms * 1e-3) / 1e9 / peak,
-        "spmv_nz_per_block": fmt["nz_per_block"], "ml_cells": mi["cells"],
+        "spmv_nz_per_block": fmt["nz_per_block"], "ml_cells": mi["cells"], "ml_distributed_levels": mi["distributed_levels"],
         "centre_deflection": float(w[nodes // 2, nodes // 2]), "thin_plate_series": w_ref, "deflection_ratio": float(w[nodes // 2, nodes // 2] / w_ref),
         "symmetry_err": float(np.abs(w - w.T).max() / np.abs(w).max()),
         "comm": "peer" if s.comm_mode() == fsb.COMM_PEER else "nccl",
@@ -552,7 +552,7 @@ def run_ours(args):
             tts_run(fsb.PC_MLRBM, 4, 0, residual=False)   # the timed Jacobi steps replaced the captured multilevel iteration
             r = tts_run(fsb.PC_MLRBM, 5000, 0)
             mi = s.ml_info()
-            r.update({"pc": "mlrbm", "ml_levels": mi["levels"], "ml_cells": mi["cells"], "ml_setup_ms": mi["setup_ms"],
+            r.update({"pc": "mlrbm", "ml_levels": mi["levels"], "ml_cells": mi["cells"], "ml_distributed_levels": mi["distributed_levels"], "ml_setup_ms": mi["setup_ms"],
                       "ml_lambda": mi["lambda"]})
             u_ml = s.solution() if args.tts_pc == "both" else None
             tts["multilevel"] = r

@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = [
     "fs_set_nodal_loads", "fs_set_interface_loads", "fs_build_rhs", "fs_assemble", "fs_solve",
     "fs_get_solution", "fs_get_solution_owned", "fs_recover_resultants", "fs_solve_host", "fs_interface_nodes", "fs_step", "fs_commit_step", "fs_get_sizes",
     "fs_export_dof_order", "fs_export_csr", "fs_export_rhs", "fs_debug_element_matrices", "fs_spmv_host",
-    "fs_bench_spmv", "fs_bench_fp64_peak", "fs_bench_contraction", "fs_set_ml_options", "fs_get_ml_info", "fs_debug_ml_level", "fs_apply_mlrbm_host", "fs_partition_plan", "fs_gather_plan", "fs_meshgen", "fs_read_xda", "fs_read_forces", "fs_write_xda",
+    "fs_bench_spmv", "fs_bench_fp64_peak", "fs_bench_contraction", "fs_set_ml_options", "fs_get_ml_info", "fs_get_ml_dist_levels", "fs_debug_ml_level", "fs_apply_mlrbm_host", "fs_partition_plan", "fs_gather_plan", "fs_meshgen", "fs_read_xda", "fs_read_forces", "fs_write_xda",
 ]
 
 
@@ -389,7 +389,9 @@ class FemShell:
         ms = C.c_double(0.0)
         self._ck(self.lib.fs_get_ml_info(self.ctx, C.byref(lv), cells, w, C.byref(ms)))
         n = int(lv.value)
-        return {"levels": n, "cells": [tuple(int(cells[3 * l + d]) for d in range(3)) for l in range(n)],
+        nd = C.c_int64(0)
+        self._ck(self.lib.fs_get_ml_dist_levels(self.ctx, C.byref(nd)))
+        return {"levels": n, "distributed_levels": int(nd.value), "cells": [tuple(int(cells[3 * l + d]) for d in range(3)) for l in range(n)],
                 "lambda": [float(w[i]) for i in range(n + 1)], "setup_ms": float(ms.value)}
 
     def ml_level(self, level, what):

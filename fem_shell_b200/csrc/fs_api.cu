@@ -811,6 +811,14 @@ int fs_get_ml_info(fs_context *c, int64_t *levels, int64_t *cells, double *weigh
     return FS_OK;
 }
 
+int fs_get_ml_dist_levels(fs_context *c, int64_t *n_dist)
+{
+    FS_CHECK_CTX(c);
+    if (!n_dist) return fail(c, FS_ERR_ARG, "null output");
+    *n_dist = c->ml_geom_ready ? c->ml.n_dist : 0;
+    return FS_OK;
+}
+
 int fs_debug_ml_level(fs_context *c, int level, int what, double *out, int64_t capacity, int64_t *count)
 {
     FS_CHECK_CTX(c);

@@ -83,6 +83,13 @@ struct MlLevelBuf {
     DevBuf<double> minv;         // (6n)^2, dense level only
     DevBuf<double> x, xb, b, r, t;  // 6n each
     double omega = 0.0, lambda = 0.0;
+    // distribution over the ranks (fs_mlpc.cu "distributed lattice levels"): cells are dealt out in slabs (all cells
+    // sharing the index of the slowest-varying active dimension); arrays keep their full size, a rank computes its own
+    // slabs [s0, s1) and keeps `halo` slabs of the neighbours' values valid on either side
+    bool dist = false;
+    int slab_len = 0, n_slabs = 0, s0 = 0, s1 = 0, halo = 1;
+    int c0 = 0, c1 = 0;             // owned cells [c0, c1) (replicated level: all)
+    DevBuf<double> stage;           // one slab: neighbour's partial sums of a restriction
 };
 
 struct MlHier {
@@ -94,6 +101,8 @@ struct MlHier {
     DevBuf<double> d_scalar;
     double omega0 = 0.0, lambda0 = 0.0;
     float setup_ms = 0.f;
+    int n_dist = 0;              // leading lattice levels that are distributed (0: all replicated)
+    std::vector<int> bounds[ML_MAX_LEVELS];  // first owned slab of every rank (+ n_slabs), per distributed level
 };
 
 }  // namespace fs

@@ -12,6 +12,17 @@
 //   coarsest        k_dense_matvec with the pseudo-inverse
 //   mesh level      k_f_prolong_t, SpMV, k_f_prolong_add   x += t - w D^-1 A t,  t = P_t e_1
 //                   SpMV, k_f_post_finish   z = x + w D^-1 (r - A x); partial r.z; advances the CG recurrence
+//
+// Distributed lattice levels (several ranks).  The cells of a lattice are dealt out in SLABS -- all cells sharing the
+// index of the slowest-varying active dimension -- in the order of the ranks' node blocks: rank j owns the slabs from
+// the one holding its first owned node up to the one before rank j+1's (bounds S_j; parent level: ceil(S_j / 3)).
+// Every array keeps its full size and global cell indices; a rank computes its own slabs only and keeps `halo` slabs
+// of its neighbours valid on either side (exchanged before each stencil application).  Restrictions form partial
+// sums where they are computed; the one boundary slab whose owner is the neighbour travels there and is added (two
+// addends: order-independent).  Below ML_DIST_MIN_CELLS cells, or with fewer than two slabs per rank, a level (and
+// everything coarser) is replicated as before: the last distributed level all-reduces its restricted residual.
+// The scheme needs the node blocks to follow the slab direction (true for meshGen's numbering and the first-encounter
+// order on it); otherwise every level stays replicated and only the restricted level-1 residual is all-reduced.
 #include <algorithm>
 #include <cmath>
 
@@ -104,13 +115,13 @@ k_f_resid(int64_t n6, const double *__restrict__ b, const double *__restrict__ q
 
 // b_1[a] = sum over the owned nodes i of aggregate a of B_i^T (r1_i - w q_i); eight lanes per aggregate
 __global__ void __launch_bounds__(256)
-k_f_restrict(const __grid_constant__ LatGeom g, const int32_t *__restrict__ sup_ptr, const int32_t *__restrict__ sup_node,
+k_f_restrict(const __grid_constant__ LatGeom g, int a0, int a1, const int32_t *__restrict__ sup_ptr, const int32_t *__restrict__ sup_node,
              const double *__restrict__ xyz_own, const uint8_t *__restrict__ mask_own, const double *__restrict__ r1,
              const double *__restrict__ q, double omega, double *__restrict__ y, const CgState *state, int chk)
 {
     ML_RETURN_IF_DONE(state, chk);
-    const int a = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3), sub = threadIdx.x & 7;
-    const bool valid = a < g.n;  // whole groups of eight share `a`; shuffles below stay inside the group
+    const int a = a0 + (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3), sub = threadIdx.x & 7;
+    const bool valid = a < a1;  // whole groups of eight share `a`; shuffles below stay inside the group
     double acc[6] = {0, 0, 0, 0, 0, 0};
     if (valid) {
         int k[3];
@@ -234,15 +245,15 @@ enum { LAT_RESID = 0, LAT_RSMOOTH = 1, LAT_PADD = 2, LAT_POST = 3 };
 //   POST     out1 = in + w D^+ (aux - v)       (out1 must not alias in)
 template <int MODE, int NS>
 __global__ void __launch_bounds__(192)
-k_lat_stencil(const __grid_constant__ LatGeom g, const double *__restrict__ A, const double *__restrict__ dinv,
+k_lat_stencil(const __grid_constant__ LatGeom g, int c0, int c1, const double *__restrict__ A, const double *__restrict__ dinv,
               const double *__restrict__ in, const double *aux, double *out1, double *__restrict__ out2, double omega,
               int flag, const CgState *state, int chk)
 {
     ML_RETURN_IF_DONE(state, chk);
     __shared__ __align__(16) double sh[192];
     const int64_t n6 = 6 * (int64_t)g.n;
-    const int64_t t = blockIdx.x * (int64_t)192 + threadIdx.x;
-    const bool valid = t < n6;
+    const int64_t t = 6 * (int64_t)c0 + blockIdx.x * (int64_t)192 + threadIdx.x;   // cells [c0, c1): this rank's slabs
+    const bool valid = t < 6 * (int64_t)c1;
     double v = 0.0;
     if (valid) {
         const int p = (int)(t / 6);
@@ -285,23 +296,25 @@ k_lat_stencil(const __grid_constant__ LatGeom g, const double *__restrict__ A, c
 }
 
 __global__ void __launch_bounds__(256)
-k_lat_smooth0(int64_t n6, const double *__restrict__ b, const double *__restrict__ dinv, double omega, double *__restrict__ x,
+k_lat_smooth0(int64_t t0, int64_t n6, const double *__restrict__ b, const double *__restrict__ dinv, double omega, double *__restrict__ x,
               const CgState *state, int chk)
 {
     ML_RETURN_IF_DONE(state, chk);
-    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t t = t0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // entries [t0, n6)
     if (t >= n6) return;
     x[t] = omega * dinv_row(dinv, t, b + 6 * (t / 6));
 }
 
 // parent cell K gathers its (up to 3^d) children: y[K] = sum B_c^T s_c, B_c = rigid-body modes of K at the child centre
+// parents [P0, P1); only children in [cc0, cc1) count (a rank's own cells: the sum is partial for a parent whose
+// children are split between two ranks)
 __global__ void __launch_bounds__(128)
-k_lat_restrict(const __grid_constant__ LatGeom gc, const __grid_constant__ LatGeom gp, const double *__restrict__ s,
-               double *__restrict__ y, const CgState *state, int chk)
+k_lat_restrict(const __grid_constant__ LatGeom gc, const __grid_constant__ LatGeom gp, int P0, int P1, int cc0, int cc1,
+               const double *__restrict__ s, double *__restrict__ y, const CgState *state, int chk)
 {
     ML_RETURN_IF_DONE(state, chk);
-    const int K = blockIdx.x * blockDim.x + threadIdx.x;
-    if (K >= gp.n) return;
+    const int K = P0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (K >= P1) return;
     int kp[3];
     double cp[3], acc[6] = {0, 0, 0, 0, 0, 0};
     lat_unindex(gp, K, kp);
@@ -312,10 +325,12 @@ k_lat_restrict(const __grid_constant__ LatGeom gc, const __grid_constant__ LatGe
             for (int i0 = 0; i0 < n0; i0++) {
                 const int kc[3] = {gc.active[0] ? 3 * kp[0] + i0 : 0, gc.active[1] ? 3 * kp[1] + i1 : 0, gc.active[2] ? 3 * kp[2] + i2 : 0};
                 if (kc[0] >= gc.np[0] || kc[1] >= gc.np[1] || kc[2] >= gc.np[2]) continue;
+                const int ci = lat_index(gc, kc);
+                if (ci < cc0 || ci >= cc1) continue;
                 double cc[3], sv[6];
                 lat_centre(gc, kc, cc);
                 const double rho[3] = {cc[0] - cp[0], cc[1] - cp[1], cc[2] - cp[2]};
-                load6(s + 6 * (size_t)lat_index(gc, kc), sv);
+                load6(s + 6 * (size_t)ci, sv);
                 rbm_apply_t(rho, sv, acc);
             }
     store6(y + 6 * (size_t)K, acc);
@@ -323,12 +338,12 @@ k_lat_restrict(const __grid_constant__ LatGeom gc, const __grid_constant__ LatGe
 
 // child cell: t = B_c e[parent]
 __global__ void __launch_bounds__(256)
-k_lat_prolong_t(const __grid_constant__ LatGeom gc, const __grid_constant__ LatGeom gp, const double *__restrict__ e,
+k_lat_prolong_t(const __grid_constant__ LatGeom gc, const __grid_constant__ LatGeom gp, int c0, int c1, const double *__restrict__ e,
                 double *__restrict__ tv, const CgState *state, int chk)
 {
     ML_RETURN_IF_DONE(state, chk);
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= gc.n) return;
+    const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;   // children [c0, c1)
+    if (c >= c1) return;
     int kc[3], kp[3];
     double cc[3], cp[3], ev[6], v[6];
     lat_unindex(gc, c, kc);
@@ -379,12 +394,12 @@ __global__ void k_lat_set_probe(const __grid_constant__ LatGeom g, int c0, int c
 // neighbour of colour col
 // With a paired probe (mode2 >= 0) row i of the response belongs to the column of the mode in ITS class (bit i of
 // class_a set: the class of `mode`); its entry in the other column is a structural zero and stays zero.
-__global__ void k_lat_collect(const __grid_constant__ LatGeom g, int c0, int c1, int c2, int mode, int mode2, unsigned class_a,
+__global__ void k_lat_collect(const __grid_constant__ LatGeom g, int cell0, int cell1, int c0, int c1, int c2, int mode, int mode2, unsigned class_a,
                               const double *__restrict__ y, double *__restrict__ A)
 {
     const int64_t n6 = 6 * (int64_t)g.n;
-    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= n6) return;
+    const int64_t t = 6 * (int64_t)cell0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // this rank's cells
+    if (t >= 6 * (int64_t)cell1) return;
     const int a = (int)(t / 6);
     int k[3], o[3];
     lat_unindex(g, a, k);
@@ -437,10 +452,10 @@ __device__ void ginv6(double M[6][6])
             if (!used[i] || !used[j]) M[i][j] = 0.0;
 }
 
-__global__ void k_lat_extract_dinv(const __grid_constant__ LatGeom g, const double *__restrict__ A, double *__restrict__ dinv)
+__global__ void k_lat_extract_dinv(const __grid_constant__ LatGeom g, int cell0, int cell1, const double *__restrict__ A, double *__restrict__ dinv)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= g.n) return;
+    const int p = cell0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= cell1) return;
     const int64_t n6 = 6 * (int64_t)g.n;
     const int zero[3] = {0, 0, 0};
     const int sc = lat_stencil_slot(g, zero);
@@ -533,6 +548,14 @@ k_dense_gj_step(int n, int k, double *__restrict__ M, const double *__restrict__
     if (i == k + 1) {  // each thread re-reads exactly the entries it wrote
         for (int j = threadIdx.x; j < n; j += blockDim.x) rowout[j] = Mi[j];
     }
+}
+
+// y += s (the neighbour's partial sums of a boundary slab; two addends, so the order does not matter)
+__global__ void k_add_into(int64_t n, const double *__restrict__ s, double *__restrict__ y, const CgState *state, int chk)
+{
+    ML_RETURN_IF_DONE(state, chk);
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n) y[t] += s[t];
 }
 
 // deterministic pseudo-random start vector of the power iterations
@@ -657,8 +680,136 @@ static int ml_build_geometry(fs_context *c)
     FS_CUDA(c, cudaMemset(m.d_r1.p, 0, sizeof(double) * 6 * n_local));
     FS_CUDA(c, cudaMemset(m.d_t.p, 0, sizeof(double) * 6 * n_local));
     FS_CUDA(c, m.d_scalar.alloc(4));
+
+    // ---- distribution of the leading lattice levels over the ranks (header comment) ----
+    for (int l = 0; l < m.n_lat; l++) {
+        MlLevelBuf &L = m.lat[l];
+        L.dist = false;
+        L.c0 = 0;
+        L.c1 = L.g.n;
+        int slow = 0;
+        for (int d = 0; d < 3; d++)
+            if (L.g.active[d]) slow = d;
+        L.n_slabs = L.g.np[slow];
+        L.slab_len = L.g.n / L.n_slabs;
+        L.s0 = 0;
+        L.s1 = L.n_slabs;
+        L.halo = 1;
+        m.bounds[l].clear();
+    }
+    m.n_dist = 0;
+    if (c->world > 1) {
+        const int W = c->world, R = c->rank;
+        int64_t min_cells = 32768;
+        if (const char *e = getenv("FS_ML_DIST_MIN_CELLS")) min_cells = std::max<int64_t>(1, atoll(e));
+        MlLevelBuf &L0 = m.lat[0];
+        // slabs touched by this rank's owned / local nodes
+        int32_t mine[5] = {0, INT32_MAX, -1, INT32_MAX, -1};   // first owned node's slab, owned min/max, local min/max
+        for (int64_t i = 0; i < n_local; i++) {
+            const int32_t sl = agg[i] / L0.slab_len;
+            mine[3] = std::min(mine[3], sl);
+            mine[4] = std::max(mine[4], sl);
+            if (i >= own_lo && i < own_lo + n_own) {
+                if (i == own_lo) mine[0] = sl;
+                mine[1] = std::min(mine[1], sl);
+                mine[2] = std::max(mine[2], sl);
+            }
+        }
+        DevBuf<int32_t> d_all;
+        FS_CUDA(c, d_all.alloc(5 * (size_t)(W + 1)));
+        FS_CUDA(c, cudaMemcpyAsync(d_all.p + 5 * W, mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+        FS_NCCL_ML(c, nccl().AllGather(d_all.p + 5 * W, d_all.p, 5, ncclInt32, (ncclComm_t)c->comm, c->stream));
+        std::vector<int32_t> all(5 * (size_t)W);
+        FS_CUDA(c, cudaMemcpyAsync(all.data(), d_all.p, sizeof(int32_t) * 5 * W, cudaMemcpyDeviceToHost, c->stream));
+        FS_CUDA(c, cudaStreamSynchronize(c->stream));
+        std::vector<int> S(W + 1);
+        S[0] = 0;
+        S[W] = L0.n_slabs;
+        for (int j = 1; j < W; j++) S[j] = all[5 * j];
+        bool ok = !L0.dense && L0.g.n >= min_cells;
+        int H = 1;
+        for (int j = 0; j < W && ok; j++) {
+            const int omin = all[5 * j + 1], omax = all[5 * j + 2], lmin = all[5 * j + 3], lmax = all[5 * j + 4];
+            if (omax < omin) ok = false;                                    // a rank without owned nodes
+            if (omin < S[j] || omax > std::min(S[j + 1], L0.n_slabs - 1)) ok = false;   // owned nodes leave [S_j, S_j+1]
+            H = std::max(H, std::max(S[j] - lmin, lmax - (S[j + 1] - 1)));
+        }
+        if (H > 2) ok = false;
+        for (int j = 0; j < W && ok; j++)
+            if (S[j + 1] - S[j] < std::max(2, H)) ok = false;
+        for (int l = 0; l < m.n_lat && ok; l++) {
+            MlLevelBuf &L = m.lat[l];
+            if (l > 0) {   // parent bounds: ceil(S / 3)
+                if (L.dense || L.g.n < min_cells) break;
+                std::vector<int> P(W + 1);
+                P[0] = 0;
+                P[W] = L.n_slabs;
+                bool fine_enough = true;
+                for (int j = 1; j < W; j++) P[j] = (S[j] + 2) / 3;
+                for (int j = 0; j < W; j++)
+                    if (P[j + 1] - P[j] < 2) fine_enough = false;
+                if (!fine_enough) break;
+                S = P;
+            }
+            L.dist = true;
+            L.halo = l == 0 ? H : 1;
+            L.s0 = S[R];
+            L.s1 = S[R + 1];
+            L.c0 = L.s0 * L.slab_len;
+            L.c1 = L.s1 * L.slab_len;
+            m.bounds[l] = S;
+            FS_CUDA(c, L.stage.alloc(6 * (size_t)L.slab_len));
+            m.n_dist = l + 1;
+        }
+        if (getenv("FS_TIMING") && R == 0) fprintf(stderr, "[fs timing] multilevel: %d of %d lattice levels distributed over %d ranks (halo %d)\n", m.n_dist, m.n_lat, W, H);
+    }
     c->ml_geom_ready = true;
     c->ml_values_ready = false;
+    return FS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// exchanges of a distributed level (NCCL point-to-point on the context stream; graph-capturable)
+// ---------------------------------------------------------------------------------------------
+// the `halo` boundary slabs of the neighbours' values into this rank's copy of vec (and ours into theirs)
+static int lat_halo(fs_context *c, int l, double *vec)
+{
+    MlLevelBuf &L = c->ml.lat[l];
+    if (!L.dist) return FS_OK;
+    const size_t slab = 6 * (size_t)L.slab_len, h = (size_t)L.halo * slab;
+    const int R = c->rank, W = c->world;
+    ncclComm_t comm = (ncclComm_t)c->comm;
+    FS_NCCL_ML(c, nccl().GroupStart());
+    if (R > 0) {
+        FS_NCCL_ML(c, nccl().Send(vec + 6 * (size_t)L.c0, h, ncclDouble, R - 1, comm, c->stream));
+        FS_NCCL_ML(c, nccl().Recv(vec + 6 * (size_t)L.c0 - h, h, ncclDouble, R - 1, comm, c->stream));
+    }
+    if (R < W - 1) {
+        FS_NCCL_ML(c, nccl().Send(vec + 6 * (size_t)L.c1 - h, h, ncclDouble, R + 1, comm, c->stream));
+        FS_NCCL_ML(c, nccl().Recv(vec + 6 * (size_t)L.c1, h, ncclDouble, R + 1, comm, c->stream));
+    }
+    FS_NCCL_ML(c, nccl().GroupEnd());
+    return FS_OK;
+}
+
+// partial sums of ONE slab that belongs to a neighbour travel there and are added.  up: the slab after this rank's
+// last one goes to rank+1 (restriction from the mesh: owned nodes reach into the next rank's first slab); down: the
+// slab before this rank's first one goes to rank-1 (restriction between lattices: a parent whose children are split).
+// send_it / recv_it: both sides derive them from the shared bounds.
+static int lat_reverse_add(fs_context *c, int l, double *vec, bool up, bool send_it, bool recv_it, int chk)
+{
+    MlLevelBuf &L = c->ml.lat[l];
+    const size_t slab = 6 * (size_t)L.slab_len;
+    const int R = c->rank;
+    ncclComm_t comm = (ncclComm_t)c->comm;
+    if (!send_it && !recv_it) return FS_OK;
+    FS_NCCL_ML(c, nccl().GroupStart());
+    if (send_it) FS_NCCL_ML(c, nccl().Send(up ? vec + 6 * (size_t)L.c1 : vec + 6 * (size_t)L.c0 - slab, slab, ncclDouble, up ? R + 1 : R - 1, comm, c->stream));
+    if (recv_it) FS_NCCL_ML(c, nccl().Recv(L.stage.p, slab, ncclDouble, up ? R - 1 : R + 1, comm, c->stream));
+    FS_NCCL_ML(c, nccl().GroupEnd());
+    if (recv_it)
+        k_add_into<<<nblk((int64_t)slab, 256), 256, 0, c->stream>>>((int64_t)slab, L.stage.p, up ? vec + 6 * (size_t)L.c0 : vec + 6 * (size_t)L.c1 - slab,
+                                                                    c->d_state.p, chk);
     return FS_OK;
 }
 
@@ -678,21 +829,30 @@ static int fine_restrict_chain(fs_context *c, const double *b, double *x, int ch
     k_f_resid<<<nblk(n6, 192), 192, 0, st>>>(n6, b ? b + o6 : nullptr, c->d_q.p + o6, c->d_minv.p, m.d_r1.p + o6, m.d_t.p + o6, st_of(c), chk);
     rc = spmv_once(c, m.d_t.p, c->d_q.p, chk != 0);
     if (rc) return rc;
-    const LatGeom &g1 = m.lat[0].g;
-    k_f_restrict<<<nblk(8 * (int64_t)g1.n, 256), 256, 0, st>>>(g1, m.d_sup_ptr.p, m.d_sup_node.p, c->d_xyz.p + 3 * c->own_lo,
-                                                              c->d_mask.p + c->own_lo, m.d_r1.p + o6, c->d_q.p + o6, m.omega0,
-                                                              m.lat[0].b.p, st_of(c), chk);
+    MlLevelBuf &L1 = m.lat[0];
+    const LatGeom &g1 = L1.g;
+    // distributed first lattice: the owned nodes reach the rank's own slabs and the first slab of the next rank
+    const int a0 = L1.dist ? L1.c0 : 0, a1 = L1.dist ? std::min(L1.s1 + 1, L1.n_slabs) * L1.slab_len : g1.n;
+    k_f_restrict<<<nblk(8 * (int64_t)(a1 - a0), 256), 256, 0, st>>>(g1, a0, a1, m.d_sup_ptr.p, m.d_sup_node.p, c->d_xyz.p + 3 * c->own_lo,
+                                                                   c->d_mask.p + c->own_lo, m.d_r1.p + o6, c->d_q.p + o6, m.omega0,
+                                                                   L1.b.p, st_of(c), chk);
+    if (L1.dist) return lat_reverse_add(c, 0, L1.b.p, true, c->rank < c->world - 1, c->rank > 0, chk);
     if (c->world > 1)
-        FS_NCCL_ML(c, nccl().AllReduce(m.lat[0].b.p, m.lat[0].b.p, 6 * (size_t)g1.n, ncclDouble, ncclSum, (ncclComm_t)c->comm, st));
+        FS_NCCL_ML(c, nccl().AllReduce(L1.b.p, L1.b.p, 6 * (size_t)g1.n, ncclDouble, ncclSum, (ncclComm_t)c->comm, st));
     return FS_OK;
 }
 
-// mesh level: x (+)= P e  (e on the first lattice, replicated)
-static int fine_prolong_chain(fs_context *c, const double *e, double *x, bool accumulate, int chk)
+// mesh level: x (+)= P e  (e on the first lattice: replicated, or valid on this rank's slabs -- then its halo slabs,
+// which hold the cells of the halo nodes, are fetched first; e_is_global: set-up probes are written everywhere)
+static int fine_prolong_chain(fs_context *c, double *e, double *x, bool accumulate, int chk, bool e_is_global = false)
 {
     MlHier &m = c->ml;
     cudaStream_t st = c->stream;
     const int64_t o6 = 6 * c->own_lo, n6 = 6 * c->n_own;
+    if (!e_is_global) {
+        int rc = lat_halo(c, 0, e);
+        if (rc) return rc;
+    }
     k_f_prolong_t<<<nblk(c->n_local, 256), 256, 0, st>>>(m.lat[0].g, c->n_local, m.d_agg.p, c->d_xyz.p, c->d_mask.p, e, m.d_t.p, st_of(c), chk);
     int rc = spmv_local(c, m.d_t.p, c->d_q.p, chk != 0);  // t is complete on owned and halo nodes: no exchange
     if (rc) return rc;
@@ -700,46 +860,82 @@ static int fine_prolong_chain(fs_context *c, const double *e, double *x, bool ac
     return FS_OK;
 }
 
-static void lat_restrict_chain(fs_context *c, int l, const double *b, const double *x, int chk)
+// lattice l: N.b = P^T (b - A x) for the next level N (b may be null: zero)
+static int lat_restrict_chain(fs_context *c, int l, const double *b, double *x, int chk)
 {
     MlHier &m = c->ml;
     MlLevelBuf &L = m.lat[l], &N = m.lat[l + 1];
     cudaStream_t st = c->stream;
-    const int64_t n6 = 6 * (int64_t)L.g.n;
-    LAT_STENCIL_LAUNCH(LAT_RESID, L.g, nblk(n6, 192), st, L.g, L.A.p, L.dinv.p, x, b, L.r.p, L.t.p, L.omega, 0, st_of(c), chk);
-    LAT_STENCIL_LAUNCH(LAT_RSMOOTH, L.g, nblk(n6, 192), st, L.g, L.A.p, L.dinv.p, L.t.p, L.r.p, L.r.p, nullptr, L.omega, 0, st_of(c), chk);
-    k_lat_restrict<<<nblk(N.g.n, 128), 128, 0, st>>>(L.g, N.g, L.r.p, N.b.p, st_of(c), chk);
+    const int64_t n6 = 6 * (int64_t)(L.c1 - L.c0);
+    int rc = lat_halo(c, l, x);
+    if (rc) return rc;
+    LAT_STENCIL_LAUNCH(LAT_RESID, L.g, nblk(n6, 192), st, L.g, L.c0, L.c1, L.A.p, L.dinv.p, x, b, L.r.p, L.t.p, L.omega, 0, st_of(c), chk);
+    rc = lat_halo(c, l, L.t.p);
+    if (rc) return rc;
+    LAT_STENCIL_LAUNCH(LAT_RSMOOTH, L.g, nblk(n6, 192), st, L.g, L.c0, L.c1, L.A.p, L.dinv.p, L.t.p, L.r.p, L.r.p, nullptr, L.omega, 0, st_of(c), chk);
+    if (!L.dist) {
+        k_lat_restrict<<<nblk(N.g.n, 128), 128, 0, st>>>(L.g, N.g, 0, N.g.n, 0, L.g.n, L.r.p, N.b.p, st_of(c), chk);
+        return FS_OK;
+    }
+    // parents with at least one child among this rank's slabs; the sum is partial where the children are split
+    const int P0 = (L.s0 / 3) * N.slab_len, P1 = ((L.s1 + 2) / 3) * N.slab_len;
+    if (!N.dist) FS_CUDA(c, cudaMemsetAsync(N.b.p, 0, sizeof(double) * 6 * (size_t)N.g.n, st));
+    k_lat_restrict<<<nblk(P1 - P0, 128), 128, 0, st>>>(L.g, N.g, P0, P1, L.c0, L.c1, L.r.p, N.b.p, st_of(c), chk);
+    if (N.dist) {  // the parent slab split with the rank below belongs to that rank
+        const std::vector<int> &S = m.bounds[l];
+        const int R = c->rank, W = c->world;
+        return lat_reverse_add(c, l + 1, N.b.p, false, R > 0 && S[R] % 3 != 0, R < W - 1 && S[R + 1] % 3 != 0, chk);
+    }
+    FS_NCCL_ML(c, nccl().AllReduce(N.b.p, N.b.p, 6 * (size_t)N.g.n, ncclDouble, ncclSum, (ncclComm_t)c->comm, st));
+    return FS_OK;
 }
 
-static void lat_prolong_chain(fs_context *c, int l, const double *e, double *x, bool accumulate, int chk)
+// lattice l: x (+)= P e, e on the next level (replicated, or valid on this rank's slabs of it; e_is_global: probes)
+static int lat_prolong_chain(fs_context *c, int l, double *e, double *x, bool accumulate, int chk, bool e_is_global = false)
 {
     MlHier &m = c->ml;
     MlLevelBuf &L = m.lat[l], &N = m.lat[l + 1];
     cudaStream_t st = c->stream;
-    const int64_t n6 = 6 * (int64_t)L.g.n;
-    k_lat_prolong_t<<<nblk(L.g.n, 256), 256, 0, st>>>(L.g, N.g, e, L.t.p, st_of(c), chk);
-    LAT_STENCIL_LAUNCH(LAT_PADD, L.g, nblk(n6, 192), st, L.g, L.A.p, L.dinv.p, L.t.p, nullptr, x, nullptr, L.omega, accumulate ? 1 : 0, st_of(c), chk);
+    const int64_t n6 = 6 * (int64_t)(L.c1 - L.c0);
+    if (N.dist && !e_is_global) {
+        int rc = lat_halo(c, l + 1, e);
+        if (rc) return rc;
+    }
+    // t = P_t e on this rank's cells and one slab beyond on either side, so that the stencil below needs no exchange
+    const int t0 = L.dist ? std::max(L.c0 - L.slab_len, 0) : 0, t1 = L.dist ? std::min(L.c1 + L.slab_len, L.g.n) : L.g.n;
+    k_lat_prolong_t<<<nblk(t1 - t0, 256), 256, 0, st>>>(L.g, N.g, t0, t1, e, L.t.p, st_of(c), chk);
+    LAT_STENCIL_LAUNCH(LAT_PADD, L.g, nblk(n6, 192), st, L.g, L.c0, L.c1, L.A.p, L.dinv.p, L.t.p, nullptr, x, nullptr, L.omega, accumulate ? 1 : 0, st_of(c), chk);
+    return FS_OK;
 }
 
-// one cycle on lattice level l for the right-hand side in lat[l].b; returns where the result lives
-static const double *lat_cycle(fs_context *c, int l, int chk)
+// one cycle on lattice level l for the right-hand side in lat[l].b; *out = where the result lives (valid on this
+// rank's cells of a distributed level)
+static int lat_cycle(fs_context *c, int l, int chk, double **out)
 {
     MlHier &m = c->ml;
     MlLevelBuf &L = m.lat[l];
     cudaStream_t st = c->stream;
-    const int64_t n6 = 6 * (int64_t)L.g.n;
+    *out = L.xb.p;
     if (L.dense) {
+        const int64_t n6 = 6 * (int64_t)L.g.n;
         k_dense_matvec<<<nblk(32 * n6, 256), 256, 0, st>>>((int)n6, L.minv.p, L.b.p, L.xb.p, st_of(c), chk);
-        return L.xb.p;
+        return FS_OK;
     }
-    k_lat_smooth0<<<nblk(n6, 256), 256, 0, st>>>(n6, L.b.p, L.dinv.p, L.omega, L.x.p, st_of(c), chk);
+    const int64_t t0 = 6 * (int64_t)L.c0, t1 = 6 * (int64_t)L.c1;
+    k_lat_smooth0<<<nblk(t1 - t0, 256), 256, 0, st>>>(t0, t1, L.b.p, L.dinv.p, L.omega, L.x.p, st_of(c), chk);
     for (int gmm = 0; gmm < c->ml_gamma; gmm++) {
-        lat_restrict_chain(c, l, L.b.p, L.x.p, chk);
-        const double *e = lat_cycle(c, l + 1, chk);
-        lat_prolong_chain(c, l, e, L.x.p, true, chk);
+        int rc = lat_restrict_chain(c, l, L.b.p, L.x.p, chk);
+        if (rc) return rc;
+        double *e = nullptr;
+        rc = lat_cycle(c, l + 1, chk, &e);
+        if (rc) return rc;
+        rc = lat_prolong_chain(c, l, e, L.x.p, true, chk);
+        if (rc) return rc;
     }
-    LAT_STENCIL_LAUNCH(LAT_POST, L.g, nblk(n6, 192), st, L.g, L.A.p, L.dinv.p, L.x.p, L.b.p, L.xb.p, nullptr, L.omega, 0, st_of(c), chk);
-    return L.xb.p;
+    int rc = lat_halo(c, l, L.x.p);
+    if (rc) return rc;
+    LAT_STENCIL_LAUNCH(LAT_POST, L.g, nblk(t1 - t0, 192), st, L.g, L.c0, L.c1, L.A.p, L.dinv.p, L.x.p, L.b.p, L.xb.p, nullptr, L.omega, 0, st_of(c), chk);
+    return FS_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -803,24 +999,26 @@ static int lat_lambda(fs_context *c, int l, double *lam)
     MlHier &m = c->ml;
     MlLevelBuf &L = m.lat[l];
     cudaStream_t st = c->stream;
-    const int64_t n6 = 6 * (int64_t)L.g.n;
+    const int64_t t0 = 6 * (int64_t)L.c0, n6 = 6 * (int64_t)(L.c1 - L.c0);   // this rank's entries
     const int grid = (int)std::min<int64_t>(nblk(n6, 256), (int64_t)c->sm_count * 4);
     int rc = ml_ensure_partials(c);
     if (rc) return rc;
     FS_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned int), st));
-    k_fill_hash<<<nblk(n6, 256), 256, 0, st>>>(n6, 0x51ed270b7f4a7c15ULL + (uint64_t)l, L.x.p);
+    k_fill_hash<<<nblk(n6, 256), 256, 0, st>>>(n6, 0x51ed270b7f4a7c15ULL + (uint64_t)l + (uint64_t)t0, L.x.p + t0);
     double est = 1.0;
     for (int it = 0; it < ML_POWER_ITS; it++) {
+        rc = lat_halo(c, l, L.x.p);
+        if (rc) return rc;
         // r = -A x ; t = -D^+ A x
-        LAT_STENCIL_LAUNCH(LAT_RESID, L.g, nblk(n6, 192), st, L.g, L.A.p, L.dinv.p, L.x.p, nullptr, L.r.p, L.t.p, 0.0, 0, st_of(c), 0);
-        k_norm2<256><<<grid, 256, 0, st>>>(n6, L.x.p, c->d_partials.p, c->d_counter.p, m.d_scalar.p);
-        k_norm2<256><<<grid, 256, 0, st>>>(n6, L.t.p, c->d_partials.p, c->d_counter.p, m.d_scalar.p + 1);
+        LAT_STENCIL_LAUNCH(LAT_RESID, L.g, nblk(n6, 192), st, L.g, L.c0, L.c1, L.A.p, L.dinv.p, L.x.p, nullptr, L.r.p, L.t.p, 0.0, 0, st_of(c), 0);
+        k_norm2<256><<<grid, 256, 0, st>>>(n6, L.x.p + t0, c->d_partials.p, c->d_counter.p, m.d_scalar.p);
+        k_norm2<256><<<grid, 256, 0, st>>>(n6, L.t.p + t0, c->d_partials.p, c->d_counter.p, m.d_scalar.p + 1);
         double h[2];
-        rc = read_scalar(c, m.d_scalar.p, 2, h, false);
+        rc = read_scalar(c, m.d_scalar.p, 2, h, L.dist);
         if (rc) return rc;
         if (!(h[0] > 0.0) || !(h[1] > 0.0)) return fail(c, FS_ERR_BREAKDOWN, "multilevel set-up: power iteration collapsed on a lattice");
         est = std::sqrt(h[1] / h[0]);
-        k_scale_copy<<<nblk(n6, 256), 256, 0, st>>>(n6, L.t.p, 1.0 / std::sqrt(h[1]), L.x.p);
+        k_scale_copy<<<nblk(n6, 256), 256, 0, st>>>(n6, L.t.p + t0, 1.0 / std::sqrt(h[1]), L.x.p + t0);
     }
     *lam = 1.1 * est;
     return FS_OK;
@@ -885,15 +1083,17 @@ int ml_prepare(fs_context *c)
                         const int mode = probe_a[pi], mode2 = probe_b[pi];
                         k_lat_set_probe<<<nblk(g.n, 256), 256, 0, st>>>(g, c0, c1, c2, mode, mode2, L.xb.p);
                         if (l == 0) {
-                            rc = fine_prolong_chain(c, L.xb.p, c->d_z.p, false, 0);
+                            rc = fine_prolong_chain(c, L.xb.p, c->d_z.p, false, 0, true);
                             if (rc) return rc;
                             rc = fine_restrict_chain(c, nullptr, c->d_z.p, 0);
                             if (rc) return rc;
                         } else {
-                            lat_prolong_chain(c, l - 1, L.xb.p, m.lat[l - 1].x.p, false, 0);
-                            lat_restrict_chain(c, l - 1, nullptr, m.lat[l - 1].x.p, 0);
+                            rc = lat_prolong_chain(c, l - 1, L.xb.p, m.lat[l - 1].x.p, false, 0, true);
+                            if (rc) return rc;
+                            rc = lat_restrict_chain(c, l - 1, nullptr, m.lat[l - 1].x.p, 0);
+                            if (rc) return rc;
                         }
-                        k_lat_collect<<<nblk(n6, 256), 256, 0, st>>>(g, c0, c1, c2, mode, mode2, class_a, L.b.p, L.A.p);
+                        k_lat_collect<<<nblk(6 * (int64_t)(L.c1 - L.c0), 256), 256, 0, st>>>(g, L.c0, L.c1, c0, c1, c2, mode, mode2, class_a, L.b.p, L.A.p);
                     }
         FS_CUDA(c, cudaGetLastError());
         if (L.dense) {
@@ -908,7 +1108,7 @@ int ml_prepare(fs_context *c)
             L.omega = 0.0;
             L.lambda = 0.0;
         } else {
-            k_lat_extract_dinv<<<nblk(g.n, 64), 64, 0, st>>>(g, L.A.p, L.dinv.p);
+            k_lat_extract_dinv<<<nblk(L.c1 - L.c0, 64), 64, 0, st>>>(g, L.c0, L.c1, L.A.p, L.dinv.p);
             rc = lat_lambda(c, l, &lam);
             if (rc) return rc;
             L.lambda = lam;
@@ -934,7 +1134,9 @@ int ml_enqueue_apply(fs_context *c, bool init, double *red, int fin, int vec_gri
     k_f_smooth0<<<nblk(n6, 256), 256, 0, st>>>(n6, c->d_r.p + o6, c->d_minv.p, m.omega0, c->d_z.p + o6, st_of(c), chk);
     int rc = fine_restrict_chain(c, c->d_r.p, c->d_z.p, chk);
     if (rc) return rc;
-    const double *e = lat_cycle(c, 0, chk);
+    double *e = nullptr;
+    rc = lat_cycle(c, 0, chk, &e);
+    if (rc) return rc;
     rc = fine_prolong_chain(c, e, c->d_z.p, true, chk);
     if (rc) return rc;
     rc = spmv_once(c, c->d_z.p, c->d_q.p, chk != 0);

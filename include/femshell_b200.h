@@ -231,6 +231,10 @@ int fs_set_ml_options(fs_context *ctx, int64_t max_points, int dense_points, int
  * (room for 3*14); weights[0] = estimate of lambda_max(D^-1 A) on the mesh, weights[1+l] = on lattice l (room
  * for 15; 0 for the dense level); *setup_ms = device time of the last values set-up.  Arrays may be NULL. */
 int fs_get_ml_info(fs_context *ctx, int64_t *levels, int64_t *cells, double *weights, double *setup_ms);
+/* several ranks: number of leading lattice levels whose cells are distributed over the ranks in slabs (halo rows
+ * exchanged before each stencil application); the levels below are replicated.  0 with one rank, for lattices below
+ * FS_ML_DIST_MIN_CELLS cells (environment, default 32768), or when the node blocks do not follow the slab direction. */
+int fs_get_ml_dist_levels(fs_context *ctx, int64_t *n_dist);
 /* parity tests: copy of lattice level `level`: what = 0 the stencil (structure of arrays: entry (a,b) of the block
  * coupling cell p to its neighbour in slot s at [(6s+b)*6n + 6p + a], slot digits base 3 over the active axes,
  * offset = digit - 1), 1 the 36n pseudo-inverses of the diagonal blocks, 2 the dense inverse of the coarsest

@@ -18,6 +18,57 @@ import meshes
 from oracle import fso
 
 
+def distributed_lattice_case(rank, world, lr):
+    """multilevel preconditioner with DISTRIBUTED lattice levels (fs_mlpc.cu): a plate large enough for two lattice
+    levels above the dense one; slabs of cells per rank, halo slabs exchanged, boundary slabs of the restrictions
+    added at their owner.  Same iteration count as one GPU, same displacements as the oracle."""
+    os.environ["FS_ML_DIST_MIN_CELLS"] = "64"
+    for kind, nx, ny in (("t", 200, 151), ("q", 181, 230)):
+        m = fsb.meshgen(kind, nx, ny, 0, 0, 10, 10.0 * ny / nx, (1, 1, 1, 1), 300.0, 2, 1)
+        om = fso.Mesh(np.asarray(m["xyz"], float), m["etype"], m["eptr"], m["enodes"], m["bc"])
+        ref = fso.assemble(om, m["forces"], 0.3, 1e7, 0.5)
+        s1 = fsb.FemShell(device=lr)
+        s1.set_material(0.3, 1e7, 0.5)
+        s1.set_mesh(m["xyz"], m["etype"], m["eptr"], m["enodes"], m["bc"])
+        s1.set_nodal_loads(m["forces"])
+        s1.assemble()
+        i1 = s1.solve(rtol=1e-10, max_its=3000, pc=fsb.PC_MLRBM, warm_start=False)
+        u1 = s1.solution()
+        x1 = np.zeros(6 * ref.n_dofnodes); x1.reshape(-1, 6)[ref.dofnode] = u1
+        r1 = np.linalg.norm(ref.rhs - fso.spmv(ref, x1)) / np.linalg.norm(ref.rhs)
+        s1.close()
+        for comm in (fsb.COMM_PEER, fsb.COMM_NCCL):
+            ids = [fsb.FemShell.unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            s = fsb.FemShell(device=lr, rank=rank, world=world, nccl_id=ids[0], comm=comm)
+            s.set_material(0.3, 1e7, 0.5)
+            s.set_mesh(m["xyz"], m["etype"], m["eptr"], m["enodes"], m["bc"])
+            s.set_nodal_loads(m["forces"])
+            s.assemble()
+            info = s.solve(rtol=1e-10, max_its=3000, pc=fsb.PC_MLRBM, warm_start=False)
+            mi = s.ml_info()
+            assert mi["distributed_levels"] >= 1, mi
+            u = s.solution()
+            assert abs(info.iterations - i1.iterations) <= 2, (kind, comm, info.iterations, i1.iterations)
+            assert np.linalg.norm(u - u1) <= 1e-8 * np.linalg.norm(u1), (kind, comm, np.linalg.norm(u - u1) / np.linalg.norm(u1))
+            # a re-assembly with another material rebuilds the distributed stencils (set-up path a second time)
+            s.set_material(0.25, 2e7, 0.4)
+            s.assemble()
+            info2 = s.solve(rtol=1e-10, max_its=3000, pc=fsb.PC_MLRBM, warm_start=False)
+            ref2 = fso.assemble(om, m["forces"], 0.25, 2e7, 0.4)
+            x2 = np.zeros(6 * ref.n_dofnodes); x2.reshape(-1, 6)[ref.dofnode] = s.solution()
+            r2 = np.linalg.norm(ref2.rhs - fso.spmv(ref2, x2)) / np.linalg.norm(ref2.rhs)
+            assert r2 <= 100 * max(r1, 1e-10), (kind, comm, r2, r1)
+            s.close()
+            dist.barrier()
+            if rank == 0:
+                print("dist lattice ok %s world=%d comm=%d: %d distributed of %d levels %s, iterations %d (single %d), oracle residual %.2e (single %.2e), second material %d its %.2e"
+                      % (kind, world, comm, mi["distributed_levels"], mi["levels"], mi["cells"], info.iterations, i1.iterations,
+                         np.linalg.norm(ref.rhs - fso.spmv(ref, (lambda x: (x.reshape(-1, 6).__setitem__(ref.dofnode, u), x)[1])(np.zeros(6 * ref.n_dofnodes)))) / np.linalg.norm(ref.rhs),
+                         r1, info2.iterations, r2), flush=True)
+    del os.environ["FS_ML_DIST_MIN_CELLS"]
+
+
 def main():
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
@@ -92,6 +143,7 @@ def main():
         if rank == 0:
             print("dist ok %-6s world=%d iterations peer %d nccl %d (single %d) multilevel %d (single %d) err %.2e"
                   % (name, world, its[fsb.COMM_PEER], its[fsb.COMM_NCCL], i1.iterations, mi.iterations, m1.iterations, err), flush=True)
+    distributed_lattice_case(rank, world, lr)
     dist.destroy_process_group()
 
 

@@ -25,3 +25,4 @@ def test_distributed_assembly_and_solve(world):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("dist ok") == 3
+    assert r.stdout.count("dist lattice ok") == 4
