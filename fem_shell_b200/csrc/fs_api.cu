@@ -107,6 +107,9 @@ int fs_dist_init(fs_context *c, int rank, int world, const uint8_t id_bytes[128]
         memcpy(&id, id_bytes, 128);
         ncclComm_t comm;
         if (!nccl().ok) return fail(c, FS_ERR_COMM, "libnccl.so.2 could not be loaded");
+        // this library only sends halo slabs point to point and all-reduces a few doubles: NVLink SHARP brings nothing
+        // here, and its channel set-up costs about a second at the first collective.  The user's setting wins.
+        setenv("NCCL_NVLS_ENABLE", "0", 0);
         ncclResult_t r = nccl().CommInitRank(&comm, world, id, rank);
         if (r != ncclSuccess) return fail(c, FS_ERR_COMM, std::string("ncclCommInitRank: ") + nccl().GetErrorString(r));
         c->comm = (ncclComm *)comm;
@@ -259,26 +262,33 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
         const double inf = 1e300;
         std::vector<double> lo(3 * ht, inf), hi(3 * ht, -inf), hmax(3 * ht, 0.0);
         parallel_chunks(n_nodes, ht, [&](int t, int64_t i0, int64_t i1) {
+            double l[3] = {inf, inf, inf}, h[3] = {-inf, -inf, -inf};   // thread-local: the shared arrays are written once
             for (int64_t i = i0; i < i1; i++) {
                 if (c->dofnode[i] < 0) continue;
                 for (int d = 0; d < 3; d++) {
                     const double v = xyz[3 * i + d];
-                    lo[3 * t + d] = std::min(lo[3 * t + d], v);
-                    hi[3 * t + d] = std::max(hi[3 * t + d], v);
+                    l[d] = std::min(l[d], v);
+                    h[d] = std::max(h[d], v);
                 }
             }
+            for (int d = 0; d < 3; d++) { lo[3 * t + d] = l[d]; hi[3 * t + d] = h[d]; }
         });
         parallel_chunks(n_elem, ht, [&](int t, int64_t e0, int64_t e1) {
-            for (int64_t e = e0; e < e1; e++)
+            double hm[3] = {0.0, 0.0, 0.0};
+            for (int64_t e = e0; e < e1; e++) {
+                const int32_t *en = enodes + eptr[e];
+                const int nen = (int)(eptr[e + 1] - eptr[e]);
                 for (int d = 0; d < 3; d++) {
-                    double l = xyz[3 * (int64_t)enodes[eptr[e]] + d], h = l;
-                    for (int64_t k = eptr[e] + 1; k < eptr[e + 1]; k++) {
-                        const double v = xyz[3 * (int64_t)enodes[k] + d];
+                    double l = xyz[3 * (int64_t)en[0] + d], h = l;
+                    for (int k = 1; k < nen; k++) {
+                        const double v = xyz[3 * (int64_t)en[k] + d];
                         l = std::min(l, v);
                         h = std::max(h, v);
                     }
-                    hmax[3 * t + d] = std::max(hmax[3 * t + d], h - l);
+                    hm[d] = std::max(hm[d], h - l);
                 }
+            }
+            for (int d = 0; d < 3; d++) hmax[3 * t + d] = hm[d];
         });
         for (int d = 0; d < 3; d++) {
             c->bbox_lo[d] = inf; c->bbox_hi[d] = -inf; c->ml_h[d] = 0.0;

@@ -216,8 +216,8 @@ __device__ __forceinline__ void slice_emit(const double T[3][3], double Km[4][2]
 }
 
 // KINDS: 1 = only Quad-4 in the mesh, 2 = only Tri-3, 3 = both
-template <int KINDS>
-__global__ void __launch_bounds__(SLICE_MAX_THREADS, 2)
+template <int KINDS, int MINB>
+__global__ void __launch_bounds__(SLICE_MAX_THREADS, MINB)
 k_assemble_slice(int n_own, const int32_t *__restrict__ inc_ptr, const int4 *__restrict__ g_info, const int4 *__restrict__ g_nodes,
                  const int2 *__restrict__ meta, const double *__restrict__ xyz, const int32_t *__restrict__ sptr,
                  double *__restrict__ sell_vals, const double *__restrict__ qgp)
@@ -443,9 +443,11 @@ int slice_plan_build(fs_context *c)
     k_sl_table<<<n_slices, 128, 0, st>>>(n_own, c->d_sl_ptr.p, raw.p, aux.p, c->d_tri.p, c->d_quad.p, c->d_tri_pos.p, c->d_quad_pos.p,
                                          c->d_mask.p, c->d_sl_info.p, c->d_sl_nodes.p, c->d_sl_meta.p);
     FS_CUDA(c, cudaGetLastError());
-    FS_CUDA(c, cudaFuncSetAttribute(k_assemble_slice<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FS_CUDA(c, cudaFuncSetAttribute(k_assemble_slice<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FS_CUDA(c, cudaFuncSetAttribute(k_assemble_slice<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FS_CUDA(c, cudaFuncSetAttribute(k_assemble_slice<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FS_CUDA(c, cudaFuncSetAttribute(k_assemble_slice<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FS_CUDA(c, cudaFuncSetAttribute(k_assemble_slice<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FS_CUDA(c, cudaFuncSetAttribute(k_assemble_slice<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FS_CUDA(c, cudaFuncSetAttribute(k_assemble_slice<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t need = (size_t)32 * 14 * c->sell_slots;
     if (c->d_sell_vals.n < need) FS_CUDA(c, c->d_sell_vals.alloc(need));
     FS_CUDA(c, cudaStreamSynchronize(st));
@@ -460,7 +462,9 @@ int slice_plan_build(fs_context *c)
 int assemble_slice_enqueue(fs_context *c)
 {
     FS_CUDA(c, upload_elem_const_tu(make_elem_const(c->nu, c->E, c->thickness, c->quirks), c->stream));  // this file's c_el
-    auto kern = c->n_tri == 0 ? k_assemble_slice<1> : (c->n_quad == 0 ? k_assemble_slice<2> : k_assemble_slice<3>);
+    static const int minb = getenv("FS_SLICE_MINB") ? atoi(getenv("FS_SLICE_MINB")) : 2;   // lab switch: register cap 168 instead of 255
+    auto kern = c->n_tri == 0 ? (minb == 3 ? k_assemble_slice<1, 3> : k_assemble_slice<1, 2>)
+                              : (c->n_quad == 0 ? (minb == 3 ? k_assemble_slice<2, 3> : k_assemble_slice<2, 2>) : k_assemble_slice<3, 2>);
     kern<<<(unsigned)c->sell_slices, c->slice_threads, c->slice_smem, c->stream>>>((int)c->n_own, c->d_sl_ptr.p, c->d_sl_info.p, c->d_sl_nodes.p,
                                                                                  c->d_sl_meta.p, c->d_xyz.p, c->d_sell_sptr.p, c->d_sell_vals.p,
                                                                                  c->d_qgp.p);
