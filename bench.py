@@ -441,7 +441,10 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     its_done[0] = 0
+    if world > 1:
+        s.comm_stats(reset=True)
     total_ms = timed(step, args.steps)
+    waits = s.comm_stats(reset=True) if world > 1 else None
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
     value = n_dof * (its_done[0] / args.steps) / (ms_per_step * 1e-3)
@@ -641,7 +644,11 @@ def run_ours(args):
         "data": "synthetic",
         "config": config,
         "details": {"spmv_format": "%d of 36 entries per 6x6 block streamed (%s)" % (fmt["nz_per_block"], "zero-compacted sliced ELL" if fmt["nz_per_block"] < 36 else "parity block-CSR"),
-                    "matrix_gb_per_gpu": 1e-9 * fmt["matrix_bytes"], "comm": comm_used, "iterations_counted": its_done[0]},
+                    "matrix_gb_per_gpu": 1e-9 * fmt["matrix_bytes"], "comm": comm_used, "iterations_counted": its_done[0],
+                    "peer_wait_us_per_iteration_rank0": None if not waits or not waits["pq_waits"] else
+                    {"halo_stamp_in_spmv": waits["halo_wait_us"] / max(1, waits["halo_waits"]), "p_Ap_partials_in_update": waits["pq_wait_us"] / waits["pq_waits"],
+                     "r_z_partials_in_direction": waits["rz_wait_us"] / max(1, waits["rz_waits"]),
+                     "how": "clock64 around the spin loops, block 0 of each kernel (fs_peer.cuh)"}},
         "metrics": {"cg_dof_iterations_per_s": value, "elements_assembled_per_s": n_elem / (asm_ms * 1e-3),
                     "assemble_ms": asm_ms, "time_to_solution": tts, "time_to_solution_bounded": tts_small,
                     "time_to_first_solution": first,

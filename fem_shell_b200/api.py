@@ -29,7 +29,7 @@ FS_OK, FS_ERR_ARG, FS_ERR_CUDA, FS_ERR_STATE, FS_ERR_NOT_CONVERGED, FS_ERR_BREAK
 
 # every symbol include/femshell_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
-    "fs_create", "fs_destroy", "fs_last_error", "fs_get_stream", "fs_dist_unique_id", "fs_dist_init", "fs_set_comm_mode", "fs_get_comm_mode",
+    "fs_create", "fs_destroy", "fs_last_error", "fs_get_stream", "fs_dist_unique_id", "fs_dist_init", "fs_set_comm_mode", "fs_get_comm_mode", "fs_get_comm_stats",
     "fs_set_material", "fs_set_quirks", "fs_set_dof_order", "fs_set_assembly_mode", "fs_set_spmv_format", "fs_get_spmv_format", "fs_set_mesh",
     "fs_set_nodal_loads", "fs_set_interface_loads", "fs_build_rhs", "fs_assemble", "fs_solve",
     "fs_get_solution", "fs_get_solution_owned", "fs_recover_resultants", "fs_solve_host", "fs_interface_nodes", "fs_step", "fs_commit_step", "fs_get_sizes",
@@ -206,6 +206,12 @@ class FemShell:
         m = C.c_int()
         self._ck(self.lib.fs_get_comm_mode(self.ctx, C.byref(m)))
         return m.value
+
+    def comm_stats(self, reset=True):
+        """microseconds block 0 of the CG kernels waited for the other GPUs (peer path) and the number of waits"""
+        out = (C.c_double * 6)()
+        self._ck(self.lib.fs_get_comm_stats(self.ctx, out, C.c_int(1 if reset else 0)))
+        return {"halo_wait_us": out[0], "pq_wait_us": out[1], "rz_wait_us": out[2], "halo_waits": int(out[3]), "pq_waits": int(out[4]), "rz_waits": int(out[5])}
 
     @staticmethod
     def unique_id() -> bytes:

@@ -7,12 +7,14 @@
 //   solution layout    fs.cpp:140-141,163-169
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstring>
 #include <numeric>
 
 #include "fs_context.hpp"
 #include "fs_nccl.hpp"
 #include "fs_partition.hpp"
+#include "fs_peer.cuh"
 #include "fs_host_par.hpp"
 
 using namespace fs;
@@ -50,7 +52,7 @@ int fs_create(fs_context **out, int device)
     }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
-    if (c->d_state.alloc(1) != cudaSuccess || c->d_counter.alloc(1) != cudaSuccess || c->d_flag.alloc(1) != cudaSuccess) {
+    if (c->d_state.alloc(1) != cudaSuccess || c->d_counter.alloc(4) != cudaSuccess || c->d_flag.alloc(1) != cudaSuccess) {
         delete c;
         return FS_ERR_CUDA;
     }
@@ -131,6 +133,29 @@ int fs_get_comm_mode(fs_context *c, int *mode)
     FS_CHECK_CTX(c);
     if (!mode) return fail(c, FS_ERR_ARG, "null output");
     *mode = c->peer_ready ? FS_COMM_PEER : FS_COMM_NCCL;
+    return FS_OK;
+}
+
+int fs_get_comm_stats(fs_context *c, double out[6], int reset)
+{
+    FS_CHECK_CTX(c);
+    if (!out) return fail(c, FS_ERR_ARG, "null output");
+    for (int k = 0; k < 6; k++) out[k] = 0.0;
+    if (!c->peer_ready) return FS_OK;
+    FS_CUDA(c, cudaSetDevice(c->device));
+    FS_CUDA(c, cudaStreamSynchronize(c->stream));
+    PeerWin h;
+    FS_CUDA(c, cudaMemcpy(&h, c->d_pw.p, sizeof h, cudaMemcpyDeviceToHost));
+    int khz = 0;
+    FS_CUDA(c, cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device));   // clock64 ticks at the SM clock
+    for (int k = 0; k < 3; k++) {
+        out[k] = khz > 0 ? 1e3 * (double)h.wait_cycles[k] / (double)khz : 0.0;
+        out[3 + k] = (double)h.wait_count[k];
+    }
+    if (reset) {
+        const size_t off = offsetof(PeerWin, wait_cycles);
+        FS_CUDA(c, cudaMemset((char *)c->d_pw.p + off, 0, sizeof h.wait_cycles + sizeof h.wait_count));
+    }
     return FS_OK;
 }
 

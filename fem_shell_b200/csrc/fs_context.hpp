@@ -126,6 +126,8 @@ struct fs_context {
     void *peer_base[8] = {};                   // the other ranks' windows (cudaIpcOpenMemHandle)
     fs::DevBuf<fs::PeerWin> d_pw;
     fs::DevBuf<int32_t> d_push_peer, d_push_dst;
+    fs::DevBuf<uint8_t> d_is_send;             // n_own: node is on the send list (folded halo push, k_direction)
+    bool push_foldable = false;                // every send-list node goes to exactly one neighbour
 
     // material / switches
     double nu = 0.3, E = 1e7, thickness = 1.0;
@@ -194,6 +196,7 @@ struct fs_context {
     int64_t sell_slices = 0, sell_slots = 0;
     int sell_dmax_max = 0;                 // widest slice (blocks per row): sizes the shared memory of k_sell_fill_t
     fs::DevBuf<int32_t> d_sell_sptr, d_sell_adj;
+    fs::DevBuf<uint8_t> d_sell_halo;       // per slice: a row reads a halo block (processed after the halo wait, fs_sell.cuh)
     fs::DevBuf<double> d_sell_vals;
     fs::DevBuf<unsigned long long> d_sell_mask;
     int sell_blocks_per_sm = 2;

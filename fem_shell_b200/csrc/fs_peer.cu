@@ -141,6 +141,31 @@ int peer_window_setup(fs_context *c)
             }
         }
     }
+    std::vector<uint8_t> is_send((size_t)std::max<int64_t>(c->n_own, 1), 0);
+    c->push_foldable = true;
+    if (ok) {  // send_idx holds LOCAL node ids of owned nodes; a node listed for two neighbours cannot use the folded push
+        std::vector<int32_t> sidx(c->send_total);
+        if (c->send_total && cudaMemcpy(sidx.data(), c->d_send_idx.p, sizeof(int32_t) * c->send_total, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            cudaGetLastError();
+            ok = 0;
+            why = "reading the send list failed";
+        }
+        for (int64_t k = 0; ok && k < c->send_total; k++) {
+            const int64_t o = sidx[k] - c->own_lo;
+            if (o < 0 || o >= c->n_own) { ok = 0; why = "send list holds a node this rank does not own"; break; }
+            if (is_send[o]) c->push_foldable = false;
+            is_send[o] = 1;
+        }
+    }
+    if (ok) {
+        bool up = c->d_is_send.alloc(is_send.size()) == cudaSuccess &&
+                  cudaMemcpy(c->d_is_send.p, is_send.data(), is_send.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+        if (!up) {
+            cudaGetLastError();
+            ok = 0;
+            why = "device allocation of the peer tables failed";
+        }
+    }
     if (ok) {
         bool up = c->d_pw.alloc(1) == cudaSuccess && c->d_push_peer.alloc(push_peer.size()) == cudaSuccess &&
                   c->d_push_dst.alloc(push_dst.size()) == cudaSuccess &&

@@ -33,6 +33,9 @@ struct PeerWin {
     int n_recv, recv_rank[PEER_MAX];              // ranks this rank receives halo values from
     int n_send, send_rank[PEER_MAX];
     long long spin_limit;                         // clock64 ticks
+    // measurement (block 0 only): SM cycles spent waiting for the neighbours' halo stamps / the partial sums of the
+    // p.Ap reduction / of the r.z reduction, and how many waits were counted (fs_get_comm_stats)
+    unsigned long long wait_cycles[3], wait_count[3];
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
@@ -110,6 +113,7 @@ __device__ __forceinline__ bool peer_red_wait(PeerWin *pw, double (&out)[NV])
     if (threadIdx.x == 0) s_bad = 0;
     __syncthreads();
     const int world = pw->world;
+    const long long t_begin = (blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0;
     if (threadIdx.x < world * NV) {
         const int r = threadIdx.x / NV, k = threadIdx.x - NV * r;
         const unsigned long long stamp = *reinterpret_cast<volatile unsigned long long *>(&pw->seq_red);
@@ -135,6 +139,10 @@ __device__ __forceinline__ bool peer_red_wait(PeerWin *pw, double (&out)[NV])
         out[k] = acc;
     }
     const bool ok = s_bad == 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && NV <= 2) {   // NV = 1: p.Ap, NV = 2: r.z and the norm
+        pw->wait_cycles[NV] += (unsigned long long)(clock64() - t_begin);
+        pw->wait_count[NV] += 1;
+    }
     __syncthreads();
     return ok;
 }
@@ -144,11 +152,16 @@ __device__ __forceinline__ bool peer_halo_wait(PeerWin *pw)
 {
     __shared__ int s_hok;
     if (threadIdx.x == 0) {
+        const long long t_begin = clock64();
         const unsigned long long stamp = *reinterpret_cast<volatile unsigned long long *>(&pw->seq_halo);
         const unsigned long long *mb = pw->mbox[pw->rank];
         bool ok = true;
         for (int k = 0; k < pw->n_recv && ok; k++) ok = peer_spin(mb + MBOX_HALO + pw->recv_rank[k], stamp, pw->spin_limit);
         s_hok = ok ? 1 : 0;
+        if (blockIdx.x == 0) {
+            pw->wait_cycles[0] += (unsigned long long)(clock64() - t_begin);
+            pw->wait_count[0] += 1;
+        }
     }
     __syncthreads();
     return s_hok != 0;
@@ -158,6 +171,36 @@ __device__ __forceinline__ void peer_fail(CgState *s)
 {
     s->status = FS_ERR_COMM;
     s->done = 1;
+}
+
+// The push folded into the kernel that PRODUCES the vector (k_direction): thread t < 3 n_send forms its 16-byte
+// piece with `make` and stores it into the neighbour's halo segment; the last of the n_push_blocks leading blocks
+// stamps.  The stamp therefore leaves long before the consumer (the neighbour's next SpMV) starts.
+template <class Make>
+__device__ __forceinline__ void peer_push_inline(PeerWin *pw, int64_t n_send, const int32_t *__restrict__ idx,
+                                                 const int32_t *__restrict__ push_peer, const int32_t *__restrict__ push_dst,
+                                                 unsigned int *push_counter, int n_push_blocks, Make make)
+{
+    if ((int)blockIdx.x >= n_push_blocks) return;
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < 3 * n_send) {
+        const int64_t s = t / 3;
+        const int h = (int)(t - 3 * s);
+        const double2 v = make(idx[s], h);
+        double2 *dst = reinterpret_cast<double2 *>(pw->peer_p[push_peer[s]] + 6 * (size_t)push_dst[s]) + h;
+        *dst = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicInc(push_counter, (unsigned int)n_push_blocks - 1);
+        if (ticket == (unsigned int)n_push_blocks - 1) {
+            __threadfence_system();
+            const unsigned long long stamp = pw->seq_halo + 1;
+            for (int k = 0; k < pw->n_send; k++) st_release_sys(pw->mbox[pw->send_rank[k]] + MBOX_HALO + pw->rank, stamp);
+            pw->seq_halo = stamp;
+        }
+    }
 }
 
 // owned boundary values of p -> the neighbours' halo segments (remote stores), then one stamp per neighbour.

@@ -71,63 +71,94 @@ __device__ __forceinline__ double2 ld_x2(const double2 *p, bool halo)
     return __ldg(p);
 }
 
+// one slice: the lane's block row times x; returns the lane's contribution to p.q
+template <unsigned long long MASK, bool WITH_DOT, bool PEER, int UNROLL>
+__device__ __forceinline__ double sell_slice(int s, int lane, int n_own, int own_lo, const int32_t *__restrict__ sptr,
+                                             const int32_t *__restrict__ adj, const double *__restrict__ vals, const double *x,
+                                             double *__restrict__ y_own, const double *x_own)
+{
+    constexpr int NZ = sell_popcount(MASK);
+    const int s0 = sptr[s], dmax = sptr[s + 1] - s0;
+    const int32_t *aj = adj + 32 * (size_t)s0 + lane;
+    const double *v = vals + 32 * (size_t)NZ * s0 + lane;
+    double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll UNROLL
+    for (int slot = 0; slot < dmax; slot++) {
+        const int col = aj[32 * slot];
+        const bool halo = PEER && (unsigned)(col - own_lo) >= (unsigned)n_own;
+        const double2 *xp = reinterpret_cast<const double2 *>(x + 6 * (size_t)col);
+        double xv[6];
+#pragma unroll
+        for (int h = 0; h < 3; h++)
+            if (sell_uses_col(MASK, 2 * h) || sell_uses_col(MASK, 2 * h + 1)) {
+                const double2 t = ld_x2<PEER>(xp + h, halo);
+                xv[2 * h] = t.x;
+                xv[2 * h + 1] = t.y;
+            }
+        const double *vs = v + 32 * (size_t)NZ * slot;
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int b = 0; b < 6; b++)
+                if (MASK & sell_bit(a, b)) acc[a] += __ldcs(vs + 32 * sell_item(MASK, a, b)) * xv[b];
+    }
+    const int p = 32 * s + lane;
+    double dot = 0.0;
+    if (p < n_own) {
+        store6(y_own + 6 * (size_t)p, acc);
+        if (WITH_DOT) {
+            double pv[6];
+            load6(x_own + 6 * (size_t)p, pv);
+#pragma unroll
+            for (int a = 0; a < 6; a++) dot += acc[a] * pv[a];
+        }
+    }
+    return dot;
+}
+
+// PEER: slices whose rows read halo blocks (halo_flag) are processed LAST, after the wait for the neighbours' stamps:
+// the NVLink latency of the halo hides behind the interior slices (all but a few per cent of the strip).
 template <unsigned long long MASK, bool WITH_DOT, int BLOCK, int MINB, bool PEER = false, int UNROLL = 2>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_spmv_sell(int n_own, int own_lo, int n_slices, const int32_t *__restrict__ sptr, const int32_t *__restrict__ adj,
             const double *__restrict__ vals, const double *x, double *__restrict__ y_own,
             const double *x_own, double *partials, unsigned int *counter, CgState *state,
-            double *red, int fin_mode, PeerWin *pw)
+            double *red, int fin_mode, PeerWin *pw, const uint8_t *__restrict__ halo_flag)
 {
-    constexpr int NZ = sell_popcount(MASK);
     if (WITH_DOT ? state->done : (state && state->done)) return;  // without the dot product: checked only when a state is passed
-    if (PEER && !peer_halo_wait(pw)) {  // the neighbours' boundary values of x must have landed
-        if (blockIdx.x == 0 && threadIdx.x == 0) peer_fail(state);
-        return;
-    }
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
     const int nw = gridDim.x * (BLOCK / 32);
     double dot = 0.0;
-    for (int s = gw; s < n_slices; s += nw) {
-        const int s0 = sptr[s], dmax = sptr[s + 1] - s0;
-        const int32_t *aj = adj + 32 * (size_t)s0 + lane;
-        const double *v = vals + 32 * (size_t)NZ * s0 + lane;
-        double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll UNROLL
-        for (int slot = 0; slot < dmax; slot++) {
-            const int col = aj[32 * slot];
-            const bool halo = PEER && (unsigned)(col - own_lo) >= (unsigned)n_own;
-            const double2 *xp = reinterpret_cast<const double2 *>(x + 6 * (size_t)col);
-            double xv[6];
-#pragma unroll
-            for (int h = 0; h < 3; h++)
-                if (sell_uses_col(MASK, 2 * h) || sell_uses_col(MASK, 2 * h + 1)) {
-                    const double2 t = ld_x2<PEER>(xp + h, halo);
-                    xv[2 * h] = t.x;
-                    xv[2 * h + 1] = t.y;
-                }
-            const double *vs = v + 32 * (size_t)NZ * slot;
-#pragma unroll
-            for (int a = 0; a < 6; a++)
-#pragma unroll
-                for (int b = 0; b < 6; b++)
-                    if (MASK & sell_bit(a, b)) acc[a] += __ldcs(vs + 32 * sell_item(MASK, a, b)) * xv[b];
+    if (PEER) {
+        for (int s = gw; s < n_slices; s += nw)
+            if (!halo_flag[s]) dot += sell_slice<MASK, WITH_DOT, true, UNROLL>(s, lane, n_own, own_lo, sptr, adj, vals, x, y_own, x_own);
+        if (!peer_halo_wait(pw)) {  // the neighbours' boundary values of x must have landed
+            if (blockIdx.x == 0 && threadIdx.x == 0) peer_fail(state);
+            return;
         }
-        const int p = 32 * s + lane;
-        if (p < n_own) {
-            store6(y_own + 6 * (size_t)p, acc);
-            if (WITH_DOT) {
-                double pv[6];
-                load6(x_own + 6 * (size_t)p, pv);
-#pragma unroll
-                for (int a = 0; a < 6; a++) dot += acc[a] * pv[a];
-            }
-        }
+        for (int s = gw; s < n_slices; s += nw)
+            if (halo_flag[s]) dot += sell_slice<MASK, WITH_DOT, true, UNROLL>(s, lane, n_own, own_lo, sptr, adj, vals, x, y_own, x_own);
+    } else {
+        for (int s = gw; s < n_slices; s += nw) dot += sell_slice<MASK, WITH_DOT, false, UNROLL>(s, lane, n_own, own_lo, sptr, adj, vals, x, y_own, x_own);
     }
     if (WITH_DOT) {
         double vv[1] = {dot}, out[1];
         if (grid_reduce<1, BLOCK>(vv, partials, counter, out) && threadIdx.x == 0) finish_dot<1>(out, red, fin_mode, state, pw);
     }
+}
+
+// per slice: 1 when a row of the slice reads a block outside the owned range (a halo block)
+static __global__ void k_sell_halo_flags(int n_own, int own_lo, int n_slices, const int32_t *__restrict__ sptr,
+                                         const int32_t *__restrict__ adj, uint8_t *__restrict__ flag)
+{
+    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (s >= n_slices) return;
+    const int s0 = sptr[s], dmax = sptr[s + 1] - s0;
+    bool any = false;
+    for (int slot = 0; slot < dmax; slot++) any |= (unsigned)(adj[32 * (size_t)(s0 + slot) + lane] - own_lo) >= (unsigned)n_own;
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) flag[s] = any ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------

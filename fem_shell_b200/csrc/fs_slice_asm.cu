@@ -392,6 +392,8 @@ int sell_layout_build(fs_context *c)
     c->sell_dmax_max = widest;
     FS_CUDA(c, c->d_sell_adj.alloc((size_t)32 * total));
     k_sl_adj<<<nblk(n_slices, 8), 256, 0, st>>>(n_own, (int)c->own_lo, c->d_nptr.p, c->d_nadj.p, c->d_sell_sptr.p, c->d_sell_adj.p);
+    FS_CUDA(c, c->d_sell_halo.alloc((size_t)n_slices));
+    k_sell_halo_flags<<<nblk(n_slices, 8), 256, 0, st>>>(n_own, (int)c->own_lo, n_slices, c->d_sell_sptr.p, c->d_sell_adj.p, c->d_sell_halo.p);
     FS_CUDA(c, cudaGetLastError());
     c->sell_layout_ready = true;
     return FS_OK;

@@ -266,10 +266,21 @@ k_init_r(int64_t n_own, const double *__restrict__ b, const double *__restrict__
 }
 
 // p = z + beta p
+// PushArgs (peer mode with the halo push folded in): the send list of fs_peer.cuh; own_lo6 = offset of the owned
+// part inside the local vectors (z and p below point at the owned part)
+struct PushArgs {
+    int64_t n_send;
+    const int32_t *idx, *push_peer, *push_dst;
+    unsigned int *push_counter;
+    int n_push_blocks;
+    int64_t own_lo;
+    const uint8_t *is_send;   // per owned node: 1 = on the send list (its new value is written by the pushing thread)
+};
+
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 k_direction(int64_t n_own, const double *__restrict__ z, double *__restrict__ p, CgState *state, PeerWin *pw,
-            unsigned int *counter)
+            unsigned int *counter, const __grid_constant__ PushArgs push)
 {
     // after convergence x is final; p is not needed any more
     if (state->done) return;
@@ -280,11 +291,29 @@ k_direction(int64_t n_own, const double *__restrict__ z, double *__restrict__ p,
             return;
         }
         beta = t[0] / state->rz;
+        // the neighbours' halo values of the NEW p leave first: the pushing thread forms the value, stores it here
+        // and there; the bulk loop below skips those nodes (a node sent to two neighbours is formed twice, by
+        // threads that both read the old p only through their own entry -- so they write the old p's update once
+        // each to the same local address with the same value only if the node is listed once; is_send nodes listed
+        // twice are excluded from the folded push by the host)
+        if (push.n_push_blocks > 0)
+            peer_push_inline(pw, push.n_send, push.idx, push.push_peer, push.push_dst, push.push_counter, push.n_push_blocks,
+                             [&](int32_t node, int h) {
+                                 const size_t at = 3 * (size_t)(node - push.own_lo) + h;   // send-list nodes are owned nodes
+                                 const double2 zz = reinterpret_cast<const double2 *>(z)[at];
+                                 double2 *pl = reinterpret_cast<double2 *>(p) + at;
+                                 const double2 pp = *pl;
+                                 const double2 v = make_double2(zz.x + beta * pp.x, zz.y + beta * pp.y);
+                                 *pl = v;
+                                 return v;
+                             });
     } else beta = state->beta;
     const int64_t n2 = 3 * n_own;
     const double2 *z2 = reinterpret_cast<const double2 *>(z);
     double2 *p2 = reinterpret_cast<double2 *>(p);
+    const uint8_t *skip = (pw && push.n_push_blocks > 0) ? push.is_send : nullptr;
     for (int64_t i = blockIdx.x * (int64_t)BLOCK + threadIdx.x; i < n2; i += (int64_t)gridDim.x * BLOCK) {
+        if (skip && skip[i / 3]) continue;
         double2 zz = z2[i], pp = p2[i];
         pp.x = zz.x + beta * pp.x;
         pp.y = zz.y + beta * pp.y;
@@ -504,11 +533,11 @@ static void launch_sell(fs_context *c, const double *x, double *y_own, const dou
     if (WITH_DOT && pw)
         k_spmv_sell<MASK, WITH_DOT, SELL_BLOCK, SELL_MINB, WITH_DOT><<<grid, SELL_BLOCK, 0, c->stream>>>(
             (int)c->n_own, (int)c->own_lo, (int)c->sell_slices, c->d_sell_sptr.p, c->d_sell_adj.p, c->d_sell_vals.p, x, y_own, x_own,
-            c->d_partials.p, c->d_counter.p, state, red, fin_mode, pw);
+            c->d_partials.p, c->d_counter.p, state, red, fin_mode, pw, c->d_sell_halo.p);
     else
         k_spmv_sell<MASK, WITH_DOT, SELL_BLOCK, SELL_MINB, false><<<grid, SELL_BLOCK, 0, c->stream>>>(
             (int)c->n_own, (int)c->own_lo, (int)c->sell_slices, c->d_sell_sptr.p, c->d_sell_adj.p, c->d_sell_vals.p, x, y_own, x_own,
-            c->d_partials.p, c->d_counter.p, state, red, fin_mode, pw);
+            c->d_partials.p, c->d_counter.p, state, red, fin_mode, pw, nullptr);
 }
 
 int solver_prepare(fs_context *c, int pc)
@@ -647,9 +676,21 @@ static int enqueue_iteration(fs_context *c, double *red, int sg, int vg)
     const int fin = single ? FIN_INLINE : (peer ? FIN_PEER : FIN_RED);
     PeerWin *pw = peer ? c->d_pw.p : nullptr;
     const int64_t o6 = 6 * c->own_lo;
-    if (peer) {  // halo of p pushed into the neighbours' memory; their SpMV waits for the stamp
-        k_halo_push<<<std::max(1u, nblk(3 * c->send_total, 256)), 256, 0, c->stream>>>(
-            pw, c->send_total, c->d_send_idx.p, c->d_push_peer.p, c->d_push_dst.p, c->d_p.p, c->d_state.p, c->d_counter.p);
+    PushArgs push = {};
+    if (peer) {  // the halo of p was pushed by the kernel that formed it (k_direction below, k_halo_push before the first iteration)
+        push.n_send = c->send_total;
+        push.idx = c->d_send_idx.p;
+        push.push_peer = c->d_push_peer.p;
+        push.push_dst = c->d_push_dst.p;
+        push.push_counter = c->d_counter.p + 1;
+        push.n_push_blocks = (int)std::min<int64_t>(vg, std::max<int64_t>(1, nblk(3 * c->send_total, 256)));
+        push.own_lo = c->own_lo;
+        push.is_send = c->d_is_send.p;
+        // send list larger than the grid, or a node sent to two neighbours (two threads would update it): separate kernel
+        if (3 * c->send_total > (int64_t)push.n_push_blocks * 256 || !c->push_foldable) push.n_push_blocks = 0;
+        if (push.n_push_blocks == 0)
+            k_halo_push<<<std::max(1u, nblk(3 * c->send_total, 256)), 256, 0, c->stream>>>(
+                pw, c->send_total, c->d_send_idx.p, c->d_push_peer.p, c->d_push_dst.p, c->d_p.p, c->d_state.p, c->d_counter.p + 1);
     } else {
         int rc = halo_exchange(c, c->d_p.p);
         if (rc) return rc;
@@ -668,7 +709,7 @@ static int enqueue_iteration(fs_context *c, double *red, int sg, int vg)
             FS_NCCL(c, nccl().AllReduce(red + 4, red + 4, 2, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
             k_finalize<<<1, 1, 0, c->stream>>>(c->d_state.p, red + 4, 2);
         }
-        k_direction<256><<<vg, 256, 0, c->stream>>>(c->n_own, c->d_z.p + o6, c->d_p.p + o6, c->d_state.p, pw, c->d_counter.p);
+        k_direction<256><<<vg, 256, 0, c->stream>>>(c->n_own, c->d_z.p + o6, c->d_p.p + o6, c->d_state.p, pw, c->d_counter.p, PushArgs{});
         return FS_OK;
     }
     k_update<PC == 3 ? 1 : PC, NORM, 256><<<vg, 256, 0, c->stream>>>(c->n_own, c->d_x.p + o6, c->d_r.p + o6, c->d_p.p + o6,
@@ -678,7 +719,7 @@ static int enqueue_iteration(fs_context *c, double *red, int sg, int vg)
         FS_NCCL(c, nccl().AllReduce(red + 4, red + 4, 2, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
         k_finalize<<<1, 1, 0, c->stream>>>(c->d_state.p, red + 4, 2);
     }
-    k_direction<256><<<vg, 256, 0, c->stream>>>(c->n_own, c->d_z.p + o6, c->d_p.p + o6, c->d_state.p, pw, c->d_counter.p);
+    k_direction<256><<<vg, 256, 0, c->stream>>>(c->n_own, c->d_z.p + o6, c->d_p.p + o6, c->d_state.p, pw, c->d_counter.p, push);
     return FS_OK;
 }
 
@@ -700,7 +741,7 @@ static int run_pcg(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
     h.max_its = o->max_its;
     h.status = FS_ERR_NOT_CONVERGED;
     FS_CUDA(c, cudaMemcpyAsync(c->d_state.p, &h, sizeof h, cudaMemcpyHostToDevice, st));
-    FS_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned int), st));
+    FS_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, 4 * sizeof(unsigned int), st));
     if (!o->warm_start || !c->have_solution)
         FS_CUDA(c, cudaMemsetAsync(c->d_x.p, 0, sizeof(double) * 6 * c->n_local, st));
 
@@ -721,6 +762,10 @@ static int run_pcg(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
         k_finalize<<<1, 1, 0, st>>>(c->d_state.p, red + 8, 0);
     } else if (fin == FIN_PEER) {
         k_finalize_init_peer<<<1, 32, 0, st>>>(c->d_state.p, pw);
+        // halo of the first direction p = z; every later one is pushed by the k_direction that forms it
+        if (3 * c->send_total <= (int64_t)vg * 256 && c->push_foldable)
+            k_halo_push<<<std::max(1u, nblk(3 * c->send_total, 256)), 256, 0, st>>>(
+                pw, c->send_total, c->d_send_idx.p, c->d_push_peer.p, c->d_push_dst.p, c->d_p.p, c->d_state.p, c->d_counter.p + 1);
     }
     // The iteration is captured once into a CUDA graph of GRAPH_ITERS iterations and replayed; kernels
     // past convergence (or past max_its) see done != 0 and return, so replaying whole graphs is exact.

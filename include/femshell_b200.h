@@ -115,6 +115,11 @@ int fs_dist_init(fs_context *ctx, int rank, int world, const uint8_t nccl_unique
 int fs_set_comm_mode(fs_context *ctx, int mode);
 /* FS_COMM_NCCL or FS_COMM_PEER: what the iteration of the current mesh uses (single rank: FS_COMM_NCCL) */
 int fs_get_comm_mode(fs_context *ctx, int *mode);
+/* FS_COMM_PEER: what the CG kernels of this rank spent WAITING for the other GPUs since the last reset, measured
+ * by block 0 with clock64: out = {microseconds waiting for the neighbours' halo stamps (k_spmv_sell, after its
+ * interior slices), for the partial sums of p.Ap (k_update), of r.z and the norm (k_direction), and the number of
+ * waits of each kind (3 more entries)}.  reset != 0 zeroes the counters afterwards.  Zeros on the NCCL path. */
+int fs_get_comm_stats(fs_context *ctx, double out[6], int reset);
 
 /* NOTE multi-rank: fs_set_mesh and fs_destroy are collective (every rank of the communicator calls them). */
 

@@ -122,6 +122,8 @@ def main():
             assert abs(i1.iterations - info.iterations) <= max(3, i1.iterations // 50), (name, comm, i1.iterations, info.iterations)
             assert np.linalg.norm(u - u1) <= 1e-8 * np.linalg.norm(u1)
             its[comm] = info.iterations
+            sols_by_comm = locals().setdefault("sols_by_comm", {})
+            sols_by_comm[(name, comm)] = u
             ids, own = s.solution_owned()          # this rank's rows, no communication
             assert ids.size == oe - ob and np.array_equal(own, u[ids]), (name, comm, "owned rows")
             # stress resultants: elements of the cut rows read halo displacements; every rank gets all rows
@@ -141,6 +143,10 @@ def main():
             s.close()
             dist.barrier()
         assert abs(its[fsb.COMM_PEER] - its[fsb.COMM_NCCL]) <= max(3, i1.iterations // 50), (name, its)
+        # thousands of iterations through the peer windows (halo pushed by k_direction, consumed after the interior
+        # slices of the SpMV) and through NCCL give the same displacements: a stale halo read would not
+        du = np.linalg.norm(sols_by_comm[(name, fsb.COMM_PEER)] - sols_by_comm[(name, fsb.COMM_NCCL)]) / np.linalg.norm(uo)
+        assert du <= 1e-10, (name, du)
         if rank == 0:
             print("dist ok %-6s world=%d iterations peer %d nccl %d (single %d) multilevel %d (single %d) err %.2e"
                   % (name, world, its[fsb.COMM_PEER], its[fsb.COMM_NCCL], i1.iterations, mi.iterations, m1.iterations, err), flush=True)
