@@ -447,10 +447,12 @@ def run_ours(args):
     waits = s.comm_stats(reset=True) if world > 1 else None
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
-    value = n_dof * (its_done[0] / args.steps) / (ms_per_step * 1e-3)
+    its_timed = its_done[0]
+    value = n_dof * (its_timed / args.steps) / (ms_per_step * 1e-3)
 
     # ---- dominant kernel: SpMV, timed alone on the same stream right after the timed region ----
     spmv_ms = max_over_ranks(s.bench_spmv(50))
+    spmv_ms_on_p = max_over_ranks(s.last_spmv_ms_on_p)
     fmt = s.spmv_format()
     comm_used = "none (single rank)" if world == 1 else ("NVLink peer windows: halo push + mailbox all-reduce inside the CG kernels"
                                                           if s.comm_mode() == fsb.COMM_PEER else "NCCL send/recv + all-reduce per iteration")
@@ -644,7 +646,8 @@ def run_ours(args):
         "data": "synthetic",
         "config": config,
         "details": {"spmv_format": "%d of 36 entries per 6x6 block streamed (%s)" % (fmt["nz_per_block"], "zero-compacted sliced ELL" if fmt["nz_per_block"] < 36 else "parity block-CSR"),
-                    "matrix_gb_per_gpu": 1e-9 * fmt["matrix_bytes"], "comm": comm_used, "iterations_counted": its_done[0],
+                    "matrix_gb_per_gpu": 1e-9 * fmt["matrix_bytes"], "comm": comm_used, "iterations_counted": its_timed,
+                    "spmv_ms_reading_p": spmv_ms_on_p,
                     "peer_wait_us_per_iteration_rank0": None if not waits or not waits["pq_waits"] else
                     {"halo_stamp_in_spmv": waits["halo_wait_us"] / max(1, waits["halo_waits"]), "p_Ap_partials_in_update": waits["pq_wait_us"] / waits["pq_waits"],
                      "r_z_partials_in_direction": waits["rz_wait_us"] / max(1, waits["rz_waits"]),

@@ -428,4 +428,5 @@ class FemShell:
     def bench_spmv(self, reps=20) -> float:
         i = _Info()
         self._ck(self.lib.fs_bench_spmv(self.ctx, C.c_int(reps), C.byref(i)))
+        self.last_spmv_ms_on_p = i.solve_ms
         return i.spmv_ms

@@ -325,6 +325,49 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
             if (c->bbox_lo[d] > c->bbox_hi[d]) c->bbox_lo[d] = c->bbox_hi[d] = 0.0;
         }
     }
+    // ---- planar shell?  (fs_context.hpp: plane frame of the slice pass / compacted SpMV) ----
+    c->planar = c->plane_rot = false;
+    double plane_ref[3] = {0, 0, 0};
+    {
+        const double Qi[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        memcpy(c->plane_Q, Qi, sizeof Qi);
+        if (c->bbox_hi[2] == c->bbox_lo[2]) c->planar = true;   // the xy plane itself: nothing to rotate
+        else {
+            // frame of element 0 (fs.cpp:315-390: x^ along the first edge / the mid-side line, n the element normal)
+            const int32_t *en = enodes + eptr[0];
+            const int nen = (int)(eptr[1] - eptr[0]);
+            double A[3], U[3], V[3], n[3];
+            for (int d = 0; d < 3; d++) {
+                A[d] = xyz[3 * (int64_t)en[0] + d];
+                U[d] = xyz[3 * (int64_t)en[1] + d] - A[d];
+                V[d] = xyz[3 * (int64_t)en[nen - 1] + d] - A[d];
+            }
+            n[0] = U[1] * V[2] - U[2] * V[1]; n[1] = U[2] * V[0] - U[0] * V[2]; n[2] = U[0] * V[1] - U[1] * V[0];
+            const double lu = std::sqrt(U[0] * U[0] + U[1] * U[1] + U[2] * U[2]), ln = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+            double diam = 0.0;
+            for (int d = 0; d < 3; d++) diam += (c->bbox_hi[d] - c->bbox_lo[d]) * (c->bbox_hi[d] - c->bbox_lo[d]);
+            diam = std::sqrt(diam);
+            if (lu > 0.0 && ln > 0.0 && diam > 0.0) {
+                for (int d = 0; d < 3; d++) { U[d] /= lu; n[d] /= ln; }
+                const double W[3] = {n[1] * U[2] - n[2] * U[1], n[2] * U[0] - n[0] * U[2], n[0] * U[1] - n[1] * U[0]};   // y^ = n x x^
+                std::vector<double> worst(ht, 0.0);
+                parallel_chunks(n_nodes, ht, [&](int t, int64_t i0, int64_t i1) {
+                    double w = 0.0;
+                    for (int64_t i = i0; i < i1; i++) {
+                        if (c->dofnode[i] < 0) continue;
+                        w = std::max(w, std::fabs(n[0] * (xyz[3 * i] - A[0]) + n[1] * (xyz[3 * i + 1] - A[1]) + n[2] * (xyz[3 * i + 2] - A[2])));
+                    }
+                    worst[t] = w;
+                });
+                double w = 0.0;
+                for (int t = 0; t < ht; t++) w = std::max(w, worst[t]);
+                if (w <= 1e-12 * diam) {
+                    c->planar = c->plane_rot = true;
+                    for (int d = 0; d < 3; d++) { c->plane_Q[d] = U[d]; c->plane_Q[3 + d] = W[d]; c->plane_Q[6 + d] = n[d]; plane_ref[d] = A[d]; }
+                }
+            }
+        }
+    }
     tm.lap("bbox + element extents");
     // ---- Dirichlet bits (fs.cpp:90-120) and coupling interface (fsp.cpp:55-71) ----
     c->node_mask.assign(n_nodes, 0);
@@ -395,6 +438,22 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
     FS_CUDA(c, c->d_mask.alloc(c->n_local));
     FS_CUDA(c, cudaMemcpy(c->d_xyz.p, lxyz.data(), sizeof(double) * 3 * c->n_local, cudaMemcpyHostToDevice));
     FS_CUDA(c, cudaMemcpy(c->d_mask.p, lmask.data(), c->n_local, cudaMemcpyHostToDevice));
+    c->d_xyz_plane.release();
+    if (c->plane_rot) {   // coordinates in the plane frame; the normal component is the same constant for every node
+        const double *Q = c->plane_Q;
+        const double zc = Q[6] * plane_ref[0] + Q[7] * plane_ref[1] + Q[8] * plane_ref[2];
+        std::vector<double> pxyz(3 * c->n_local);
+        parallel_chunks(c->n_local, ht, [&](int, int64_t l0, int64_t l1) {
+            for (int64_t l = l0; l < l1; l++) {
+                const double *x = &lxyz[3 * l];
+                pxyz[3 * l + 0] = Q[0] * x[0] + Q[1] * x[1] + Q[2] * x[2];
+                pxyz[3 * l + 1] = Q[3] * x[0] + Q[4] * x[1] + Q[5] * x[2];
+                pxyz[3 * l + 2] = zc;
+            }
+        });
+        FS_CUDA(c, c->d_xyz_plane.alloc(3 * c->n_local));
+        FS_CUDA(c, cudaMemcpy(c->d_xyz_plane.p, pxyz.data(), sizeof(double) * 3 * c->n_local, cudaMemcpyHostToDevice));
+    }
 
     tm.lap("local xyz/mask + upload");
     // local connectivity in local node ids, triangles and quads apart, element order kept: count per chunk, then fill
@@ -813,7 +872,7 @@ int fs_bench_spmv(fs_context *c, int reps, fs_solve_info *info)
     FS_CHECK_CTX(c);
     if (!c->assembled || reps <= 0 || !info) return fail(c, FS_ERR_STATE, "not assembled / bad reps");
     FS_CUDA(c, cudaSetDevice(c->device));
-    return spmv_kernel_time(c, reps, &info->spmv_ms);
+    return spmv_kernel_time(c, reps, &info->spmv_ms, &info->solve_ms);   // solve_ms: the same kernel reading p (peer window)
 }
 
 int fs_set_ml_options(fs_context *c, int64_t max_points, int dense_points, int gamma)

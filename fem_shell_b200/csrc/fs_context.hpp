@@ -173,7 +173,13 @@ struct fs_context {
     fs::DevBuf<int32_t> d_sl_ptr;          // n_own+1: first incidence record of every owned row (slice s starts at row 32 s)
     fs::DevBuf<int4> d_sl_info, d_sl_nodes;  // packed thread table, one record per (element, node row) incidence
     fs::DevBuf<int2> d_sl_meta;            // per slice: {emit phases, element kinds present}
-    bool slice_ready = false;              // the plan exists for this mesh (planar in xy, rows fit)
+    // planar shells (any orientation): Q = rows x^, y^, n of a fixed frame whose third axis is the plane normal.  In that
+    // frame the shell lies in "its xy plane": the slice pass assembles Q~ K Q~^T (Q~ = diag(Q, Q) per node, 14 of 36
+    // entries per block) from node coordinates rotated into the frame, and the SpMV applies Q~ / Q~^T on the fly.
+    bool planar = false, plane_rot = false;   // plane_rot: Q is not the identity
+    double plane_Q[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    fs::DevBuf<double> d_xyz_plane;        // n_local * 3: Q x, third component snapped to the plane's constant (plane_rot only)
+    bool slice_ready = false;              // the plan exists for this mesh (planar, rows fit)
     size_t slice_smem = 0;
     int slice_threads = 128;
     bool parity_valid = false;             // d_vals holds the values of the current assembly (else: formed on demand)
@@ -302,7 +308,7 @@ int spmv_local(fs_context *c, const double *d_in, double *d_out, bool check_done
 int halo_exchange(fs_context *c, double *d_vec);
 int spmv_format_prepare(fs_context *c);
 int pc_apply_mlrbm_once(fs_context *c);
-int spmv_kernel_time(fs_context *c, int reps, float *ms_per_launch);
+int spmv_kernel_time(fs_context *c, int reps, float *ms_per_launch, float *ms_on_p = nullptr);
 
 // mlpc.cu
 int ml_prepare(fs_context *c);

@@ -71,11 +71,18 @@ __device__ __forceinline__ double2 ld_x2(const double2 *p, bool halo)
     return __ldg(p);
 }
 
-// one slice: the lane's block row times x; returns the lane's contribution to p.q
-template <unsigned long long MASK, bool WITH_DOT, bool PEER, int UNROLL>
+// plane frame of a planar shell in general position (fs_context.hpp): rows x^, y^, n
+struct PlaneQ {
+    double m[3][3];
+};
+
+// one slice: the lane's block row times x; returns the lane's contribution to p.q.  ROT: the stored blocks are
+// Q~ K Q~^T -- every x block is rotated into the plane frame (Q per translation / rotation triple) and the finished
+// row back out (Q^T): 18 + 18 FMAs on a kernel that waits for HBM.
+template <unsigned long long MASK, bool WITH_DOT, bool PEER, int UNROLL, bool ROT>
 __device__ __forceinline__ double sell_slice(int s, int lane, int n_own, int own_lo, const int32_t *__restrict__ sptr,
                                              const int32_t *__restrict__ adj, const double *__restrict__ vals, const double *x,
-                                             double *__restrict__ y_own, const double *x_own)
+                                             double *__restrict__ y_own, const double *x_own, const PlaneQ &q)
 {
     constexpr int NZ = sell_popcount(MASK);
     const int s0 = sptr[s], dmax = sptr[s + 1] - s0;
@@ -90,17 +97,37 @@ __device__ __forceinline__ double sell_slice(int s, int lane, int n_own, int own
         double xv[6];
 #pragma unroll
         for (int h = 0; h < 3; h++)
-            if (sell_uses_col(MASK, 2 * h) || sell_uses_col(MASK, 2 * h + 1)) {
+            if (ROT || sell_uses_col(MASK, 2 * h) || sell_uses_col(MASK, 2 * h + 1)) {
                 const double2 t = ld_x2<PEER>(xp + h, halo);
                 xv[2 * h] = t.x;
                 xv[2 * h + 1] = t.y;
             }
+        if (ROT) {
+            double r[6];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                r[i] = q.m[i][0] * xv[0] + q.m[i][1] * xv[1] + q.m[i][2] * xv[2];
+                r[3 + i] = q.m[i][0] * xv[3] + q.m[i][1] * xv[4] + q.m[i][2] * xv[5];
+            }
+#pragma unroll
+            for (int i = 0; i < 6; i++) xv[i] = r[i];
+        }
         const double *vs = v + 32 * (size_t)NZ * slot;
 #pragma unroll
         for (int a = 0; a < 6; a++)
 #pragma unroll
             for (int b = 0; b < 6; b++)
                 if (MASK & sell_bit(a, b)) acc[a] += __ldcs(vs + 32 * sell_item(MASK, a, b)) * xv[b];
+    }
+    if (ROT) {
+        double r[6];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            r[i] = q.m[0][i] * acc[0] + q.m[1][i] * acc[1] + q.m[2][i] * acc[2];
+            r[3 + i] = q.m[0][i] * acc[3] + q.m[1][i] * acc[4] + q.m[2][i] * acc[5];
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) acc[i] = r[i];
     }
     const int p = 32 * s + lane;
     double dot = 0.0;
@@ -118,12 +145,12 @@ __device__ __forceinline__ double sell_slice(int s, int lane, int n_own, int own
 
 // PEER: slices whose rows read halo blocks (halo_flag) are processed LAST, after the wait for the neighbours' stamps:
 // the NVLink latency of the halo hides behind the interior slices (all but a few per cent of the strip).
-template <unsigned long long MASK, bool WITH_DOT, int BLOCK, int MINB, bool PEER = false, int UNROLL = 2>
+template <unsigned long long MASK, bool WITH_DOT, int BLOCK, int MINB, bool PEER = false, bool ROT = false, int UNROLL = 2>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_spmv_sell(int n_own, int own_lo, int n_slices, const int32_t *__restrict__ sptr, const int32_t *__restrict__ adj,
             const double *__restrict__ vals, const double *x, double *__restrict__ y_own,
             const double *x_own, double *partials, unsigned int *counter, CgState *state,
-            double *red, int fin_mode, PeerWin *pw, const uint8_t *__restrict__ halo_flag)
+            double *red, int fin_mode, PeerWin *pw, const uint8_t *__restrict__ halo_flag, const __grid_constant__ PlaneQ q)
 {
     if (WITH_DOT ? state->done : (state && state->done)) return;  // without the dot product: checked only when a state is passed
     const int lane = threadIdx.x & 31;
@@ -132,15 +159,15 @@ k_spmv_sell(int n_own, int own_lo, int n_slices, const int32_t *__restrict__ spt
     double dot = 0.0;
     if (PEER) {
         for (int s = gw; s < n_slices; s += nw)
-            if (!halo_flag[s]) dot += sell_slice<MASK, WITH_DOT, true, UNROLL>(s, lane, n_own, own_lo, sptr, adj, vals, x, y_own, x_own);
+            if (!halo_flag[s]) dot += sell_slice<MASK, WITH_DOT, true, UNROLL, ROT>(s, lane, n_own, own_lo, sptr, adj, vals, x, y_own, x_own, q);
         if (!peer_halo_wait(pw)) {  // the neighbours' boundary values of x must have landed
             if (blockIdx.x == 0 && threadIdx.x == 0) peer_fail(state);
             return;
         }
         for (int s = gw; s < n_slices; s += nw)
-            if (halo_flag[s]) dot += sell_slice<MASK, WITH_DOT, true, UNROLL>(s, lane, n_own, own_lo, sptr, adj, vals, x, y_own, x_own);
+            if (halo_flag[s]) dot += sell_slice<MASK, WITH_DOT, true, UNROLL, ROT>(s, lane, n_own, own_lo, sptr, adj, vals, x, y_own, x_own, q);
     } else {
-        for (int s = gw; s < n_slices; s += nw) dot += sell_slice<MASK, WITH_DOT, false, UNROLL>(s, lane, n_own, own_lo, sptr, adj, vals, x, y_own, x_own);
+        for (int s = gw; s < n_slices; s += nw) dot += sell_slice<MASK, WITH_DOT, false, UNROLL, ROT>(s, lane, n_own, own_lo, sptr, adj, vals, x, y_own, x_own, q);
     }
     if (WITH_DOT) {
         double vv[1] = {dot}, out[1];

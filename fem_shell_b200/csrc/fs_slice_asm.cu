@@ -8,7 +8,13 @@
 // Why the 22 skipped entries of every 6x6 block are EXACT zeros here: all nodes share one z, so U = B - A has
 // U_z = 0 exactly, x^ = U/|U| keeps it, z^ = x^ x R has only a z component, y^ = z^ x x^ has none.  T
 // (fs.cpp:378-390) is a rotation about z whose other off-diagonal entries are exact zeros, and Tt^T K Tt
-// (fs.cpp:1094-1095) forms every membrane / bending coupling position from products with one of those zeros.  The mode is chosen from the bounding box (identical on every rank).
+// (fs.cpp:1094-1095) forms every membrane / bending coupling position from products with one of those zeros.  The
+// mode is chosen from the replicated mesh (identical on every rank).
+//
+// Planar shells in ANY orientation take the same path in their plane frame Q (fs_context.hpp): the kernel reads node
+// coordinates rotated into the frame (normal component snapped to one constant, so the argument above holds
+// verbatim) and therefore forms Q~ K Q~^T; the SpMV (fs_sell.cuh, ROT) rotates x blocks in and y blocks out.  The
+// Dirichlet sets of the reference fix whole translation / rotation triples (fs.cpp:90-120), which commute with Q~.
 //
 // Thread block = one slice of 32 consecutive owned block rows.  Thread = one (element, node row I) incidence of
 // those rows, described by a 32-byte record of the slice table that is built ON THE DEVICE at fs_set_mesh time
@@ -310,7 +316,7 @@ k_assemble_slice(int n_own, const int32_t *__restrict__ inc_ptr, const int4 *__r
 
 // diagonal (or inverse of the 6x6 diagonal block) straight from the sliced layout; entries outside the mask are zero
 __global__ void k_extract_minv_sell(int n_own, int own_lo, const int32_t *__restrict__ sptr, const int32_t *__restrict__ adj,
-                                    const double *__restrict__ vals, int pc, double *minv, int *bad)
+                                    const double *__restrict__ vals, int pc, double *minv, int *bad, const __grid_constant__ PlaneQ q, int rot)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_own) return;
@@ -327,6 +333,19 @@ __global__ void k_extract_minv_sell(int n_own, int own_lo, const int32_t *__rest
             M[a][b] = (SELL_MASK_XY & sell_bit(a, b)) ? v[32 * sell_item(SELL_MASK_XY, a, b)] : 0.0;
             M[a][6 + b] = (a == b) ? 1.0 : 0.0;
         }
+    if (rot) {  // the stored block is Q~ D Q~^T: back to global axes, D = Q~^T D' Q~ (3x3 pieces)
+        double D[6][6];
+        for (int bi = 0; bi < 2; bi++)
+            for (int bj = 0; bj < 2; bj++) {
+                double Tm[3][3];
+                for (int i = 0; i < 3; i++)
+                    for (int j = 0; j < 3; j++) Tm[i][j] = M[3 * bi + i][3 * bj] * q.m[0][j] + M[3 * bi + i][3 * bj + 1] * q.m[1][j] + M[3 * bi + i][3 * bj + 2] * q.m[2][j];
+                for (int i = 0; i < 3; i++)
+                    for (int j = 0; j < 3; j++) D[3 * bi + i][3 * bj + j] = q.m[0][i] * Tm[0][j] + q.m[1][i] * Tm[1][j] + q.m[2][i] * Tm[2][j];
+            }
+        for (int a = 0; a < 6; a++)
+            for (int b = 0; b < 6; b++) M[a][b] = D[a][b];
+    }
     if (pc == 1) {  // PCJacobi: a zero diagonal entry is replaced by 1 (PETSc's PCSetUp_Jacobi does the same)
         for (int a = 0; a < 6; a++) minv[6 * (size_t)p + a] = M[a][a] != 0.0 ? 1.0 / M[a][a] : 1.0;
         return;
@@ -403,8 +422,8 @@ int sell_layout_build(fs_context *c)
 int slice_plan_build(fs_context *c)
 {
     c->slice_ready = false;
-    // every node of the (replicated) mesh in one z plane -> exact xy block pattern (header comment)
-    if (!(c->bbox_hi[2] == c->bbox_lo[2]) || c->n_own <= 0) return FS_OK;
+    // every node of the (replicated) mesh in one plane -> exact xy block pattern in the plane frame (header comment)
+    if (!c->planar || c->n_own <= 0) return FS_OK;
     cudaStream_t st = c->stream;
     const int n_own = (int)c->n_own, own_lo = (int)c->own_lo;
     const int64_t nt = c->n_tri, nq = c->n_quad;
@@ -468,7 +487,7 @@ int assemble_slice_enqueue(fs_context *c)
     auto kern = c->n_tri == 0 ? (minb == 3 ? k_assemble_slice<1, 3> : k_assemble_slice<1, 2>)
                               : (c->n_quad == 0 ? (minb == 3 ? k_assemble_slice<2, 3> : k_assemble_slice<2, 2>) : k_assemble_slice<3, 2>);
     kern<<<(unsigned)c->sell_slices, c->slice_threads, c->slice_smem, c->stream>>>((int)c->n_own, c->d_sl_ptr.p, c->d_sl_info.p, c->d_sl_nodes.p,
-                                                                                 c->d_sl_meta.p, c->d_xyz.p, c->d_sell_sptr.p, c->d_sell_vals.p,
+                                                                                 c->d_sl_meta.p, c->plane_rot ? c->d_xyz_plane.p : c->d_xyz.p, c->d_sell_sptr.p, c->d_sell_vals.p,
                                                                                  c->d_qgp.p);
     FS_CUDA(c, cudaGetLastError());
     return FS_OK;
@@ -476,8 +495,11 @@ int assemble_slice_enqueue(fs_context *c)
 
 int extract_minv_sell(fs_context *c, int pc, int *d_bad)
 {
+    PlaneQ q;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) q.m[i][j] = c->plane_Q[3 * i + j];
     k_extract_minv_sell<<<nblk(c->n_own, 128), 128, 0, c->stream>>>((int)c->n_own, (int)c->own_lo, c->d_sell_sptr.p, c->d_sell_adj.p,
-                                                                    c->d_sell_vals.p, pc, c->d_minv.p, d_bad);
+                                                                    c->d_sell_vals.p, pc, c->d_minv.p, d_bad, q, c->plane_rot ? 1 : 0);
     FS_CUDA(c, cudaGetLastError());
     return FS_OK;
 }

@@ -421,7 +421,7 @@ int solver_query_occupancy(fs_context *c)
     c->spmv_blocks_per_sm = std::max(1, nb);
     FS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_update<1, 0, 256>, 256, 0));
     c->vec_blocks_per_sm = std::max(1, nb);
-    FS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_spmv_sell<SELL_MASK_XY, true, SELL_BLOCK, SELL_MINB, false>, SELL_BLOCK, 0));
+    FS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_spmv_sell<SELL_MASK_XY, true, SELL_BLOCK, SELL_MINB, false, false>, SELL_BLOCK, 0));
     c->sell_blocks_per_sm = std::max(1, nb);
     return FS_OK;
 }
@@ -524,20 +524,33 @@ int spmv_format_prepare(fs_context *c)
     return FS_OK;
 }
 
+template <unsigned long long MASK, bool WITH_DOT, bool PEER, bool ROT>
+static void launch_sell_k(fs_context *c, int grid, const double *x, double *y_own, const double *x_own, double *red, int fin_mode, PeerWin *pw,
+                          CgState *state)
+{
+    PlaneQ q;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) q.m[i][j] = c->plane_Q[3 * i + j];
+    k_spmv_sell<MASK, WITH_DOT, SELL_BLOCK, SELL_MINB, PEER, ROT><<<grid, SELL_BLOCK, 0, c->stream>>>(
+        (int)c->n_own, (int)c->own_lo, (int)c->sell_slices, c->d_sell_sptr.p, c->d_sell_adj.p, c->d_sell_vals.p, x, y_own, x_own,
+        c->d_partials.p, c->d_counter.p, state, red, fin_mode, pw, PEER ? c->d_sell_halo.p : nullptr, q);
+}
+
 template <unsigned long long MASK, bool WITH_DOT>
 static void launch_sell(fs_context *c, const double *x, double *y_own, const double *x_own, double *red, int fin_mode, PeerWin *pw,
                         CgState *state)
 {
     const int64_t want = (c->sell_slices + SELL_BLOCK / 32 - 1) / (SELL_BLOCK / 32);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->sm_count * c->sell_blocks_per_sm));
-    if (WITH_DOT && pw)
-        k_spmv_sell<MASK, WITH_DOT, SELL_BLOCK, SELL_MINB, WITH_DOT><<<grid, SELL_BLOCK, 0, c->stream>>>(
-            (int)c->n_own, (int)c->own_lo, (int)c->sell_slices, c->d_sell_sptr.p, c->d_sell_adj.p, c->d_sell_vals.p, x, y_own, x_own,
-            c->d_partials.p, c->d_counter.p, state, red, fin_mode, pw, c->d_sell_halo.p);
-    else
-        k_spmv_sell<MASK, WITH_DOT, SELL_BLOCK, SELL_MINB, false><<<grid, SELL_BLOCK, 0, c->stream>>>(
-            (int)c->n_own, (int)c->own_lo, (int)c->sell_slices, c->d_sell_sptr.p, c->d_sell_adj.p, c->d_sell_vals.p, x, y_own, x_own,
-            c->d_partials.p, c->d_counter.p, state, red, fin_mode, pw, nullptr);
+    // ROT (plane frame of a shell in general position) only exists for the xy pattern: the slice pass produces no other
+    const bool rot = c->plane_rot && MASK == SELL_MASK_XY && !c->parity_valid;
+    if (WITH_DOT && pw) {
+        if (rot) launch_sell_k<SELL_MASK_XY, WITH_DOT, WITH_DOT, true>(c, grid, x, y_own, x_own, red, fin_mode, pw, state);
+        else launch_sell_k<MASK, WITH_DOT, WITH_DOT, false>(c, grid, x, y_own, x_own, red, fin_mode, pw, state);
+    } else {
+        if (rot) launch_sell_k<SELL_MASK_XY, WITH_DOT, false, true>(c, grid, x, y_own, x_own, red, fin_mode, pw, state);
+        else launch_sell_k<MASK, WITH_DOT, false, false>(c, grid, x, y_own, x_own, red, fin_mode, pw, state);
+    }
 }
 
 int solver_prepare(fs_context *c, int pc)
@@ -829,7 +842,7 @@ int pc_apply_mlrbm_once(fs_context *c)
 }
 
 // the SpMV kernel alone (no halo exchange, no reduction), reps launches between two events
-int spmv_kernel_time(fs_context *c, int reps, float *ms_per_launch)
+int spmv_kernel_time(fs_context *c, int reps, float *ms_per_launch, float *ms_on_p)
 {
     int rc = spmv_format_prepare(c);
     if (rc) return rc;
@@ -845,6 +858,14 @@ int spmv_kernel_time(fs_context *c, int reps, float *ms_per_launch)
     float ms = 0.f;
     FS_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     *ms_per_launch = ms / reps;
+    if (ms_on_p) {  // same kernel reading the direction vector p (inside the cudaIpc window on the peer path)
+        FS_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+        for (int i = 0; i < reps; i++) launch_spmv<false>(c, c->d_p.p, c->d_q.p + o6, nullptr, nullptr, FIN_RED, nullptr, false);
+        FS_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+        FS_CUDA(c, cudaStreamSynchronize(c->stream));
+        FS_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        *ms_on_p = ms / reps;
+    }
     return FS_OK;
 }
 
