@@ -466,7 +466,7 @@ def run_ours(args):
     kflop_el, bytes_el = 15.7e3, 2630.0          # Quad-4: flops and minimum HBM bytes per element
     asm_rate = n_elem / world / (asm_ms * 1e-3)  # per GPU
     assembly_roofline = {
-        "kernel": "k_assemble_gather" if args.asm == "gather" else "k_assemble_colored",
+        "kernel": s.assembly_path(),
         "fp64": {"achieved": asm_rate * kflop_el / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": asm_rate * kflop_el / 1e12 / fp64_peak,
                  "peak_source": "measured here (fs_bench_fp64_peak, dependent-FMA chains)"},
         "hbm": {"achieved": asm_rate * bytes_el / 1e9, "peak": peak, "unit": "GB/s", "frac": asm_rate * bytes_el / 1e9 / peak},
@@ -651,6 +651,8 @@ def run_ours(args):
                     "peer_wait_us_per_iteration_rank0": None if not waits or not waits["pq_waits"] else
                     {"halo_stamp_in_spmv": waits["halo_wait_us"] / max(1, waits["halo_waits"]), "p_Ap_partials_in_update": waits["pq_wait_us"] / waits["pq_waits"],
                      "r_z_partials_in_direction": waits["rz_wait_us"] / max(1, waits["rz_waits"]),
+                     "kernel_wall_us": {"k_spmv_sell": waits["spmv_us"] / waits["pq_waits"], "k_update": waits["update_us"] / waits["pq_waits"],
+                                        "k_direction": waits["direction_us"] / max(1, waits["rz_waits"]), "iteration": 1e3 * ms_per_step / iters},
                      "how": "clock64 around the spin loops, block 0 of each kernel (fs_peer.cuh)"}},
         "metrics": {"cg_dof_iterations_per_s": value, "elements_assembled_per_s": n_elem / (asm_ms * 1e-3),
                     "assemble_ms": asm_ms, "time_to_solution": tts, "time_to_solution_bounded": tts_small,

@@ -31,7 +31,7 @@ FS_OK, FS_ERR_ARG, FS_ERR_CUDA, FS_ERR_STATE, FS_ERR_NOT_CONVERGED, FS_ERR_BREAK
 EXPORTED_SYMBOLS = [
     "fs_create", "fs_destroy", "fs_last_error", "fs_get_stream", "fs_dist_unique_id", "fs_dist_init", "fs_set_comm_mode", "fs_get_comm_mode", "fs_get_comm_stats",
     "fs_set_material", "fs_set_quirks", "fs_set_dof_order", "fs_set_assembly_mode", "fs_set_spmv_format", "fs_get_spmv_format", "fs_set_mesh",
-    "fs_set_nodal_loads", "fs_set_interface_loads", "fs_build_rhs", "fs_assemble", "fs_solve",
+    "fs_set_nodal_loads", "fs_set_interface_loads", "fs_build_rhs", "fs_assemble", "fs_get_assembly_path", "fs_solve",
     "fs_get_solution", "fs_get_solution_owned", "fs_recover_resultants", "fs_solve_host", "fs_interface_nodes", "fs_step", "fs_commit_step", "fs_get_sizes",
     "fs_export_dof_order", "fs_export_csr", "fs_export_rhs", "fs_debug_element_matrices", "fs_spmv_host",
     "fs_bench_spmv", "fs_bench_fp64_peak", "fs_bench_contraction", "fs_set_ml_options", "fs_get_ml_info", "fs_get_ml_dist_levels", "fs_debug_ml_level", "fs_apply_mlrbm_host", "fs_partition_plan", "fs_gather_plan", "fs_meshgen", "fs_read_xda", "fs_read_forces", "fs_write_xda",
@@ -209,9 +209,10 @@ class FemShell:
 
     def comm_stats(self, reset=True):
         """microseconds block 0 of the CG kernels waited for the other GPUs (peer path) and the number of waits"""
-        out = (C.c_double * 6)()
+        out = (C.c_double * 9)()
         self._ck(self.lib.fs_get_comm_stats(self.ctx, out, C.c_int(1 if reset else 0)))
-        return {"halo_wait_us": out[0], "pq_wait_us": out[1], "rz_wait_us": out[2], "halo_waits": int(out[3]), "pq_waits": int(out[4]), "rz_waits": int(out[5])}
+        return {"halo_wait_us": out[0], "pq_wait_us": out[1], "rz_wait_us": out[2], "halo_waits": int(out[3]), "pq_waits": int(out[4]), "rz_waits": int(out[5]),
+                "spmv_us": out[6], "update_us": out[7], "direction_us": out[8]}
 
     @staticmethod
     def unique_id() -> bytes:
@@ -289,6 +290,11 @@ class FemShell:
         ms = C.c_float()
         self._ck(self.lib.fs_assemble(self.ctx, C.byref(ms)))
         return ms.value
+
+    def assembly_path(self) -> str:
+        p = C.c_int()
+        self._ck(self.lib.fs_get_assembly_path(self.ctx, C.byref(p)))
+        return ("k_assemble_colored", "k_assemble_gather", "k_assemble_slice")[p.value]
 
     @staticmethod
     def _opts(rtol, max_its, pc, norm_type, warm_start, check_every):

@@ -136,11 +136,11 @@ int fs_get_comm_mode(fs_context *c, int *mode)
     return FS_OK;
 }
 
-int fs_get_comm_stats(fs_context *c, double out[6], int reset)
+int fs_get_comm_stats(fs_context *c, double out[9], int reset)
 {
     FS_CHECK_CTX(c);
     if (!out) return fail(c, FS_ERR_ARG, "null output");
-    for (int k = 0; k < 6; k++) out[k] = 0.0;
+    for (int k = 0; k < 9; k++) out[k] = 0.0;
     if (!c->peer_ready) return FS_OK;
     FS_CUDA(c, cudaSetDevice(c->device));
     FS_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -151,10 +151,11 @@ int fs_get_comm_stats(fs_context *c, double out[6], int reset)
     for (int k = 0; k < 3; k++) {
         out[k] = khz > 0 ? 1e3 * (double)h.wait_cycles[k] / (double)khz : 0.0;
         out[3 + k] = (double)h.wait_count[k];
+        out[6 + k] = 1e-3 * (double)h.kern_ns[k];
     }
     if (reset) {
         const size_t off = offsetof(PeerWin, wait_cycles);
-        FS_CUDA(c, cudaMemset((char *)c->d_pw.p + off, 0, sizeof h.wait_cycles + sizeof h.wait_count));
+        FS_CUDA(c, cudaMemset((char *)c->d_pw.p + off, 0, sizeof h.wait_cycles + sizeof h.wait_count + sizeof h.kern_ns + sizeof h.kern_t0));
     }
     return FS_OK;
 }
@@ -600,6 +601,14 @@ int fs_assemble(fs_context *c, float *ms)
     if (!c->material_set) return fail(c, FS_ERR_STATE, "fs_assemble before fs_set_material");
     FS_CUDA(c, cudaSetDevice(c->device));
     return assemble_values(c, ms);
+}
+
+int fs_get_assembly_path(fs_context *c, int *path)
+{
+    FS_CHECK_CTX(c);
+    if (!path || !c->assembled) return fail(c, FS_ERR_STATE, "not assembled / null output");
+    *path = !c->parity_valid ? 2 : ((c->asm_mode == FS_ASM_GATHER && c->gather_ready) ? 1 : 0);
+    return FS_OK;
 }
 
 static void default_opts(fs_solve_opts &o)

@@ -24,6 +24,8 @@ constexpr int MBOX_RED = 0;                       // [2 parities][PEER_MAX ranks
 constexpr int MBOX_HALO = 2 * PEER_MAX * 8;       // [PEER_MAX] halo stamps
 constexpr int MBOX_WORDS = 256;                   // 2 KB header in front of p
 
+struct PeerWin;
+__device__ __forceinline__ unsigned long long global_ns();
 struct PeerWin {
     int rank, world;
     unsigned long long seq_red;                   // stamp of this rank's latest reduction contribution
@@ -36,7 +38,26 @@ struct PeerWin {
     // measurement (block 0 only): SM cycles spent waiting for the neighbours' halo stamps / the partial sums of the
     // p.Ap reduction / of the r.z reduction, and how many waits were counted (fs_get_comm_stats)
     unsigned long long wait_cycles[3], wait_count[3];
+    // wall-clock (globaltimer, ns) from block 0's entry to the end of the last block, summed per kernel:
+    // 0 k_spmv_sell, 1 k_update, 2 k_direction; kern_t0 = entry time of the running kernel
+    unsigned long long kern_ns[3], kern_t0[3];
 };
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void peer_kern_begin(PeerWin *pw, int k)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long *>(&pw->kern_t0[k]) = global_ns();
+}
+// called by ONE thread of the block that finishes last
+__device__ __forceinline__ void peer_kern_end(PeerWin *pw, int k)
+{
+    pw->kern_ns[k] += global_ns() - *reinterpret_cast<volatile unsigned long long *>(&pw->kern_t0[k]);
+}
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
 {

@@ -158,6 +158,7 @@ k_spmv_sell(int n_own, int own_lo, int n_slices, const int32_t *__restrict__ spt
     const int nw = gridDim.x * (BLOCK / 32);
     double dot = 0.0;
     if (PEER) {
+        peer_kern_begin(pw, 0);
         for (int s = gw; s < n_slices; s += nw)
             if (!halo_flag[s]) dot += sell_slice<MASK, WITH_DOT, true, UNROLL, ROT>(s, lane, n_own, own_lo, sptr, adj, vals, x, y_own, x_own, q);
         if (!peer_halo_wait(pw)) {  // the neighbours' boundary values of x must have landed
@@ -171,7 +172,10 @@ k_spmv_sell(int n_own, int own_lo, int n_slices, const int32_t *__restrict__ spt
     }
     if (WITH_DOT) {
         double vv[1] = {dot}, out[1];
-        if (grid_reduce<1, BLOCK>(vv, partials, counter, out) && threadIdx.x == 0) finish_dot<1>(out, red, fin_mode, state, pw);
+        if (grid_reduce<1, BLOCK>(vv, partials, counter, out) && threadIdx.x == 0) {
+            finish_dot<1>(out, red, fin_mode, state, pw);
+            if (PEER) peer_kern_end(pw, 0);
+        }
     }
 }
 

@@ -173,6 +173,7 @@ k_update(int64_t n_own, double *__restrict__ x, double *__restrict__ r, const do
     if (state->done) return;
     double alpha;
     if (pw) {  // p.Ap arrives as one partial per rank in the mailbox: finish the sum here (fs_peer.cuh)
+        peer_kern_begin(pw, 1);
         double t[1];
         const bool ok = peer_red_wait<1>(pw, t);
         const bool spd = t[0] > 0.0;
@@ -206,7 +207,10 @@ k_update(int64_t n_own, double *__restrict__ x, double *__restrict__ r, const do
         }
     }
     double v[2] = {rz, nn}, out[2];
-    if (grid_reduce<2, BLOCK>(v, partials, counter, out) && threadIdx.x == 0) finish_dot<2>(out, red, fin_mode, state, pw);
+    if (grid_reduce<2, BLOCK>(v, partials, counter, out) && threadIdx.x == 0) {
+        finish_dot<2>(out, red, fin_mode, state, pw);
+        if (pw) peer_kern_end(pw, 1);
+    }
 }
 
 // x += alpha p ; r -= alpha q ; partial ||r||^2 -- first half of k_update for the multilevel preconditioner
@@ -286,6 +290,7 @@ k_direction(int64_t n_own, const double *__restrict__ z, double *__restrict__ p,
     if (state->done) return;
     double beta, t[2] = {0.0, 0.0};
     if (pw) {  // r.z and the norm arrive as per-rank partials: finish the sums, beta from the OLD r.z
+        peer_kern_begin(pw, 2);
         if (!peer_red_wait<2>(pw, t)) {
             if (blockIdx.x == 0 && threadIdx.x == 0) peer_fail(state);
             return;
@@ -321,7 +326,10 @@ k_direction(int64_t n_own, const double *__restrict__ z, double *__restrict__ p,
     }
     if (pw) {  // the block that finishes last advances the recurrence (every block has read the old state)
         __syncthreads();
-        if (threadIdx.x == 0 && atomicInc(counter, gridDim.x - 1) == gridDim.x - 1) finalize_update(state, t[0], t[1]);
+        if (threadIdx.x == 0 && atomicInc(counter, gridDim.x - 1) == gridDim.x - 1) {
+            finalize_update(state, t[0], t[1]);
+            peer_kern_end(pw, 2);
+        }
     }
 }
 

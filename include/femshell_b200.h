@@ -118,8 +118,10 @@ int fs_get_comm_mode(fs_context *ctx, int *mode);
 /* FS_COMM_PEER: what the CG kernels of this rank spent WAITING for the other GPUs since the last reset, measured
  * by block 0 with clock64: out = {microseconds waiting for the neighbours' halo stamps (k_spmv_sell, after its
  * interior slices), for the partial sums of p.Ap (k_update), of r.z and the norm (k_direction), and the number of
- * waits of each kind (3 more entries)}.  reset != 0 zeroes the counters afterwards.  Zeros on the NCCL path. */
-int fs_get_comm_stats(fs_context *ctx, double out[6], int reset);
+ * waits of each kind (3 more entries), and the wall-clock microseconds (globaltimer) from the entry of block 0 to the
+ * end of the last block summed over the launches of k_spmv_sell, k_update, k_direction (3 more entries)}.
+ * reset != 0 zeroes the counters afterwards.  Zeros on the NCCL path. */
+int fs_get_comm_stats(fs_context *ctx, double out[9], int reset);
 
 /* NOTE multi-rank: fs_set_mesh and fs_destroy are collective (every rank of the communicator calls them). */
 
@@ -157,6 +159,9 @@ int fs_build_rhs(fs_context *ctx, double scale);
  * the block-CSR matrix, rhs.  The sparsity pattern and the element colouring are built on the
  * first call and kept.  *ms (optional) receives the device time of the values pass. */
 int fs_assemble(fs_context *ctx, float *ms);
+/* which kernel the last fs_assemble ran: 0 k_assemble_colored, 1 k_assemble_gather (parity block-CSR), 2 k_assemble_slice
+ * (planar shells: straight into the compacted SpMV format, parity CSR on demand) */
+int fs_get_assembly_path(fs_context *ctx, int *path);
 /* replaces LinearImplicitSystem::solve -> KSPSolve (fs.cpp:138) for an already assembled system.
  * opts == NULL: the reference's defaults as far as they apply to CG -- rtol 1e-12, 5000 iterations, Jacobi,
  * PRECONDITIONED norm (KSPCG's default), warm start.  A solve that ends in FS_ERR_BREAKDOWN / FS_ERR_COMM leaves no

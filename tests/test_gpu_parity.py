@@ -470,7 +470,11 @@ def test_slice_pass_assembles_the_compacted_format_directly(fso, fsb, case, dof)
     rowptr, colidx, vals = s.export_csr()
     rr, rc, rv = ref.csr()
     assert np.array_equal(rowptr, rr) and np.array_equal(colidx, rc)
-    assert block_scaled_error(vals, rv, ref.nptr) <= 1e-12
+    # sliver triangles of the Delaunay patch: a coupling block is a difference of terms as large as the diagonal
+    # blocks, so its rounding noise scales with the element, not with the (cancelled) block (see
+    # test_element_matrices_general_elements)
+    tol = 1e-11 if case == "delaunay_mixed" else 1e-12
+    assert block_scaled_error(vals, rv, ref.nptr) <= tol
     assert s.spmv_format()["nz_per_block"] == 14          # forming it did not change what the iteration streams
     # re-assembly with another material refreshes the compacted values (and the diagonal taken from them)
     s.set_material(0.2, 2 * E, 0.8 * t)
@@ -478,7 +482,7 @@ def test_slice_pass_assembles_the_compacted_format_directly(fso, fsb, case, dof)
     ref2 = fso.assemble(om, m["forces"], 0.2, 2 * E, 0.8 * t, dof_mode=dof)
     y2, y2r = s.spmv(x), fso.spmv(ref2, x)
     assert np.abs(y2 - y2r).max() <= 1e-13 * np.abs(y2r).max()
-    assert block_scaled_error(s.export_csr(with_cols=False)[2], ref2.vals, ref2.nptr) <= 1e-12
+    assert block_scaled_error(s.export_csr(with_cols=False)[2], ref2.vals, ref2.nptr) <= tol
 
 
 def test_slice_pass_is_bitwise_reproducible_and_matches_the_copy_from_parity(fsb):
