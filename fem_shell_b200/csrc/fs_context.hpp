@@ -202,7 +202,8 @@ struct fs_context {
     int64_t sell_slices = 0, sell_slots = 0;
     int sell_dmax_max = 0;                 // widest slice (blocks per row): sizes the shared memory of k_sell_fill_t
     fs::DevBuf<int32_t> d_sell_sptr, d_sell_adj;
-    fs::DevBuf<uint8_t> d_sell_halo;       // per slice: a row reads a halo block (processed after the halo wait, fs_sell.cuh)
+    fs::DevBuf<int32_t> d_sell_order;      // several ranks: interior slices first, then those reading halo blocks (fs_sell.cuh)
+    int sell_n_interior = 0;
     fs::DevBuf<double> d_sell_vals;
     fs::DevBuf<unsigned long long> d_sell_mask;
     int sell_blocks_per_sm = 2;

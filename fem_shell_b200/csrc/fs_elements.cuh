@@ -195,6 +195,28 @@ __device__ __forceinline__ void membrane_accum(double f, double pxI, double pyI,
     m[1][1] += f * (pyI * d11 * pyj + pxI * d33 * pxj);
 }
 
+// the same sums with the factors that do not depend on j hoisted: 8 multiplications per Gauss point, then
+// 8 FMAs per column block (membrane_accum: 20 FP64 instructions per block)
+struct MembraneRow {
+    double a, b, c, d, e, f;
+};
+__device__ __forceinline__ MembraneRow membrane_row_coeffs(double f, double pxI, double pyI)
+{
+    const double fx = f * pxI, fy = f * pyI;
+    MembraneRow r;
+    r.a = fx * c_el.dm11; r.b = fy * c_el.dm33; r.c = fx * c_el.dm12;
+    r.d = fy * c_el.dm12; r.e = fx * c_el.dm33; r.f = fy * c_el.dm11;
+    return r;
+}
+__device__ __forceinline__ void membrane_accum_row(const MembraneRow &r, double pxj, double pyj, double m[2][2])
+{
+    // FMA chains INTO the accumulator (a sum in parentheses added afterwards costs an extra DADD per entry)
+    m[0][0] = fma(r.b, pyj, fma(r.a, pxj, m[0][0]));
+    m[0][1] = fma(r.b, pxj, fma(r.c, pyj, m[0][1]));
+    m[1][0] = fma(r.e, pyj, fma(r.d, pxj, m[1][0]));
+    m[1][1] = fma(r.e, pxj, fma(r.f, pyj, m[1][1]));
+}
+
 // CST, fs.cpp:445-468
 template <int I>
 __device__ __forceinline__ void tri_membrane_row(const TriGeom &g, double Km[3][2][2])
@@ -308,9 +330,9 @@ __device__ __forceinline__ void quad_membrane_row_rt(const QuadGeom &g, int I, d
             py[k] = b12 * dr[k] + b13 * ds[k];
         }
         const double f = det * c_el.thickness;
-        const double pxI = pick4(I, px), pyI = pick4(I, py);
+        const MembraneRow mr = membrane_row_coeffs(f, pick4(I, px), pick4(I, py));
 #pragma unroll
-        for (int j = 0; j < 4; j++) membrane_accum(f, pxI, pyI, px[j], py[j], Km[j]);
+        for (int j = 0; j < 4; j++) membrane_accum_row(mr, px[j], py[j], Km[j]);
     }
 }
 
@@ -513,9 +535,9 @@ __device__ __forceinline__ void tri_plate_row_rt(const TriGeom &g, int I, double
             const double m0 = sel_f64(I == 0, M[0][0][c], sel_f64(I == 1, M[1][0][c], M[2][0][c]));
             const double m1 = sel_f64(I == 0, M[0][1][c], sel_f64(I == 1, M[1][1][c], M[2][1][c]));
             const double m2 = sel_f64(I == 0, M[0][2][c], sel_f64(I == 1, M[1][2][c], M[2][2][c]));
-            E[0][c] = d11 * m0 + d12 * m1;
-            E[1][c] = d12 * m0 + d11 * m1;
-            E[2][c] = d33 * m2;
+            E[0][c] = (d11 * m0 + d12 * m1) * (1.0 / 6.0);   // the Gauss weight rides on E (fs.cpp:560-562)
+            E[1][c] = (d12 * m0 + d11 * m1) * (1.0 / 6.0);
+            E[2][c] = d33 * m2 * (1.0 / 6.0);
         }
 #pragma unroll
         for (int j = 0; j < 3; j++)
@@ -523,7 +545,7 @@ __device__ __forceinline__ void tri_plate_row_rt(const TriGeom &g, int I, double
             for (int r = 0; r < 3; r++)
 #pragma unroll
                 for (int c = 0; c < 3; c++)
-                    Kp[j][r][c] += (E[0][r] * M[j][0][c] + E[1][r] * M[j][1][c] + E[2][r] * M[j][2][c]) * (1.0 / 6.0);
+                    Kp[j][r][c] = fma(E[2][r], M[j][2][c], fma(E[1][r], M[j][1][c], fma(E[0][r], M[j][0][c], Kp[j][r][c])));
     }
     const double f = 2.0 * g.area;
 #pragma unroll
@@ -739,17 +761,18 @@ __device__ __forceinline__ void quad_plate_row_rt(const QuadGeom &g, int I, cons
         const double i00 = j11 * di, i01 = -j01 * di, i10 = -j10 * di, i11 = j00 * di;
         double Bc[3][3], E[3][3];
         quad_bcols_rt(hk, qtab + (gp * 4 + I) * 6, i00, i01, i10, i11, Bc);
+        const double e11 = d11 * det, e12 = d12 * det, e33 = d33 * det;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            E[0][c] = (d11 * Bc[0][c] + d12 * Bc[1][c]) * det;
-            E[1][c] = (d12 * Bc[0][c] + d11 * Bc[1][c]) * det;
-            E[2][c] = d33 * Bc[2][c] * det;
+            E[0][c] = fma(e12, Bc[1][c], e11 * Bc[0][c]);
+            E[1][c] = fma(e11, Bc[1][c], e12 * Bc[0][c]);
+            E[2][c] = e33 * Bc[2][c];
         }
 #define FS_QUAD_ACC_RT(J)                                                                          \
     {                                                                                              \
         quad_bcols<J>(h, r, s, i00, i01, i10, i11, Bc);                                            \
         _Pragma("unroll") for (int rr = 0; rr < 3; rr++) _Pragma("unroll") for (int c = 0; c < 3; c++) \
-            Kp[J][rr][c] += E[0][rr] * Bc[0][c] + E[1][rr] * Bc[1][c] + E[2][rr] * Bc[2][c];       \
+            Kp[J][rr][c] = fma(E[2][rr], Bc[2][c], fma(E[1][rr], Bc[1][c], fma(E[0][rr], Bc[0][c], Kp[J][rr][c]))); \
     }
         FS_QUAD_ACC_RT(0)
         FS_QUAD_ACC_RT(1)

@@ -4,6 +4,7 @@
 // handles (plus the local index at which each neighbour's values land in its halo) over the NCCL
 // communicator that fs_dist_init created, and maps the other ranks' windows.  Replaces, for the Krylov
 // loop, PETSc's VecScatter + MPI_Allreduce (fs.cpp:138).  Collective: called from fs_set_mesh on every rank.
+#include <algorithm>
 #include <cstring>
 
 #include "fs_context.hpp"
@@ -178,6 +179,14 @@ int peer_window_setup(fs_context *c)
             ok = 0;
             why = "device allocation of the peer tables failed";
         }
+    }
+    // folding the halo push into k_direction changes WHEN a rank pushes (and how often per solve): all ranks or none
+    {
+        const int64_t vg = std::max<int64_t>(1, std::min<int64_t>((c->n_own + 255) / 256, (int64_t)c->sm_count * c->vec_blocks_per_sm));
+        int fold = (c->push_foldable && 3 * c->send_total <= vg * 256) ? 1 : 0;
+        int rcf = nccl_barrier(c, &fold);
+        if (rcf != FS_OK) ok = 0;
+        c->push_foldable = fold != 0;
     }
     // every rank must take the same path; the all-reduce is also the barrier "all mailboxes are zeroed"
     int all_ok = ok;

@@ -115,11 +115,19 @@ __device__ __forceinline__ void peer_red_push(PeerWin *pw, const double (&v)[NV]
         w[k][0] = (bits & 0xffffffffull) | tag;
         w[k][1] = (bits >> 32) | tag;
     }
-    for (int r = 0; r < pw->world; r++) {
-        unsigned long long *slot = pw->mbox[r] + MBOX_RED + ((par * PEER_MAX + me) * 4) * 2;
+    // all mailbox pointers first (independent loads), then the stores back to back: a load between two stores would
+    // wait for the store's "memory" clobber and add an L2 round trip per rank to the tail of the producing kernel
+    unsigned long long *mb[PEER_MAX];
+    const int world = pw->world;
 #pragma unroll
-        for (int k = 0; k < NV; k++) st_relaxed_sys_v2(slot + 2 * k, w[k][0], w[k][1]);
-    }
+    for (int r = 0; r < PEER_MAX; r++) mb[r] = pw->mbox[r];
+#pragma unroll
+    for (int r = 0; r < PEER_MAX; r++)
+        if (r < world) {
+            unsigned long long *slot = mb[r] + MBOX_RED + ((par * PEER_MAX + me) * 4) * 2;
+#pragma unroll
+            for (int k = 0; k < NV; k++) st_relaxed_sys_v2(slot + 2 * k, w[k][0], w[k][1]);
+        }
     pw->seq_red = stamp;
 }
 

@@ -67,7 +67,7 @@ __host__ __device__ constexpr bool sell_uses_col(unsigned long long mask, int b)
 template <bool PEER>
 __device__ __forceinline__ double2 ld_x2(const double2 *p, bool halo)
 {
-    if (PEER) return halo ? __ldcg(p) : *p;
+    if (PEER) return halo ? __ldcg(p) : __ldg(p);   // owned blocks are read-only for the kernel's lifetime: ld.global.nc is legal
     return __ldg(p);
 }
 
@@ -143,14 +143,16 @@ __device__ __forceinline__ double sell_slice(int s, int lane, int n_own, int own
     return dot;
 }
 
-// PEER: slices whose rows read halo blocks (halo_flag) are processed LAST, after the wait for the neighbours' stamps:
-// the NVLink latency of the halo hides behind the interior slices (all but a few per cent of the strip).
+// PEER: slices whose rows read halo blocks are processed LAST, after the wait for the neighbours' stamps: the NVLink
+// latency of the halo hides behind the interior slices (all but a few per cent of the strip).  order[] lists the
+// interior slices first (n_interior of them), then the ones that read halo blocks; the next index is fetched while
+// the current slice streams.
 template <unsigned long long MASK, bool WITH_DOT, int BLOCK, int MINB, bool PEER = false, bool ROT = false, int UNROLL = 2>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_spmv_sell(int n_own, int own_lo, int n_slices, const int32_t *__restrict__ sptr, const int32_t *__restrict__ adj,
             const double *__restrict__ vals, const double *x, double *__restrict__ y_own,
             const double *x_own, double *partials, unsigned int *counter, CgState *state,
-            double *red, int fin_mode, PeerWin *pw, const uint8_t *__restrict__ halo_flag, const __grid_constant__ PlaneQ q)
+            double *red, int fin_mode, PeerWin *pw, const int32_t *__restrict__ order, int n_interior, const __grid_constant__ PlaneQ q)
 {
     if (WITH_DOT ? state->done : (state && state->done)) return;  // without the dot product: checked only when a state is passed
     const int lane = threadIdx.x & 31;
@@ -159,14 +161,18 @@ k_spmv_sell(int n_own, int own_lo, int n_slices, const int32_t *__restrict__ spt
     double dot = 0.0;
     if (PEER) {
         peer_kern_begin(pw, 0);
-        for (int s = gw; s < n_slices; s += nw)
-            if (!halo_flag[s]) dot += sell_slice<MASK, WITH_DOT, true, UNROLL, ROT>(s, lane, n_own, own_lo, sptr, adj, vals, x, y_own, x_own, q);
+        int s_next = gw < n_interior ? order[gw] : 0;
+        for (int k = gw; k < n_interior; k += nw) {
+            const int s = s_next;
+            if (k + nw < n_interior) s_next = order[k + nw];
+            dot += sell_slice<MASK, WITH_DOT, true, UNROLL, ROT>(s, lane, n_own, own_lo, sptr, adj, vals, x, y_own, x_own, q);
+        }
         if (!peer_halo_wait(pw)) {  // the neighbours' boundary values of x must have landed
             if (blockIdx.x == 0 && threadIdx.x == 0) peer_fail(state);
             return;
         }
-        for (int s = gw; s < n_slices; s += nw)
-            if (halo_flag[s]) dot += sell_slice<MASK, WITH_DOT, true, UNROLL, ROT>(s, lane, n_own, own_lo, sptr, adj, vals, x, y_own, x_own, q);
+        for (int k = n_interior + gw; k < n_slices; k += nw)
+            dot += sell_slice<MASK, WITH_DOT, true, UNROLL, ROT>(order[k], lane, n_own, own_lo, sptr, adj, vals, x, y_own, x_own, q);
     } else {
         for (int s = gw; s < n_slices; s += nw) dot += sell_slice<MASK, WITH_DOT, false, UNROLL, ROT>(s, lane, n_own, own_lo, sptr, adj, vals, x, y_own, x_own, q);
     }
@@ -179,9 +185,9 @@ k_spmv_sell(int n_own, int own_lo, int n_slices, const int32_t *__restrict__ spt
     }
 }
 
-// per slice: 1 when a row of the slice reads a block outside the owned range (a halo block)
+// per slice: 1 when a row of the slice reads a block outside the owned range (a halo block), and its complement
 static __global__ void k_sell_halo_flags(int n_own, int own_lo, int n_slices, const int32_t *__restrict__ sptr,
-                                         const int32_t *__restrict__ adj, uint8_t *__restrict__ flag)
+                                         const int32_t *__restrict__ adj, int32_t *__restrict__ flag, int32_t *__restrict__ nflag)
 {
     const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (s >= n_slices) return;
@@ -189,7 +195,19 @@ static __global__ void k_sell_halo_flags(int n_own, int own_lo, int n_slices, co
     bool any = false;
     for (int slot = 0; slot < dmax; slot++) any |= (unsigned)(adj[32 * (size_t)(s0 + slot) + lane] - own_lo) >= (unsigned)n_own;
     any = __any_sync(0xffffffffu, any);
-    if (lane == 0) flag[s] = any ? 1 : 0;
+    if (lane == 0) {
+        flag[s] = any ? 1 : 0;
+        nflag[s] = any ? 0 : 1;
+    }
+}
+
+// order = interior slices (ascending), then the slices that read halo blocks (ascending)
+static __global__ void k_sell_order(int n_slices, const int32_t *__restrict__ flag, const int32_t *__restrict__ pos_in, const int32_t *__restrict__ pos_halo,
+                                    int n_interior, int32_t *__restrict__ order)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slices) return;
+    order[flag[s] ? n_interior + pos_halo[s] : pos_in[s]] = s;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -296,33 +296,35 @@ k_direction(int64_t n_own, const double *__restrict__ z, double *__restrict__ p,
             return;
         }
         beta = t[0] / state->rz;
-        // the neighbours' halo values of the NEW p leave first: the pushing thread forms the value, stores it here
-        // and there; the bulk loop below skips those nodes (a node sent to two neighbours is formed twice, by
-        // threads that both read the old p only through their own entry -- so they write the old p's update once
-        // each to the same local address with the same value only if the node is listed once; is_send nodes listed
-        // twice are excluded from the folded push by the host)
-        if (push.n_push_blocks > 0)
-            peer_push_inline(pw, push.n_send, push.idx, push.push_peer, push.push_dst, push.push_counter, push.n_push_blocks,
-                             [&](int32_t node, int h) {
-                                 const size_t at = 3 * (size_t)(node - push.own_lo) + h;   // send-list nodes are owned nodes
-                                 const double2 zz = reinterpret_cast<const double2 *>(z)[at];
-                                 double2 *pl = reinterpret_cast<double2 *>(p) + at;
-                                 const double2 pp = *pl;
-                                 const double2 v = make_double2(zz.x + beta * pp.x, zz.y + beta * pp.y);
-                                 *pl = v;
-                                 return v;
-                             });
     } else beta = state->beta;
-    const int64_t n2 = 3 * n_own;
-    const double2 *z2 = reinterpret_cast<const double2 *>(z);
-    double2 *p2 = reinterpret_cast<double2 *>(p);
-    const uint8_t *skip = (pw && push.n_push_blocks > 0) ? push.is_send : nullptr;
-    for (int64_t i = blockIdx.x * (int64_t)BLOCK + threadIdx.x; i < n2; i += (int64_t)gridDim.x * BLOCK) {
-        if (skip && skip[i / 3]) continue;
-        double2 zz = z2[i], pp = p2[i];
-        pp.x = zz.x + beta * pp.x;
-        pp.y = zz.y + beta * pp.y;
-        p2[i] = pp;
+    const int n_push = pw ? push.n_push_blocks : 0;   // leading blocks: the neighbours' halo values of the NEW p and nothing else
+    if ((int)blockIdx.x < n_push) {
+        // The pushing thread forms the value and stores it here and there (the bulk blocks skip send-list nodes: a
+        // bulk thread could otherwise update p before the pushing thread has read the old value).  These blocks only
+        // push: the system-scope fence before the stamp waits for the NVLink writes, which must not delay bulk work.
+        peer_push_inline(pw, push.n_send, push.idx, push.push_peer, push.push_dst, push.push_counter, n_push,
+                         [&](int32_t node, int h) {
+                             const size_t at = 3 * (size_t)(node - push.own_lo) + h;   // send-list nodes are owned nodes
+                             const double2 zz = reinterpret_cast<const double2 *>(z)[at];
+                             double2 *pl = reinterpret_cast<double2 *>(p) + at;
+                             const double2 pp = *pl;
+                             const double2 v = make_double2(zz.x + beta * pp.x, zz.y + beta * pp.y);
+                             *pl = v;
+                             return v;
+                         });
+    } else {
+        const int64_t n2 = 3 * n_own;
+        const double2 *z2 = reinterpret_cast<const double2 *>(z);
+        double2 *p2 = reinterpret_cast<double2 *>(p);
+        const uint8_t *skip = n_push > 0 ? push.is_send : nullptr;
+        const int64_t stride = (int64_t)(gridDim.x - n_push) * BLOCK;
+        for (int64_t i = (blockIdx.x - n_push) * (int64_t)BLOCK + threadIdx.x; i < n2; i += stride) {
+            const uint8_t sk = skip ? skip[i / 3] : (uint8_t)0;   // issued together with the two loads below
+            double2 zz = z2[i], pp = p2[i];
+            pp.x = zz.x + beta * pp.x;
+            pp.y = zz.y + beta * pp.y;
+            if (!sk) p2[i] = pp;
+        }
     }
     if (pw) {  // the block that finishes last advances the recurrence (every block has read the old state)
         __syncthreads();
@@ -541,7 +543,7 @@ static void launch_sell_k(fs_context *c, int grid, const double *x, double *y_ow
         for (int j = 0; j < 3; j++) q.m[i][j] = c->plane_Q[3 * i + j];
     k_spmv_sell<MASK, WITH_DOT, SELL_BLOCK, SELL_MINB, PEER, ROT><<<grid, SELL_BLOCK, 0, c->stream>>>(
         (int)c->n_own, (int)c->own_lo, (int)c->sell_slices, c->d_sell_sptr.p, c->d_sell_adj.p, c->d_sell_vals.p, x, y_own, x_own,
-        c->d_partials.p, c->d_counter.p, state, red, fin_mode, pw, PEER ? c->d_sell_halo.p : nullptr, q);
+        c->d_partials.p, c->d_counter.p, state, red, fin_mode, pw, PEER ? c->d_sell_order.p : nullptr, PEER ? c->sell_n_interior : 0, q);
 }
 
 template <unsigned long long MASK, bool WITH_DOT>
@@ -707,8 +709,9 @@ static int enqueue_iteration(fs_context *c, double *red, int sg, int vg)
         push.n_push_blocks = (int)std::min<int64_t>(vg, std::max<int64_t>(1, nblk(3 * c->send_total, 256)));
         push.own_lo = c->own_lo;
         push.is_send = c->d_is_send.p;
-        // send list larger than the grid, or a node sent to two neighbours (two threads would update it): separate kernel
-        if (3 * c->send_total > (int64_t)push.n_push_blocks * 256 || !c->push_foldable) push.n_push_blocks = 0;
+        // send list larger than the grid, or a node sent to two neighbours (two threads would update it), on ANY rank
+        // (decided collectively in peer_window_setup): separate kernel at the start of the iteration
+        if (!c->push_foldable) push.n_push_blocks = 0;
         if (push.n_push_blocks == 0)
             k_halo_push<<<std::max(1u, nblk(3 * c->send_total, 256)), 256, 0, c->stream>>>(
                 pw, c->send_total, c->d_send_idx.p, c->d_push_peer.p, c->d_push_dst.p, c->d_p.p, c->d_state.p, c->d_counter.p + 1);
@@ -740,7 +743,7 @@ static int enqueue_iteration(fs_context *c, double *red, int sg, int vg)
         FS_NCCL(c, nccl().AllReduce(red + 4, red + 4, 2, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
         k_finalize<<<1, 1, 0, c->stream>>>(c->d_state.p, red + 4, 2);
     }
-    k_direction<256><<<vg, 256, 0, c->stream>>>(c->n_own, c->d_z.p + o6, c->d_p.p + o6, c->d_state.p, pw, c->d_counter.p, push);
+    k_direction<256><<<vg + push.n_push_blocks, 256, 0, c->stream>>>(c->n_own, c->d_z.p + o6, c->d_p.p + o6, c->d_state.p, pw, c->d_counter.p, push);
     return FS_OK;
 }
 
@@ -784,7 +787,7 @@ static int run_pcg(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
     } else if (fin == FIN_PEER) {
         k_finalize_init_peer<<<1, 32, 0, st>>>(c->d_state.p, pw);
         // halo of the first direction p = z; every later one is pushed by the k_direction that forms it
-        if (3 * c->send_total <= (int64_t)vg * 256 && c->push_foldable)
+        if (c->push_foldable)
             k_halo_push<<<std::max(1u, nblk(3 * c->send_total, 256)), 256, 0, st>>>(
                 pw, c->send_total, c->d_send_idx.p, c->d_push_peer.p, c->d_push_dst.p, c->d_p.p, c->d_state.p, c->d_counter.p + 1);
     }
@@ -833,6 +836,7 @@ static int run_pcg(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
         info->spmv_ms = 0.f;
         FS_CUDA(c, cudaEventElapsedTime(&info->solve_ms, c->ev0, c->ev1));
     }
+    if (s.status == FS_ERR_COMM) return fail(c, FS_ERR_COMM, "a wait for another GPU's halo or partial sums timed out (peer windows)");
     if (s.status == FS_ERR_BREAKDOWN) return fail(c, FS_ERR_BREAKDOWN, "CG breakdown: p.Ap <= 0 (matrix not positive definite)");
     if (s.status == FS_ERR_NOT_CONVERGED) return fail(c, FS_ERR_NOT_CONVERGED, "CG did not reach rtol within max_its");
     return FS_OK;
