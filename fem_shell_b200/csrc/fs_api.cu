@@ -115,6 +115,25 @@ int fs_dist_init(fs_context *c, int rank, int world, const uint8_t id_bytes[128]
         ncclResult_t r = nccl().CommInitRank(&comm, world, id, rank);
         if (r != ncclSuccess) return fail(c, FS_ERR_COMM, std::string("ncclCommInitRank: ") + nccl().GetErrorString(r));
         c->comm = (ncclComm *)comm;
+        // NCCL connects its channels at the FIRST collective of each kind (0.3 s on 2 GPUs, 1.1 s on 8: measured as the
+        // "peer window" phase of the first fs_set_mesh, profiles/r02h).  That is communicator set-up: pay it here, once,
+        // with the three operations the library uses (all-reduce, all-gather, send/recv with the neighbouring ranks).
+        PhaseTimer tm("fs_dist_init");
+        DevBuf<double> w;
+        FS_CUDA(c, w.alloc(64 * (size_t)(world + 1)));
+        FS_CUDA(c, cudaMemsetAsync(w.p, 0, sizeof(double) * 64 * (world + 1), c->stream));
+        r = nccl().AllReduce(w.p, w.p, 4, ncclDouble, ncclSum, comm, c->stream);
+        if (r == ncclSuccess) r = nccl().AllGather(w.p + 64 * world, w.p, 256, ncclChar, comm, c->stream);
+        if (r == ncclSuccess) r = nccl().GroupStart();
+        for (int nb = rank - 1; nb <= rank + 1 && r == ncclSuccess; nb += 2)
+            if (nb >= 0 && nb < world) {
+                r = nccl().Send(w.p, 8, ncclDouble, nb, comm, c->stream);
+                if (r == ncclSuccess) r = nccl().Recv(w.p + 8 + 8 * (nb > rank), 8, ncclDouble, nb, comm, c->stream);
+            }
+        if (r == ncclSuccess) r = nccl().GroupEnd();
+        if (r != ncclSuccess) return fail(c, FS_ERR_COMM, std::string("communicator warm-up: ") + nccl().GetErrorString(r));
+        FS_CUDA(c, cudaStreamSynchronize(c->stream));
+        tm.lap("first collectives (channel set-up)");
     }
     return FS_OK;
 }

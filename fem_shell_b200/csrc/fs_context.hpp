@@ -202,8 +202,7 @@ struct fs_context {
     int64_t sell_slices = 0, sell_slots = 0;
     int sell_dmax_max = 0;                 // widest slice (blocks per row): sizes the shared memory of k_sell_fill_t
     fs::DevBuf<int32_t> d_sell_sptr, d_sell_adj;
-    fs::DevBuf<int32_t> d_sell_order;      // several ranks: interior slices first, then those reading halo blocks (fs_sell.cuh)
-    int sell_n_interior = 0;
+    fs::DevBuf<int32_t> d_sell_hflag;      // several ranks, per slice: 1 = a row of the slice reads halo blocks (fs_sell.cuh)
     fs::DevBuf<double> d_sell_vals;
     fs::DevBuf<unsigned long long> d_sell_mask;
     int sell_blocks_per_sm = 2;

@@ -42,17 +42,21 @@ int peer_window_teardown(fs_context *c)
 {
     if (!c->win_base) return FS_OK;
     cudaSetDevice(c->device);
+    PhaseTimer tm("peer_window_teardown");
     if (c->stream) cudaStreamSynchronize(c->stream);
     // nobody may still be pushing into a window that is about to disappear
     if (c->comm && c->world > 1) nccl_barrier(c, nullptr);
+    tm.lap("barrier");
     for (int r = 0; r < PEER_MAX; r++)
         if (c->peer_base[r]) {
             cudaIpcCloseMemHandle(c->peer_base[r]);
             c->peer_base[r] = nullptr;
         }
+    tm.lap("cudaIpcCloseMemHandle");
     if (c->comm && c->world > 1) nccl_barrier(c, nullptr);
     c->d_p.release();  // view into the window
     cudaFree(c->win_base);
+    tm.lap("barrier + cudaFree");
     c->win_base = nullptr;
     c->peer_ready = false;
     return FS_OK;
@@ -69,6 +73,7 @@ int peer_window_setup(fs_context *c)
     cudaStream_t st = c->stream;
     const int me = c->rank, W = c->world;
     int ok = 1;
+    PhaseTimer tm("peer_window_setup");
 
     // ---- own window: [mailbox | p]; p moves into it ----
     const size_t p_bytes = sizeof(double) * 6 * (size_t)c->n_local;
@@ -85,6 +90,7 @@ int peer_window_setup(fs_context *c)
     for (const Peer &pr : c->peers)
         if (pr.recv_count > 0 && pr.rank < PEER_MAX) mine.recv_off_from[pr.rank] = pr.recv_off;
     mine.ok = ok;
+    tm.lap("window alloc + export");
 
     // ---- all-gather the metadata ----
     DevBuf<char> d_meta;
@@ -99,6 +105,7 @@ int peer_window_setup(fs_context *c)
     FS_CUDA(c, cudaMemcpyAsync(meta.data(), d_meta.p, sizeof(PeerMeta) * W, cudaMemcpyDeviceToHost, st));
     FS_CUDA(c, cudaStreamSynchronize(st));
     for (int r = 0; r < W; r++) ok = ok && meta[r].ok;
+    tm.lap("all-gather of the handles");
 
     // ---- map the other windows ----
     void *pb[PEER_MAX] = {};
@@ -111,6 +118,7 @@ int peer_window_setup(fs_context *c)
                 ok = 0;
             }
         }
+    tm.lap("cudaIpcOpenMemHandle");
     // ---- device-side description: everything that can fail locally happens BEFORE the one collective decision ----
     PeerWin h;
     memset(&h, 0, sizeof h);
@@ -180,6 +188,7 @@ int peer_window_setup(fs_context *c)
             why = "device allocation of the peer tables failed";
         }
     }
+    tm.lap("tables");
     // folding the halo push into k_direction changes WHEN a rank pushes (and how often per solve): all ranks or none
     {
         const int64_t vg = std::max<int64_t>(1, std::min<int64_t>((c->n_own + 255) / 256, (int64_t)c->sm_count * c->vec_blocks_per_sm));
@@ -205,6 +214,7 @@ int peer_window_setup(fs_context *c)
         return FS_OK;  // AUTO: stay on the NCCL path
     }
 
+    tm.lap("two verdict barriers");
     c->win_base = base;
     for (int r = 0; r < W; r++) c->peer_base[r] = pb[r];
     c->d_p.view((double *)((char *)base + MBOX_WORDS * 8), 6 * (size_t)c->n_local);

@@ -196,6 +196,21 @@ __device__ __forceinline__ bool peer_halo_wait(PeerWin *pw)
     return s_hok != 0;
 }
 
+// one warp: lane 0 waits for the stamps (acquire), the shuffle orders the other lanes' later loads behind it
+__device__ __forceinline__ bool peer_halo_wait_warp(PeerWin *pw, int lane)
+{
+    int ok = 1;
+    if (lane == 0) {
+        const long long t_begin = clock64();
+        const unsigned long long stamp = *reinterpret_cast<volatile unsigned long long *>(&pw->seq_halo);
+        const unsigned long long *mb = pw->mbox[pw->rank];
+        for (int k = 0; k < pw->n_recv && ok; k++) ok = peer_spin(mb + MBOX_HALO + pw->recv_rank[k], stamp, pw->spin_limit) ? 1 : 0;
+        atomicAdd(&pw->wait_cycles[0], (unsigned long long)(clock64() - t_begin));   // every waiting warp counts: average per wait
+        atomicAdd(&pw->wait_count[0], 1ull);
+    }
+    return __shfl_sync(0xffffffffu, ok, 0) != 0;
+}
+
 __device__ __forceinline__ void peer_fail(CgState *s)
 {
     s->status = FS_ERR_COMM;

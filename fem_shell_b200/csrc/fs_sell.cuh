@@ -143,16 +143,18 @@ __device__ __forceinline__ double sell_slice(int s, int lane, int n_own, int own
     return dot;
 }
 
-// PEER: slices whose rows read halo blocks are processed LAST, after the wait for the neighbours' stamps: the NVLink
-// latency of the halo hides behind the interior slices (all but a few per cent of the strip).  order[] lists the
-// interior slices first (n_interior of them), then the ones that read halo blocks; the next index is fetched while
-// the current slice streams.
+// PEER: hflag[s] != 0 marks the slices whose rows read halo blocks (a few per cent of a strip: its first and last
+// node rows).  A warp waits for the neighbours' stamps only when it reaches its first such slice (the push left with
+// the leading blocks of the previous k_direction, so the wait is usually over before it starts) and loads that
+// slice's halo blocks past L1; every other slice runs the single-rank loop -- owned blocks of x are read-only for
+// this kernel's lifetime.  Slices are walked in storage order: measured on 2 GPUs (profiles/r02h), moving the halo
+// slices behind a mid-kernel wait cost one extra slice time (~9 us of a 176 us kernel) in the tail.
 template <unsigned long long MASK, bool WITH_DOT, int BLOCK, int MINB, bool PEER = false, bool ROT = false, int UNROLL = 2>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_spmv_sell(int n_own, int own_lo, int n_slices, const int32_t *__restrict__ sptr, const int32_t *__restrict__ adj,
             const double *__restrict__ vals, const double *x, double *__restrict__ y_own,
             const double *x_own, double *partials, unsigned int *counter, CgState *state,
-            double *red, int fin_mode, PeerWin *pw, const int32_t *__restrict__ order, int n_interior, const __grid_constant__ PlaneQ q)
+            double *red, int fin_mode, PeerWin *pw, const int32_t *__restrict__ hflag, const __grid_constant__ PlaneQ q)
 {
     if (WITH_DOT ? state->done : (state && state->done)) return;  // without the dot product: checked only when a state is passed
     const int lane = threadIdx.x & 31;
@@ -161,18 +163,20 @@ k_spmv_sell(int n_own, int own_lo, int n_slices, const int32_t *__restrict__ spt
     double dot = 0.0;
     if (PEER) {
         peer_kern_begin(pw, 0);
-        int s_next = gw < n_interior ? order[gw] : 0;
-        for (int k = gw; k < n_interior; k += nw) {
-            const int s = s_next;
-            if (k + nw < n_interior) s_next = order[k + nw];
-            dot += sell_slice<MASK, WITH_DOT, true, UNROLL, ROT>(s, lane, n_own, own_lo, sptr, adj, vals, x, y_own, x_own, q);
+        bool waited = false;
+        int f_next = gw < n_slices ? hflag[gw] : 0;
+        for (int s = gw; s < n_slices; s += nw) {
+            const int f = f_next;
+            if (s + nw < n_slices) f_next = hflag[s + nw];
+            if (f) {   // warp-uniform
+                if (!waited) {
+                    if (!peer_halo_wait_warp(pw, lane)) peer_fail(state);   // the solve ends as FS_ERR_COMM; this product is discarded
+                    waited = true;
+                }
+                dot += sell_slice<MASK, WITH_DOT, true, UNROLL, ROT>(s, lane, n_own, own_lo, sptr, adj, vals, x, y_own, x_own, q);
+            } else
+                dot += sell_slice<MASK, WITH_DOT, false, UNROLL, ROT>(s, lane, n_own, own_lo, sptr, adj, vals, x, y_own, x_own, q);
         }
-        if (!peer_halo_wait(pw)) {  // the neighbours' boundary values of x must have landed
-            if (blockIdx.x == 0 && threadIdx.x == 0) peer_fail(state);
-            return;
-        }
-        for (int k = n_interior + gw; k < n_slices; k += nw)
-            dot += sell_slice<MASK, WITH_DOT, true, UNROLL, ROT>(order[k], lane, n_own, own_lo, sptr, adj, vals, x, y_own, x_own, q);
     } else {
         for (int s = gw; s < n_slices; s += nw) dot += sell_slice<MASK, WITH_DOT, false, UNROLL, ROT>(s, lane, n_own, own_lo, sptr, adj, vals, x, y_own, x_own, q);
     }
@@ -185,9 +189,9 @@ k_spmv_sell(int n_own, int own_lo, int n_slices, const int32_t *__restrict__ spt
     }
 }
 
-// per slice: 1 when a row of the slice reads a block outside the owned range (a halo block), and its complement
+// per slice: 1 when a row of the slice reads a block outside the owned range (a halo block)
 static __global__ void k_sell_halo_flags(int n_own, int own_lo, int n_slices, const int32_t *__restrict__ sptr,
-                                         const int32_t *__restrict__ adj, int32_t *__restrict__ flag, int32_t *__restrict__ nflag)
+                                         const int32_t *__restrict__ adj, int32_t *__restrict__ flag)
 {
     const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (s >= n_slices) return;
@@ -195,19 +199,7 @@ static __global__ void k_sell_halo_flags(int n_own, int own_lo, int n_slices, co
     bool any = false;
     for (int slot = 0; slot < dmax; slot++) any |= (unsigned)(adj[32 * (size_t)(s0 + slot) + lane] - own_lo) >= (unsigned)n_own;
     any = __any_sync(0xffffffffu, any);
-    if (lane == 0) {
-        flag[s] = any ? 1 : 0;
-        nflag[s] = any ? 0 : 1;
-    }
-}
-
-// order = interior slices (ascending), then the slices that read halo blocks (ascending)
-static __global__ void k_sell_order(int n_slices, const int32_t *__restrict__ flag, const int32_t *__restrict__ pos_in, const int32_t *__restrict__ pos_halo,
-                                    int n_interior, int32_t *__restrict__ order)
-{
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_slices) return;
-    order[flag[s] ? n_interior + pos_halo[s] : pos_in[s]] = s;
+    if (lane == 0) flag[s] = any ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------

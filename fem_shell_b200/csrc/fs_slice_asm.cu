@@ -411,25 +411,9 @@ int sell_layout_build(fs_context *c)
     c->sell_dmax_max = widest;
     FS_CUDA(c, c->d_sell_adj.alloc((size_t)32 * total));
     k_sl_adj<<<nblk(n_slices, 8), 256, 0, st>>>(n_own, (int)c->own_lo, c->d_nptr.p, c->d_nadj.p, c->d_sell_sptr.p, c->d_sell_adj.p);
-    if (c->world > 1) {  // processing order of the peer-path SpMV: interior slices first (fs_sell.cuh)
-        DevBuf<int32_t> flag, nflag, pin, phalo;
-        FS_CUDA(c, flag.alloc((size_t)n_slices + 1));
-        FS_CUDA(c, nflag.alloc((size_t)n_slices + 1));
-        FS_CUDA(c, pin.alloc((size_t)n_slices + 1));
-        FS_CUDA(c, phalo.alloc((size_t)n_slices + 1));
-        FS_CUDA(c, cudaMemsetAsync(flag.p, 0, sizeof(int32_t) * ((size_t)n_slices + 1), st));
-        FS_CUDA(c, cudaMemsetAsync(nflag.p, 0, sizeof(int32_t) * ((size_t)n_slices + 1), st));
-        k_sell_halo_flags<<<nblk(n_slices, 8), 256, 0, st>>>(n_own, (int)c->own_lo, n_slices, c->d_sell_sptr.p, c->d_sell_adj.p, flag.p, nflag.p);
-        rc = scan_excl(c, nflag.p, pin.p, (int64_t)n_slices + 1);
-        if (rc) return rc;
-        rc = scan_excl(c, flag.p, phalo.p, (int64_t)n_slices + 1);
-        if (rc) return rc;
-        int32_t n_in = 0;
-        FS_CUDA(c, cudaMemcpy(&n_in, pin.p + n_slices, sizeof n_in, cudaMemcpyDeviceToHost));
-        c->sell_n_interior = n_in;
-        FS_CUDA(c, c->d_sell_order.alloc((size_t)n_slices));
-        k_sell_order<<<nblk(n_slices, 256), 256, 0, st>>>(n_slices, flag.p, pin.p, phalo.p, n_in, c->d_sell_order.p);
-        FS_CUDA(c, cudaStreamSynchronize(st));
+    if (c->world > 1) {  // peer-path SpMV: which slices read halo blocks (fs_sell.cuh)
+        FS_CUDA(c, c->d_sell_hflag.alloc((size_t)n_slices));
+        k_sell_halo_flags<<<nblk(n_slices, 8), 256, 0, st>>>(n_own, (int)c->own_lo, n_slices, c->d_sell_sptr.p, c->d_sell_adj.p, c->d_sell_hflag.p);
     }
     FS_CUDA(c, cudaGetLastError());
     c->sell_layout_ready = true;

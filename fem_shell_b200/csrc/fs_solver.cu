@@ -543,7 +543,7 @@ static void launch_sell_k(fs_context *c, int grid, const double *x, double *y_ow
         for (int j = 0; j < 3; j++) q.m[i][j] = c->plane_Q[3 * i + j];
     k_spmv_sell<MASK, WITH_DOT, SELL_BLOCK, SELL_MINB, PEER, ROT><<<grid, SELL_BLOCK, 0, c->stream>>>(
         (int)c->n_own, (int)c->own_lo, (int)c->sell_slices, c->d_sell_sptr.p, c->d_sell_adj.p, c->d_sell_vals.p, x, y_own, x_own,
-        c->d_partials.p, c->d_counter.p, state, red, fin_mode, pw, PEER ? c->d_sell_order.p : nullptr, PEER ? c->sell_n_interior : 0, q);
+        c->d_partials.p, c->d_counter.p, state, red, fin_mode, pw, PEER ? c->d_sell_hflag.p : nullptr, q);
 }
 
 template <unsigned long long MASK, bool WITH_DOT>
