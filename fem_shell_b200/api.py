@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = [
     "fs_set_nodal_loads", "fs_set_interface_loads", "fs_build_rhs", "fs_assemble", "fs_get_assembly_path", "fs_solve",
     "fs_get_solution", "fs_get_solution_owned", "fs_recover_resultants", "fs_solve_host", "fs_interface_nodes", "fs_step", "fs_commit_step", "fs_get_sizes",
     "fs_export_dof_order", "fs_export_csr", "fs_export_rhs", "fs_debug_element_matrices", "fs_spmv_host",
-    "fs_bench_spmv", "fs_bench_fp64_peak", "fs_bench_contraction", "fs_set_ml_options", "fs_get_ml_info", "fs_get_ml_dist_levels", "fs_debug_ml_level", "fs_apply_mlrbm_host", "fs_partition_plan", "fs_gather_plan", "fs_meshgen", "fs_read_xda", "fs_read_forces", "fs_write_xda",
+    "fs_bench_spmv", "fs_bench_fp64_peak", "fs_bench_contraction", "fs_set_ml_options", "fs_get_ml_info", "fs_get_ml_dist_levels", "fs_get_ml_profile", "fs_debug_ml_level", "fs_apply_mlrbm_host", "fs_partition_plan", "fs_gather_plan", "fs_meshgen", "fs_read_xda", "fs_read_forces", "fs_write_xda",
 ]
 
 
@@ -405,6 +405,16 @@ class FemShell:
         self._ck(self.lib.fs_get_ml_dist_levels(self.ctx, C.byref(nd)))
         return {"levels": n, "distributed_levels": int(nd.value), "cells": [tuple(int(cells[3 * l + d]) for d in range(3)) for l in range(n)],
                 "lambda": [float(w[i]) for i in range(n + 1)], "setup_ms": float(ms.value)}
+
+    def ml_profile(self, reset=True):
+        """FS_ML_PROFILE=1 runs: per-iteration stage times (ms) of the multilevel-preconditioned CG"""
+        ms = (C.c_double * 8)()
+        n = C.c_int64(0)
+        self._ck(self.lib.fs_get_ml_profile(self.ctx, ms, C.byref(n), C.c_int(1 if reset else 0)))
+        k = max(1, int(n.value))
+        names = ("halo_spmv_update", "presmooth_restrict", "lattice_cycle", "prolong", "postsmooth_spmv_rz", "allreduce_direction",
+                 "lattice_level2_visit1", "lattice_level2_visit2")
+        return {"iterations": int(n.value), **{nm: float(ms[i]) / k for i, nm in enumerate(names)}}
 
     def ml_level(self, level, what):
         n = C.c_int64(0)

@@ -73,6 +73,8 @@ int fs_destroy(fs_context *c)
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+    for (cudaEvent_t e : c->prof.ev)
+        if (e) cudaEventDestroy(e);
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);
         cudaStreamDestroy(c->copy_stream);
@@ -906,7 +908,11 @@ int fs_bench_spmv(fs_context *c, int reps, fs_solve_info *info)
 int fs_set_ml_options(fs_context *c, int64_t max_points, int dense_points, int gamma)
 {
     FS_CHECK_CTX(c);
-    if (max_points < 1 || dense_points < 1 || dense_points > fs::ML_DENSE_MAX_POINTS || gamma < 1 || gamma > 3)
+    // gamma: one digit = the same cycle index on every lattice level; two digits "fd" = f visits of the second lattice
+    // per visit of the first, d on every deeper level (21: W on top, V below)
+    const int g_first = gamma >= 10 ? gamma / 10 : gamma, g_deep = gamma % 10;
+    if (max_points < 1 || dense_points < 1 || dense_points > fs::ML_DENSE_MAX_POINTS || gamma < 1 || gamma > 33 || g_first < 1 || g_first > 3 || g_deep < 1 ||
+        g_deep > 3)
         return fail(c, FS_ERR_ARG, "multilevel options out of range");
     if (max_points != c->ml_max_points || dense_points != c->ml_dense_points || gamma != c->ml_gamma) {
         c->ml_max_points = max_points;
@@ -938,6 +944,19 @@ int fs_get_ml_dist_levels(fs_context *c, int64_t *n_dist)
     FS_CHECK_CTX(c);
     if (!n_dist) return fail(c, FS_ERR_ARG, "null output");
     *n_dist = c->ml_geom_ready ? c->ml.n_dist : 0;
+    return FS_OK;
+}
+
+int fs_get_ml_profile(fs_context *c, double ms[8], int64_t *iterations, int reset)
+{
+    FS_CHECK_CTX(c);
+    if (!ms || !iterations) return fail(c, FS_ERR_ARG, "null output");
+    for (int k = 0; k < 8; k++) ms[k] = c->prof.ms[k];
+    *iterations = c->prof.n;
+    if (reset) {
+        for (double &v : c->prof.ms) v = 0.0;
+        c->prof.n = 0;
+    }
     return FS_OK;
 }
 

@@ -222,7 +222,7 @@ struct fs_context {
     double ml_h[3] = {0, 0, 0};            // largest element extent per axis (identical on every rank)
     int64_t ml_max_points = 1 << 22;       // cap on the cells of the first lattice
     int ml_dense_points = fs::ML_DENSE_MAX_POINTS;  // a lattice with at most this many cells is solved densely
-    int ml_gamma = 2;                      // cycle index on the lattice levels (1 = V, 2 = W)
+    int ml_gamma = 2;                      // cycle index on the lattice levels (1 = V, 2 = W; two digits: first lattice, deeper ones)
     bool ml_geom_ready = false, ml_values_ready = false;
     fs::MlHier ml;
     fs::DevBuf<double> d_partials;         // per-block partial sums
@@ -236,6 +236,14 @@ struct fs_context {
     int cg_graph_key = -1;
     double *cg_graph_red = nullptr;
     bool loads_set = false, rhs_ready = false, have_solution = false;
+
+    // FS_ML_PROFILE=1 (lab): the multilevel-preconditioned iterations run eagerly with events between their stages
+    struct StageProf {
+        bool on = false;
+        cudaEvent_t ev[12] = {};
+        double ms[10] = {};
+        long n = 0;
+    } prof;
 
     // coupled step
     std::vector<double> sols, pre_sols;

@@ -923,12 +923,15 @@ static int lat_cycle(fs_context *c, int l, int chk, double **out)
     }
     const int64_t t0 = 6 * (int64_t)L.c0, t1 = 6 * (int64_t)L.c1;
     k_lat_smooth0<<<nblk(t1 - t0, 256), 256, 0, st>>>(t0, t1, L.b.p, L.dinv.p, L.omega, L.x.p, st_of(c), chk);
-    for (int gmm = 0; gmm < c->ml_gamma; gmm++) {
+    const int n_visits = c->ml_gamma >= 10 ? (l == 0 ? c->ml_gamma / 10 : c->ml_gamma % 10) : c->ml_gamma;
+    for (int gmm = 0; gmm < n_visits; gmm++) {
         int rc = lat_restrict_chain(c, l, L.b.p, L.x.p, chk);
         if (rc) return rc;
         double *e = nullptr;
+        if (l == 0 && c->prof.on && gmm < 2) cudaEventRecord(c->prof.ev[7 + 2 * gmm], st);
         rc = lat_cycle(c, l + 1, chk, &e);
         if (rc) return rc;
+        if (l == 0 && c->prof.on && gmm < 2) cudaEventRecord(c->prof.ev[8 + 2 * gmm], st);
         rc = lat_prolong_chain(c, l, e, L.x.p, true, chk);
         if (rc) return rc;
     }
@@ -1047,9 +1050,12 @@ static void ml_probe_pairs(const fs_context *c, int *n, int a[6], int b[6], unsi
 
 int ml_prepare(fs_context *c)
 {
+    PhaseTimer tmg("ml_prepare");
     if (!c->ml_geom_ready) {
         int rc = ml_build_geometry(c);
         if (rc) return rc;
+        if (tmg.on) cudaStreamSynchronize(c->stream);
+        tmg.lap("geometry (lattices, aggregates, allocation)");
     }
     if (c->ml_values_ready) return FS_OK;
     if (c->cg_graph_exec) {  // a captured iteration carries the smoother weights of the previous values
@@ -1119,6 +1125,7 @@ int ml_prepare(fs_context *c)
     FS_CUDA(c, cudaEventRecord(e1, st));
     FS_CUDA(c, cudaStreamSynchronize(st));
     FS_CUDA(c, cudaEventElapsedTime(&m.setup_ms, e0, e1));
+    tmg.lap("values (weights, stencils, coarsest inverse)");
     c->ml_values_ready = true;
     return FS_OK;
 }
@@ -1132,13 +1139,17 @@ int ml_enqueue_apply(fs_context *c, bool init, double *red, int fin, int vec_gri
     const int64_t o6 = 6 * c->own_lo, n6 = 6 * c->n_own;
     const int chk = (init || !red) ? 0 : 1;
     k_f_smooth0<<<nblk(n6, 256), 256, 0, st>>>(n6, c->d_r.p + o6, c->d_minv.p, m.omega0, c->d_z.p + o6, st_of(c), chk);
+    auto mark = [&](int k) { if (c->prof.on) cudaEventRecord(c->prof.ev[k], st); };
     int rc = fine_restrict_chain(c, c->d_r.p, c->d_z.p, chk);
     if (rc) return rc;
+    mark(2);
     double *e = nullptr;
     rc = lat_cycle(c, 0, chk, &e);
     if (rc) return rc;
+    mark(3);
     rc = fine_prolong_chain(c, e, c->d_z.p, true, chk);
     if (rc) return rc;
+    mark(4);
     rc = spmv_once(c, c->d_z.p, c->d_q.p, chk != 0);
     if (rc) return rc;
     constexpr int PB = 192;

@@ -699,6 +699,8 @@ static int enqueue_iteration(fs_context *c, double *red, int sg, int vg)
     const int fin = single ? FIN_INLINE : (peer ? FIN_PEER : FIN_RED);
     PeerWin *pw = peer ? c->d_pw.p : nullptr;
     const int64_t o6 = 6 * c->own_lo;
+    auto mark = [&](int k) { if (PC == 3 && c->prof.on) cudaEventRecord(c->prof.ev[k], c->stream); };
+    mark(0);
     PushArgs push = {};
     if (peer) {  // the halo of p was pushed by the kernel that formed it (k_direction below, k_halo_push before the first iteration)
         push.n_send = c->send_total;
@@ -727,13 +729,16 @@ static int enqueue_iteration(fs_context *c, double *red, int sg, int vg)
     if (PC == 3) {  // z needs the lattice restriction of the updated r: update, restrict, coarse levels, prolong
         k_update_xr<256><<<vg, 256, 0, c->stream>>>(c->n_own, c->d_x.p + o6, c->d_r.p + o6, c->d_p.p + o6, c->d_q.p + o6,
                                                     c->d_partials.p, c->d_counter.p, c->d_state.p, red + 5);
+        mark(1);
         int rc = ml_enqueue_apply(c, false, red + 4, fin, vg);
         if (rc) return rc;
+        mark(5);
         if (fin == FIN_RED) {
             FS_NCCL(c, nccl().AllReduce(red + 4, red + 4, 2, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
             k_finalize<<<1, 1, 0, c->stream>>>(c->d_state.p, red + 4, 2);
         }
         k_direction<256><<<vg, 256, 0, c->stream>>>(c->n_own, c->d_z.p + o6, c->d_p.p + o6, c->d_state.p, pw, c->d_counter.p, PushArgs{});
+        mark(6);
         return FS_OK;
     }
     k_update<PC == 3 ? 1 : PC, NORM, 256><<<vg, 256, 0, c->stream>>>(c->n_own, c->d_x.p + o6, c->d_r.p + o6, c->d_p.p + o6,
@@ -793,9 +798,36 @@ static int run_pcg(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
     }
     // The iteration is captured once into a CUDA graph of GRAPH_ITERS iterations and replayed; kernels
     // past convergence (or past max_its) see done != 0 and return, so replaying whole graphs is exact.
+    if (PC == 3 && getenv("FS_ML_PROFILE")) {   // lab: eager iterations, stage times from events (tools/ml_stage_profile.py)
+        fs_context::StageProf &pf = c->prof;
+        if (!pf.ev[0])
+            for (cudaEvent_t &e : pf.ev) FS_CUDA(c, cudaEventCreate(&e));
+        pf.on = true;
+        for (;;) {
+            FS_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state.p, sizeof(CgState), cudaMemcpyDeviceToHost, st));
+            FS_CUDA(c, cudaStreamSynchronize(st));
+            if (c->h_state->done) break;
+            rc = enqueue_iteration<PC, NORM>(c, red, sg, vg);
+            if (rc) { pf.on = false; return rc; }
+            FS_CUDA(c, cudaStreamSynchronize(st));
+            for (int k = 0; k < 6; k++) {
+                float ms = 0.f;
+                FS_CUDA(c, cudaEventElapsedTime(&ms, pf.ev[k], pf.ev[k + 1]));
+                pf.ms[k] += ms;
+            }
+            for (int k = 0; k < 2; k++) {   // the two visits of the second lattice level from the first
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, pf.ev[7 + 2 * k], pf.ev[8 + 2 * k]) == cudaSuccess) pf.ms[6 + k] += ms;
+                else cudaGetLastError();
+            }
+            pf.n++;
+        }
+        pf.on = false;
+    } else {
     constexpr int GRAPH_ITERS = (PC == 3) ? 1 : 8;  // a multilevel iteration is ~100 launches already
     const int key = PC * 2 + NORM + (c->sell_active ? 8 * (1 + c->sell_kind) : 0) + (peer ? 64 : 0);
     if (!c->cg_graph_exec || c->cg_graph_key != key || c->cg_graph_red != red) {
+        PhaseTimer tmc("run_pcg");
         if (c->cg_graph_exec) cudaGraphExecDestroy(c->cg_graph_exec);
         c->cg_graph_exec = nullptr;
         cudaGraph_t graph = nullptr;
@@ -810,6 +842,7 @@ static int run_pcg(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
         FS_CUDA(c, ce);
         FS_CUDA(c, cudaGraphInstantiate(&c->cg_graph_exec, graph, 0));
         FS_CUDA(c, cudaGraphDestroy(graph));
+        tmc.lap("graph capture + instantiate");
         c->cg_graph_key = key;
         c->cg_graph_red = red;
     }
@@ -822,6 +855,7 @@ static int run_pcg(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
         int64_t n = std::min<int64_t>(batch, std::max<int64_t>(left, 1));
         for (int64_t k = 0; k < n; k += GRAPH_ITERS) FS_CUDA(c, cudaGraphLaunch(c->cg_graph_exec, st));
         FS_CUDA(c, cudaGetLastError());
+    }
     }
     FS_CUDA(c, cudaEventRecord(c->ev1, st));
     FS_CUDA(c, cudaStreamSynchronize(st));
@@ -884,8 +918,11 @@ int spmv_kernel_time(fs_context *c, int reps, float *ms_per_launch, float *ms_on
 int solver_run(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
 {
     if (!c->rhs_ready) return fail(c, FS_ERR_STATE, "no right-hand side: set loads first");
+    PhaseTimer tm("solver_run");
     int rc = solver_prepare(c, o->pc);
     if (rc) return rc;
+    if (tm.on) cudaStreamSynchronize(c->stream);
+    tm.lap("solver_prepare (format, preconditioner)");
     const int nt = o->norm_type ? 1 : 0;
     switch (o->pc * 2 + nt) {
     case 0: return run_pcg<0, 0>(c, o, info);

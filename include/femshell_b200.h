@@ -234,8 +234,9 @@ int fs_bench_contraction(fs_context *ctx, int64_t n_elem, int reps, double out[6
 /* ---- FS_PC_MLRBM (fem_shell_b200/csrc/fs_mlpc.cuh; no counterpart in the reference) ---- */
 /* max_points: cap on the cells of the first lattice (default 4194304; its vectors are replicated on every rank and
  * all-reduced once per iteration).  dense_points: a lattice with at most this many cells is inverted densely
- * (default and maximum 200).  gamma: cycle index on the lattice levels, 1 = V, 2 = W (default).  Same values on
- * all ranks. */
+ * (default and maximum 200).  gamma: cycle index on the lattice levels, 1 = V, 2 = W (default); two digits "fd" = f
+ * visits of the second lattice per visit of the first and d on every deeper level (21 = W on top, V below).  Same
+ * values on all ranks. */
 int fs_set_ml_options(fs_context *ctx, int64_t max_points, int dense_points, int gamma);
 /* *levels = number of lattice levels (0 before the first use); cells[3*l..3*l+2] = cells per axis of lattice l
  * (room for 3*14); weights[0] = estimate of lambda_max(D^-1 A) on the mesh, weights[1+l] = on lattice l (room
@@ -245,6 +246,11 @@ int fs_get_ml_info(fs_context *ctx, int64_t *levels, int64_t *cells, double *wei
  * exchanged before each stencil application); the levels below are replicated.  0 with one rank, for lattices below
  * FS_ML_DIST_MIN_CELLS cells (environment, default 32768), or when the node blocks do not follow the slab direction. */
 int fs_get_ml_dist_levels(fs_context *ctx, int64_t *n_dist);
+/* lab (environment FS_ML_PROFILE=1): FS_PC_MLRBM solves run their iterations eagerly with CUDA events between the
+ * stages; ms[0..5] = accumulated time of {halo + SpMV + update, pre-smoothing + restriction to the first lattice,
+ * lattice cycle, prolongation, post-smoothing SpMV + r.z, all-reduce + new direction}, ms[6..7] = the two visits of
+ * the second lattice level (part of ms[2]); *iterations = how many were accumulated; reset != 0 clears them. */
+int fs_get_ml_profile(fs_context *ctx, double ms[8], int64_t *iterations, int reset);
 /* parity tests: copy of lattice level `level`: what = 0 the stencil (structure of arrays: entry (a,b) of the block
  * coupling cell p to its neighbour in slot s at [(6s+b)*6n + 6p + a], slot digits base 3 over the active axes,
  * offset = digit - 1), 1 the 36n pseudo-inverses of the diagonal blocks, 2 the dense inverse of the coarsest

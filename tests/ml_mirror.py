@@ -132,7 +132,8 @@ class Mirror:
             return lev["dense"] @ b
         A, Dinv, om, P = lev["A"], lev["Dinv"], lev["om"], lev["P"]
         x = om * (Dinv @ b)
-        for _ in range(self.gamma if l >= 1 else 1):
+        g = self.gamma if self.gamma < 10 else (self.gamma // 10 if l == 1 else self.gamma % 10)
+        for _ in range(g if l >= 1 else 1):
             x = x + P @ self.cycle(l + 1, P.T @ (b - A @ x))
         return x + om * (Dinv @ (b - A @ x))
 
