@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = [
     "fs_set_nodal_loads", "fs_set_interface_loads", "fs_build_rhs", "fs_assemble", "fs_get_assembly_path", "fs_solve",
     "fs_get_solution", "fs_get_solution_owned", "fs_recover_resultants", "fs_solve_host", "fs_interface_nodes", "fs_step", "fs_commit_step", "fs_get_sizes",
     "fs_export_dof_order", "fs_export_csr", "fs_export_rhs", "fs_debug_element_matrices", "fs_spmv_host",
-    "fs_bench_spmv", "fs_bench_fp64_peak", "fs_bench_contraction", "fs_set_ml_options", "fs_get_ml_info", "fs_get_ml_dist_levels", "fs_get_ml_profile", "fs_debug_ml_level", "fs_apply_mlrbm_host", "fs_partition_plan", "fs_gather_plan", "fs_meshgen", "fs_read_xda", "fs_read_forces", "fs_write_xda",
+    "fs_bench_spmv", "fs_bench_fp64_peak", "fs_bench_contraction", "fs_set_ml_options", "fs_get_ml_info", "fs_get_ml_dist_levels", "fs_get_ml_profile", "fs_debug_ml_level", "fs_apply_mlrbm_host", "fs_partition_plan", "fs_gather_plan", "fs_meshgen", "fs_read_xda", "fs_read_mesh", "fs_write_xdr", "fs_read_forces", "fs_write_xda",
 ]
 
 
@@ -153,18 +153,36 @@ def partition_plan(eptr, enodes, n_nodes, rank, world, dof_mode=DOF_FIRST_ENCOUN
                 peers=[dict(rank=int(r[0]), send_count=int(r[1]), send_off=int(r[2]), recv_count=int(r[3]), recv_off=int(r[4])) for r in pt])
 
 
-def read_xda(path):
+def _read_with(fn_name, path):
     lib = load_library()
+    fn = getattr(lib, fn_name)
     nn, ne, nen, nb = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
-    rc = lib.fs_read_xda(path.encode(), C.byref(nn), C.byref(ne), C.byref(nen), C.byref(nb), None, None, None, None, None)
+    rc = fn(path.encode(), C.byref(nn), C.byref(ne), C.byref(nen), C.byref(nb), None, None, None, None, None)
     if rc:
-        raise FemShellError(rc, "fs_read_xda(%s)" % path)
+        raise FemShellError(rc, "%s(%s)" % (fn_name, path))
     xyz = np.empty((nn.value, 3)); etype = np.empty(ne.value, np.int32); eptr = np.empty(ne.value + 1, np.int64)
     enodes = np.empty(nen.value, np.int32); bc = np.empty((nb.value, 3), np.int32)
-    rc = lib.fs_read_xda(path.encode(), C.byref(nn), C.byref(ne), C.byref(nen), C.byref(nb), _p(xyz), _p(etype), _p(eptr), _p(enodes), _p(bc))
+    rc = fn(path.encode(), C.byref(nn), C.byref(ne), C.byref(nen), C.byref(nb), _p(xyz), _p(etype), _p(eptr), _p(enodes), _p(bc))
     if rc:
-        raise FemShellError(rc, "fs_read_xda(%s)" % path)
+        raise FemShellError(rc, "%s(%s)" % (fn_name, path))
     return dict(xyz=xyz, etype=etype, eptr=eptr, enodes=enodes, bc=bc)
+
+
+def read_xda(path):
+    return _read_with("fs_read_xda", path)
+
+
+def read_mesh(path):
+    """mesh.read() of fs.cpp:37: *.msh (Gmsh 2.x ASCII), *.xdr (binary twin of XDA) or XDA, by extension"""
+    return _read_with("fs_read_mesh", path)
+
+
+def write_xdr(path, xyz, etype, eptr, enodes, bc):
+    xyz, etype, eptr, enodes, bc = _f64(xyz), _i32(etype), _i64(eptr), _i32(enodes), _i32(bc).reshape(-1, 3)
+    rc = load_library().fs_write_xdr(path.encode(), C.c_int64(xyz.shape[0]), _p(xyz), C.c_int64(etype.size), _p(etype), _p(eptr), _p(enodes),
+                                     C.c_int64(bc.shape[0]), _p(bc))
+    if rc:
+        raise FemShellError(rc, "fs_write_xdr(%s)" % path)
 
 
 def read_forces(path, n_nodes):

@@ -42,10 +42,10 @@ struct Mesh {
     {
         file = path;
         int64_t nn = 0, ne = 0, nen = 0, nb = 0;
-        int rc = fs_read_xda(path.c_str(), &nn, &ne, &nen, &nb, nullptr, nullptr, nullptr, nullptr, nullptr);
+        int rc = fs_read_mesh(path.c_str(), &nn, &ne, &nen, &nb, nullptr, nullptr, nullptr, nullptr, nullptr);
         if (rc) throw Error(rc, "cannot read mesh file " + path);
         xyz.resize(3 * nn); etype.resize(ne); eptr.resize(ne + 1); enodes.resize(nen); bc.resize(3 * nb);
-        rc = fs_read_xda(path.c_str(), &nn, &ne, &nen, &nb, xyz.data(), etype.data(), eptr.data(), enodes.data(), bc.data());
+        rc = fs_read_mesh(path.c_str(), &nn, &ne, &nen, &nb, xyz.data(), etype.data(), eptr.data(), enodes.data(), bc.data());
         if (rc) throw Error(rc, "cannot read mesh file " + path);
         forces.assign(6 * nn, 0.0);
     }

@@ -288,6 +288,15 @@ int fs_meshgen(char kind, int nx, int ny, double min_x, double min_y, double max
 /* XDA reader (fs.cpp:37) and <base>_f reader (fs.cpp:44-67); two-call protocol as above */
 int fs_read_xda(const char *path, int64_t *n_nodes, int64_t *n_elem, int64_t *n_enodes, int64_t *n_bc,
                 double *xyz, int32_t *etype, int64_t *eptr, int32_t *enodes, int32_t *bc);
+/* mesh.read() of fs.cpp:37: the format follows the extension like libMesh's -- *.msh = Gmsh MSH 2.x ASCII (3-node
+ * triangles, 4-node quadrangles; 2-node lines carry the boundary ids as their physical group), *.xdr = the binary
+ * (Sun XDR) twin of the XDA layout, anything else = XDA.  Same two-call protocol.  The reference holds no *.msh /
+ * *.xdr fixture: these two readers follow the format descriptions (fem_shell_b200/csrc/fs_meshio.cpp). */
+int fs_read_mesh(const char *path, int64_t *n_nodes, int64_t *n_elem, int64_t *n_enodes, int64_t *n_bc,
+                 double *xyz, int32_t *etype, int64_t *eptr, int32_t *enodes, int32_t *bc);
+int fs_write_xdr(const char *path, int64_t n_nodes, const double *xyz, int64_t n_elem,
+                 const int32_t *etype, const int64_t *eptr, const int32_t *enodes, int64_t n_bc,
+                 const int32_t *bc);
 int fs_read_forces(const char *path, int64_t n_nodes, double *forces);
 int fs_write_xda(const char *path, int64_t n_nodes, const double *xyz, int64_t n_elem,
                  const int32_t *etype, const int64_t *eptr, const int32_t *enodes, int64_t n_bc,
