@@ -15,7 +15,8 @@ from dataclasses import dataclass
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfemshell_b200.so")
+# FEMSHELL_B200_LIB: lab builds of the same library (tools/asm_variants.sh); the product is the in-tree file
+LIB_PATH = os.environ.get("FEMSHELL_B200_LIB") or os.path.join(HERE, "libfemshell_b200.so")
 
 TRI3, QUAD4 = 3, 5
 DOF_FIRST_ENCOUNTER, DOF_NODE_ID = 0, 1

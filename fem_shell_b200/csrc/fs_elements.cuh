@@ -30,6 +30,13 @@ struct ElemConst {
     int quirks;               // FS_QUIRK_* bits
 };
 
+// Gauss-point loops of the run-time-row quad kernels: 4 = fully unrolled (r, s fold into the shape-function constants),
+// 1 = rolled (a quarter of the code: the values pass is short of instruction-cache hits, profiles/r02k_ncu_full.txt)
+#ifndef FS_QUAD_GP_UNROLL
+#define FS_QUAD_GP_UNROLL 4
+#endif
+constexpr int QUAD_GP_UNROLL = FS_QUAD_GP_UNROLL;
+
 __constant__ ElemConst c_el;   // one copy per translation unit that includes this header (no -rdc)
 
 // fs.cpp:273-294 initMaterialMatrices
@@ -305,7 +312,7 @@ __device__ __forceinline__ void quad_membrane_row_rt(const QuadGeom &g, int I, d
     const bool quirk = (c_el.quirks & FS_Q_DETLU) != 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) Km[j][0][0] = Km[j][0][1] = Km[j][1][0] = Km[j][1][1] = 0.0;
-#pragma unroll
+#pragma unroll QUAD_GP_UNROLL
     for (int gp = 0; gp < 4; gp++) {
         const double r = (gp & 2) ? -root : root;
         const double s = (gp & 1) ? -root : root;
@@ -748,7 +755,7 @@ __device__ __forceinline__ void quad_plate_row_rt(const QuadGeom &g, int I, cons
 #pragma unroll
         for (int r = 0; r < 3; r++) Kp[j][r][0] = Kp[j][r][1] = Kp[j][r][2] = 0.0;
     Lu2State st = {false, false};
-#pragma unroll
+#pragma unroll QUAD_GP_UNROLL
     for (int gp = 0; gp < 4; gp++) {
         const double r = (gp & 2) ? -root : root;
         const double s = (gp & 1) ? -root : root;
