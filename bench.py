@@ -110,6 +110,22 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def nvlink_kib(index):
+    """NVML's NVLink data counters of one GPU, summed over its links: (tx KiB, rx KiB) or None.  Read before and after
+    the timed region: the bytes the peer-window kernels (or NCCL) really moved, from the link side"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        v = pynvml.nvmlDeviceGetFieldValues(h, [(pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xFFFFFFFF),
+                                                 (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xFFFFFFFF)])
+        if any(x.nvmlReturn != 0 for x in v):
+            return None
+        return int(v[0].value.ullVal), int(v[1].value.ullVal)
+    except Exception:
+        return None
+
+
 def make_workload(gen, nodes_x, nodes_y, kind="q"):
     """meshGen: q nx ny 0 0 Lx Ly 1,1,1,1 q0 2 1 z  (clamped = boundary id 1, uniform load).  gen = the product's
     host generator (fsb.meshgen) on our arm, the oracle's numpy restatement (fso.meshgen) on the reference arm."""
@@ -443,7 +459,9 @@ def run_ours(args):
     its_done[0] = 0
     if world > 1:
         s.comm_stats(reset=True)
+    nvl0 = nvlink_kib(local_rank) if world > 1 else None
     total_ms = timed(step, args.steps)
+    nvl1 = nvlink_kib(local_rank) if world > 1 else None
     waits = s.comm_stats(reset=True) if world > 1 else None
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
@@ -653,7 +671,13 @@ def run_ours(args):
                      "r_z_partials_in_direction": waits["rz_wait_us"] / max(1, waits["rz_waits"]),
                      "kernel_wall_us": {"k_spmv_sell": waits["spmv_us"] / waits["pq_waits"], "k_update": waits["update_us"] / waits["pq_waits"],
                                         "k_direction": waits["direction_us"] / max(1, waits["rz_waits"]), "iteration": 1e3 * ms_per_step / iters},
-                     "how": "clock64 around the spin loops, block 0 of each kernel (fs_peer.cuh)"}},
+                     "how": "halo: average per waiting warp of k_spmv_sell; partials: clock64 around the spin loops, block 0 (fs_peer.cuh)"},
+                    # link-side evidence: NVML's NVLink data counters of rank 0's GPU around the timed region, against the bytes the
+                    # algorithm must send per iteration (48 B per send-list node + the 8-byte words of the two mailbox reductions)
+                    "nvlink_rank0": None if not (nvl0 and nvl1) else
+                    {"tx_bytes_per_iteration": 1024.0 * (nvl1[0] - nvl0[0]) / max(1, its_timed), "rx_bytes_per_iteration": 1024.0 * (nvl1[1] - nvl0[1]) / max(1, its_timed),
+                     "algorithmic_tx_bytes_per_iteration": 48.0 * nx + 16.0 * 3 * (world - 1),   # rank 0: one neighbour, one node row of the strip
+                     "source": "NVML NVLINK_THROUGHPUT_DATA_TX/RX, all links of rank 0's GPU, KiB granularity"}},
         "metrics": {"cg_dof_iterations_per_s": value, "elements_assembled_per_s": n_elem / (asm_ms * 1e-3),
                     "assemble_ms": asm_ms, "time_to_solution": tts, "time_to_solution_bounded": tts_small,
                     "time_to_first_solution": first,

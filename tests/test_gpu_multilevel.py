@@ -32,7 +32,7 @@ def dof_ordered(ref, m):
     return xyz, mask
 
 
-@pytest.mark.parametrize("gamma", [1, 2])
+@pytest.mark.parametrize("gamma", [1, 2, 21])      # 21: two visits of the second lattice per visit of the first, one below
 @pytest.mark.parametrize("case", sorted(CASES))
 def test_cycle_matches_explicit_galerkin_mirror(fso, fsb, case, gamma):
     """the probed stencils, transfer kernels, smoothers and the dense coarsest solve reproduce the cycle built
@@ -92,6 +92,26 @@ def test_multilevel_iterations_grow_slowly(fsb):
         s = gpu_system(fsb, m, 0.3, 1e7, 0.5, loads=m["forces"])
         its.append(s.solve(rtol=1e-8, max_its=2000, pc=fsb.PC_MLRBM, warm_start=False).iterations)
     assert its[0] <= 60 and its[2] <= 110 and its[2] <= 2.2 * its[0], its
+
+
+def test_stage_profile_of_the_multilevel_iteration(fsb, monkeypatch):
+    """FS_ML_PROFILE=1: the iterations run eagerly between events; same iteration count as the captured graph, and the
+    stage times add up to (about) the solve time"""
+    m = fsb.meshgen("q", 90, 70, 0, 0, 10, 8, (1, 1, 1, 1), 300.0, 2, 1)
+    s = gpu_system(fsb, m, 0.3, 1e7, 0.5, loads=m["forces"])
+    s.set_ml_options(dense_points=24)
+    ref = s.solve(rtol=1e-9, max_its=2000, pc=fsb.PC_MLRBM, warm_start=False)
+    u = s.solution()
+    monkeypatch.setenv("FS_ML_PROFILE", "1")
+    s.ml_profile(reset=True)
+    info = s.solve(rtol=1e-9, max_its=2000, pc=fsb.PC_MLRBM, warm_start=False)
+    p = s.ml_profile()
+    assert info.iterations == ref.iterations == p["iterations"]
+    assert np.array_equal(s.solution(), u)
+    stages = [p[k] for k in ("halo_spmv_update", "presmooth_restrict", "lattice_cycle", "prolong", "postsmooth_spmv_rz", "allreduce_direction")]
+    assert all(v > 0 for v in stages)
+    assert 0.5 * info.solve_ms <= sum(stages) * info.iterations <= 1.05 * info.solve_ms
+    assert p["lattice_level2_visit1"] + p["lattice_level2_visit2"] <= p["lattice_cycle"]
 
 
 def test_multilevel_rejects_preconditioned_norm(fsb):
