@@ -111,17 +111,30 @@ class ClockSampler:
 
 
 def nvlink_kib(index):
-    """NVML's NVLink data counters of one GPU, summed over its links: (tx KiB, rx KiB) or None.  Read before and after
-    the timed region: the bytes the peer-window kernels (or NCCL) really moved, from the link side"""
+    """NVLink data counters of one GPU, summed over its links: (tx KiB, rx KiB) or None.  Read before and after the timed
+    region: the bytes the peer-window kernels (or NCCL) really moved, from the link side.  NVML field values first, the
+    text of `nvidia-smi nvlink -gt d` as a fallback."""
     try:
         import pynvml
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(index)
         v = pynvml.nvmlDeviceGetFieldValues(h, [(pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xFFFFFFFF),
                                                  (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xFFFFFFFF)])
-        if any(x.nvmlReturn != 0 for x in v):
-            return None
-        return int(v[0].value.ullVal), int(v[1].value.ullVal)
+        if all(x.nvmlReturn == 0 for x in v):
+            return int(v[0].value.ullVal), int(v[1].value.ullVal)
+    except Exception:
+        pass
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=20).stdout
+        tx = rx = 0
+        seen = False
+        for ln in out.splitlines():
+            ln = ln.strip()
+            if "Data Tx:" in ln:
+                tx += int(ln.split("Data Tx:")[1].split()[0]); seen = True
+            elif "Data Rx:" in ln:
+                rx += int(ln.split("Data Rx:")[1].split()[0]); seen = True
+        return (tx, rx) if seen else None
     except Exception:
         return None
 

@@ -908,11 +908,11 @@ int fs_bench_spmv(fs_context *c, int reps, fs_solve_info *info)
 int fs_set_ml_options(fs_context *c, int64_t max_points, int dense_points, int gamma)
 {
     FS_CHECK_CTX(c);
-    // gamma: one digit = the same cycle index on every lattice level; two digits "fd" = f visits of the second lattice
-    // per visit of the first, d on every deeper level (21: W on top, V below)
-    const int g_first = gamma >= 10 ? gamma / 10 : gamma, g_deep = gamma % 10;
-    if (max_points < 1 || dense_points < 1 || dense_points > fs::ML_DENSE_MAX_POINTS || gamma < 1 || gamma > 33 || g_first < 1 || g_first > 3 || g_deep < 1 ||
-        g_deep > 3)
+    // gamma: decimal digits, most significant first: digit l = visits of lattice level l+1 per visit of level l; the last
+    // digit also serves every deeper level (2 = W everywhere, 21 = W on top and V below, 2211 = W on the two finest lattices)
+    bool digits_ok = gamma >= 1 && gamma <= 333333;
+    for (int g = gamma; g > 0 && digits_ok; g /= 10) digits_ok = g % 10 >= 1 && g % 10 <= 3;
+    if (max_points < 1 || dense_points < 1 || dense_points > fs::ML_DENSE_MAX_POINTS || !digits_ok)
         return fail(c, FS_ERR_ARG, "multilevel options out of range");
     if (max_points != c->ml_max_points || dense_points != c->ml_dense_points || gamma != c->ml_gamma) {
         c->ml_max_points = max_points;

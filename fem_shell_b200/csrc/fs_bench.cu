@@ -230,3 +230,66 @@ extern "C" int fs_bench_fp64_peak(fs_context *c, double *tflops)
     *tflops = flops / (best * 1e-3) / 1e12;
     return FS_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// kernel-to-kernel latency inside a CUDA graph, with and without programmatic dependent launch: the coarse levels of
+// the multilevel cycle and the three kernels of a CG iteration are chains of short dependent kernels
+// ---------------------------------------------------------------------------------------------
+namespace fs {
+template <bool PDL>
+__global__ void __launch_bounds__(128) k_chain_link(double *v, int n)
+{
+    if (PDL) {
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next link may be scheduled behind this grid
+        asm volatile("griddepcontrol.wait;" ::: "memory");                // ... and this one touches memory only after its predecessor is done
+    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = v[i] * 1.0000001 + 1.0;
+}
+}  // namespace fs
+
+extern "C" int fs_bench_launch_chain(fs_context *c, int links, int n, int reps, double out_us[2])
+{
+    using namespace fs;
+    if (!c || !out_us || links <= 0 || n <= 0 || reps <= 0) return FS_ERR_ARG;
+    FS_CUDA(c, cudaSetDevice(c->device));
+    DevBuf<double> v;
+    FS_CUDA(c, v.alloc((size_t)n));
+    FS_CUDA(c, cudaMemsetAsync(v.p, 0, sizeof(double) * n, c->stream));
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    for (int variant = 0; variant < 2; variant++) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        FS_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        for (int k = 0; k < links; k++) {
+            if (variant == 0) k_chain_link<false><<<grid, 128, 0, c->stream>>>(v.p, n);
+            else {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(grid);
+                cfg.blockDim = dim3(128);
+                cfg.stream = c->stream;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = 1;
+                cudaLaunchKernelEx(&cfg, k_chain_link<true>, v.p, n);
+            }
+        }
+        cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+        FS_CUDA(c, ce);
+        FS_CUDA(c, cudaGraphInstantiate(&exec, graph, 0));
+        FS_CUDA(c, cudaGraphLaunch(exec, c->stream));
+        FS_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+        for (int r = 0; r < reps; r++) FS_CUDA(c, cudaGraphLaunch(exec, c->stream));
+        FS_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+        FS_CUDA(c, cudaStreamSynchronize(c->stream));
+        float ms = 0.f;
+        FS_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        out_us[variant] = 1e3 * ms / ((double)reps * links);
+        cudaGraphExecDestroy(exec);
+        cudaGraphDestroy(graph);
+    }
+    return FS_OK;
+}
+

@@ -29,7 +29,12 @@
 namespace fs {
 
 constexpr int ML_MAX_LEVELS = 14;       // lattice levels
-constexpr int ML_DENSE_MAX_POINTS = 200;  // cells of the dense coarsest level (6 unknowns each)
+// cells of the dense coarsest level (6 unknowns each).  A lattice visit is a chain of ~12 kernels of a few microseconds and
+// a W-cycle visits level l 2^l times: on the 96 M-DOF plate the levels below 10^4 cells took 2.2 of 7.4 ms per iteration
+// (profiles/r02l_ml_stage_profile_n8.json).  Ending the hierarchy at <= 400 cells (a 2400 x 2400 inverse, 46 MB, applied
+// from L2 in ~8 us) instead of <= 200 removes the two deepest levels of that plate for ~20 ms more set-up.
+constexpr int ML_DENSE_MAX_POINTS = 512;
+constexpr int ML_DENSE_DEFAULT_POINTS = 400;
 
 struct LatGeom {
     int np[3];      // cells per dimension (1 for an inactive dimension)

@@ -230,13 +230,16 @@ int fs_bench_fp64_peak(fs_context *ctx, double *tflops);
  * DMMA, max relative difference of the per-element checksums, measured DMMA peak TFLOP/s, useful TFLOP/s FMA,
  * useful TFLOP/s DMMA}.  fem_shell_b200/csrc/fs_bench.cu. */
 int fs_bench_contraction(fs_context *ctx, int64_t n_elem, int reps, double out[6]);
+/* micro-benchmark: microseconds per link of a chain of `links` dependent kernels (n doubles each) replayed from a CUDA
+ * graph; out_us[0] = plain launches, out_us[1] = programmatic dependent launch (griddepcontrol).  fs_bench.cu. */
+int fs_bench_launch_chain(fs_context *ctx, int links, int n, int reps, double out_us[2]);
 
 /* ---- FS_PC_MLRBM (fem_shell_b200/csrc/fs_mlpc.cuh; no counterpart in the reference) ---- */
 /* max_points: cap on the cells of the first lattice (default 4194304; its vectors are replicated on every rank and
  * all-reduced once per iteration).  dense_points: a lattice with at most this many cells is inverted densely
- * (default and maximum 200).  gamma: cycle index on the lattice levels, 1 = V, 2 = W (default); two digits "fd" = f
- * visits of the second lattice per visit of the first and d on every deeper level (21 = W on top, V below).  Same
- * values on all ranks. */
+ * (default 400, maximum 512).  gamma: cycle index on the lattice levels, 1 = V, 2 = W (default); several decimal
+ * digits, most significant first: digit l = visits of lattice level l+1 per visit of level l, the last digit also
+ * serves every deeper level (21 = W on top, V below; 2211 = W on the two finest lattices).  Same values on all ranks. */
 int fs_set_ml_options(fs_context *ctx, int64_t max_points, int dense_points, int gamma);
 /* *levels = number of lattice levels (0 before the first use); cells[3*l..3*l+2] = cells per axis of lattice l
  * (room for 3*14); weights[0] = estimate of lambda_max(D^-1 A) on the mesh, weights[1+l] = on lattice l (room

@@ -132,7 +132,8 @@ class Mirror:
             return lev["dense"] @ b
         A, Dinv, om, P = lev["A"], lev["Dinv"], lev["om"], lev["P"]
         x = om * (Dinv @ b)
-        g = self.gamma if self.gamma < 10 else (self.gamma // 10 if l == 1 else self.gamma % 10)
+        digits = [int(ch) for ch in str(self.gamma)]          # digit k = visits of lattice k+1 per visit of lattice k
+        g = digits[min(l - 1, len(digits) - 1)] if l >= 1 else 1
         for _ in range(g if l >= 1 else 1):
             x = x + P @ self.cycle(l + 1, P.T @ (b - A @ x))
         return x + om * (Dinv @ (b - A @ x))
