@@ -6,15 +6,6 @@
 
 namespace fs {
 
-// First statement of a kernel that may be launched with programmatic stream serialization (launch_k, fs_context.hpp):
-// lets the NEXT kernel of the stream be scheduled as soon as every block of this grid is resident, then waits until
-// the PREVIOUS grid has completed and its writes are visible.  A no-op for plain launches.
-__device__ __forceinline__ void pdl_enter()
-{
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-}
-
 // ---------------------------------------------------------------------------------------------
 // deterministic grid reduction of NV values; returns true in the block that arrives last, with
 // the totals in out[] (valid for thread 0 of that block)

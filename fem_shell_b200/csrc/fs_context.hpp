@@ -250,8 +250,6 @@ struct fs_context {
 
     int sm_count = 148;
     int spmv_blocks_per_sm = 4, vec_blocks_per_sm = 4;
-    // programmatic dependent launch between the kernels of a captured CG iteration (fs_cg_device.cuh pdl_enter)
-    bool use_pdl = false;
 };
 
 namespace fs {
@@ -291,25 +289,6 @@ inline int fail(fs_context *c, int code, const std::string &msg)
                             std::string(#call) + ": " + cudaGetErrorString(e__) + " (" +      \
                                 __FILE__ + ":" + std::to_string(__LINE__) + ")");              \
     } while (0)
-
-// kernel launch with (pdl) or without the programmatic-stream-serialization attribute: inside a stream capture the
-// attribute turns the edge from the preceding kernel node into a programmatic one -- the kernel may be scheduled while
-// its predecessor drains and must call pdl_enter() (fs_cg_device.cuh) before it touches memory
-template <class... P, class... A>
-inline cudaError_t launch_k(bool pdl, void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args)
-{
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kern, P(args)...);
-}
 
 // assembly.cu
 int upload_element_constants(fs_context *c);

@@ -88,7 +88,6 @@ __global__ void __launch_bounds__(256)
 k_f_smooth0(int64_t n6, const double *__restrict__ b, const double *__restrict__ dinv, double omega, double *__restrict__ x,
             const CgState *state, int chk)
 {
-    pdl_enter();
     ML_RETURN_IF_DONE(state, chk);
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n6) return;
@@ -100,7 +99,6 @@ __global__ void __launch_bounds__(192)
 k_f_resid(int64_t n6, const double *__restrict__ b, const double *__restrict__ q, const double *__restrict__ dinv,
           double *__restrict__ r1, double *__restrict__ tv, const CgState *state, int chk)
 {
-    pdl_enter();
     ML_RETURN_IF_DONE(state, chk);
     __shared__ __align__(16) double sh[192];
     const int64_t t = blockIdx.x * (int64_t)192 + threadIdx.x;
@@ -121,7 +119,6 @@ k_f_restrict(const __grid_constant__ LatGeom g, int a0, int a1, const int32_t *_
              const double *__restrict__ xyz_own, const uint8_t *__restrict__ mask_own, const double *__restrict__ r1,
              const double *__restrict__ q, double omega, double *__restrict__ y, const CgState *state, int chk)
 {
-    pdl_enter();
     ML_RETURN_IF_DONE(state, chk);
     const int a = a0 + (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3), sub = threadIdx.x & 7;
     const bool valid = a < a1;  // whole groups of eight share `a`; shuffles below stay inside the group
@@ -158,7 +155,6 @@ __global__ void __launch_bounds__(256)
 k_f_prolong_t(const __grid_constant__ LatGeom g, int64_t n_local, const int32_t *__restrict__ agg, const double *__restrict__ xyz,
               const uint8_t *__restrict__ mask, const double *__restrict__ e, double *__restrict__ tv, const CgState *state, int chk)
 {
-    pdl_enter();
     ML_RETURN_IF_DONE(state, chk);
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n_local) return;
@@ -182,7 +178,6 @@ __global__ void __launch_bounds__(256)
 k_f_prolong_add(int64_t n6, const double *__restrict__ tv, const double *__restrict__ q, const double *__restrict__ dinv,
                 double omega, double *__restrict__ x, int accumulate, const CgState *state, int chk)
 {
-    pdl_enter();
     ML_RETURN_IF_DONE(state, chk);
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n6) return;
@@ -199,7 +194,6 @@ k_f_post_finish(int64_t n6, const double *__restrict__ b, const double *__restri
                 double omega, double *__restrict__ z, double *__restrict__ p, double *partials, unsigned int *counter,
                 CgState *state, double *red, int fin_mode, int chk)
 {
-    pdl_enter();
     ML_RETURN_IF_DONE(state, chk);
     __shared__ __align__(16) double sh[BLOCK];
     static_assert(BLOCK % 6 == 0, "whole nodes per block");
@@ -239,9 +233,9 @@ enum { LAT_RESID = 0, LAT_RSMOOTH = 1, LAT_PADD = 2, LAT_POST = 3 };
 
 #define LAT_STENCIL_LAUNCH(MODE, geom, grid, stream, ...)                                          \
     do {                                                                                           \
-        if ((geom).ns == 9) launch_k(c->use_pdl, k_lat_stencil<MODE, 9>, dim3(grid), dim3(192), 0, stream, __VA_ARGS__);         \
-        else if ((geom).ns == 27) launch_k(c->use_pdl, k_lat_stencil<MODE, 27>, dim3(grid), dim3(192), 0, stream, __VA_ARGS__);  \
-        else launch_k(c->use_pdl, k_lat_stencil<MODE, 3>, dim3(grid), dim3(192), 0, stream, __VA_ARGS__);                        \
+        if ((geom).ns == 9) k_lat_stencil<MODE, 9><<<grid, 192, 0, stream>>>(__VA_ARGS__);         \
+        else if ((geom).ns == 27) k_lat_stencil<MODE, 27><<<grid, 192, 0, stream>>>(__VA_ARGS__);  \
+        else k_lat_stencil<MODE, 3><<<grid, 192, 0, stream>>>(__VA_ARGS__);                        \
     } while (0)
 
 // v = A in, then
@@ -255,7 +249,6 @@ k_lat_stencil(const __grid_constant__ LatGeom g, int c0, int c1, const double *_
               const double *__restrict__ in, const double *aux, double *out1, double *__restrict__ out2, double omega,
               int flag, const CgState *state, int chk)
 {
-    pdl_enter();
     ML_RETURN_IF_DONE(state, chk);
     __shared__ __align__(16) double sh[192];
     const int64_t n6 = 6 * (int64_t)g.n;
@@ -306,7 +299,6 @@ __global__ void __launch_bounds__(256)
 k_lat_smooth0(int64_t t0, int64_t n6, const double *__restrict__ b, const double *__restrict__ dinv, double omega, double *__restrict__ x,
               const CgState *state, int chk)
 {
-    pdl_enter();
     ML_RETURN_IF_DONE(state, chk);
     const int64_t t = t0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // entries [t0, n6)
     if (t >= n6) return;
@@ -320,7 +312,6 @@ __global__ void __launch_bounds__(128)
 k_lat_restrict(const __grid_constant__ LatGeom gc, const __grid_constant__ LatGeom gp, int P0, int P1, int cc0, int cc1,
                const double *__restrict__ s, double *__restrict__ y, const CgState *state, int chk)
 {
-    pdl_enter();
     ML_RETURN_IF_DONE(state, chk);
     const int K = P0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (K >= P1) return;
@@ -350,7 +341,6 @@ __global__ void __launch_bounds__(256)
 k_lat_prolong_t(const __grid_constant__ LatGeom gc, const __grid_constant__ LatGeom gp, int c0, int c1, const double *__restrict__ e,
                 double *__restrict__ tv, const CgState *state, int chk)
 {
-    pdl_enter();
     ML_RETURN_IF_DONE(state, chk);
     const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;   // children [c0, c1)
     if (c >= c1) return;
@@ -370,7 +360,6 @@ k_lat_prolong_t(const __grid_constant__ LatGeom gc, const __grid_constant__ LatG
 __global__ void __launch_bounds__(256)
 k_dense_matvec(int n, const double *__restrict__ Minv, const double *__restrict__ b, double *__restrict__ x, const CgState *state, int chk)
 {
-    pdl_enter();
     ML_RETURN_IF_DONE(state, chk);
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (row >= n) return;
@@ -564,7 +553,6 @@ k_dense_gj_step(int n, int k, double *__restrict__ M, const double *__restrict__
 // y += s (the neighbour's partial sums of a boundary slab; two addends, so the order does not matter)
 __global__ void k_add_into(int64_t n, const double *__restrict__ s, double *__restrict__ y, const CgState *state, int chk)
 {
-    pdl_enter();
     ML_RETURN_IF_DONE(state, chk);
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t < n) y[t] += s[t];
@@ -820,7 +808,7 @@ static int lat_reverse_add(fs_context *c, int l, double *vec, bool up, bool send
     if (recv_it) FS_NCCL_ML(c, nccl().Recv(L.stage.p, slab, ncclDouble, up ? R - 1 : R + 1, comm, c->stream));
     FS_NCCL_ML(c, nccl().GroupEnd());
     if (recv_it)
-        launch_k(c->use_pdl, k_add_into, dim3(nblk((int64_t)slab, 256)), dim3(256), 0, c->stream, (int64_t)slab, L.stage.p, up ? vec + 6 * (size_t)L.c0 : vec + 6 * (size_t)L.c1 - slab,
+        k_add_into<<<nblk((int64_t)slab, 256), 256, 0, c->stream>>>((int64_t)slab, L.stage.p, up ? vec + 6 * (size_t)L.c0 : vec + 6 * (size_t)L.c1 - slab,
                                                                     c->d_state.p, chk);
     return FS_OK;
 }
@@ -838,14 +826,14 @@ static int fine_restrict_chain(fs_context *c, const double *b, double *x, int ch
     const int64_t o6 = 6 * c->own_lo, n6 = 6 * c->n_own;
     int rc = spmv_once(c, x, c->d_q.p, chk != 0);
     if (rc) return rc;
-    launch_k(c->use_pdl, k_f_resid, dim3(nblk(n6, 192)), dim3(192), 0, st, n6, b ? b + o6 : nullptr, c->d_q.p + o6, c->d_minv.p, m.d_r1.p + o6, m.d_t.p + o6, st_of(c), chk);
+    k_f_resid<<<nblk(n6, 192), 192, 0, st>>>(n6, b ? b + o6 : nullptr, c->d_q.p + o6, c->d_minv.p, m.d_r1.p + o6, m.d_t.p + o6, st_of(c), chk);
     rc = spmv_once(c, m.d_t.p, c->d_q.p, chk != 0);
     if (rc) return rc;
     MlLevelBuf &L1 = m.lat[0];
     const LatGeom &g1 = L1.g;
     // distributed first lattice: the owned nodes reach the rank's own slabs and the first slab of the next rank
     const int a0 = L1.dist ? L1.c0 : 0, a1 = L1.dist ? std::min(L1.s1 + 1, L1.n_slabs) * L1.slab_len : g1.n;
-    launch_k(c->use_pdl, k_f_restrict, dim3(nblk(8 * (int64_t)(a1 - a0), 256)), dim3(256), 0, st, g1, a0, a1, m.d_sup_ptr.p, m.d_sup_node.p, c->d_xyz.p + 3 * c->own_lo,
+    k_f_restrict<<<nblk(8 * (int64_t)(a1 - a0), 256), 256, 0, st>>>(g1, a0, a1, m.d_sup_ptr.p, m.d_sup_node.p, c->d_xyz.p + 3 * c->own_lo,
                                                                    c->d_mask.p + c->own_lo, m.d_r1.p + o6, c->d_q.p + o6, m.omega0,
                                                                    L1.b.p, st_of(c), chk);
     if (L1.dist) return lat_reverse_add(c, 0, L1.b.p, true, c->rank < c->world - 1, c->rank > 0, chk);
@@ -865,10 +853,10 @@ static int fine_prolong_chain(fs_context *c, double *e, double *x, bool accumula
         int rc = lat_halo(c, 0, e);
         if (rc) return rc;
     }
-    launch_k(c->use_pdl, k_f_prolong_t, dim3(nblk(c->n_local, 256)), dim3(256), 0, st, m.lat[0].g, c->n_local, m.d_agg.p, c->d_xyz.p, c->d_mask.p, e, m.d_t.p, st_of(c), chk);
+    k_f_prolong_t<<<nblk(c->n_local, 256), 256, 0, st>>>(m.lat[0].g, c->n_local, m.d_agg.p, c->d_xyz.p, c->d_mask.p, e, m.d_t.p, st_of(c), chk);
     int rc = spmv_local(c, m.d_t.p, c->d_q.p, chk != 0);  // t is complete on owned and halo nodes: no exchange
     if (rc) return rc;
-    launch_k(c->use_pdl, k_f_prolong_add, dim3(nblk(n6, 256)), dim3(256), 0, st, n6, m.d_t.p + o6, c->d_q.p + o6, c->d_minv.p, m.omega0, x + o6, accumulate ? 1 : 0, st_of(c), chk);
+    k_f_prolong_add<<<nblk(n6, 256), 256, 0, st>>>(n6, m.d_t.p + o6, c->d_q.p + o6, c->d_minv.p, m.omega0, x + o6, accumulate ? 1 : 0, st_of(c), chk);
     return FS_OK;
 }
 
@@ -886,13 +874,13 @@ static int lat_restrict_chain(fs_context *c, int l, const double *b, double *x, 
     if (rc) return rc;
     LAT_STENCIL_LAUNCH(LAT_RSMOOTH, L.g, nblk(n6, 192), st, L.g, L.c0, L.c1, L.A.p, L.dinv.p, L.t.p, L.r.p, L.r.p, nullptr, L.omega, 0, st_of(c), chk);
     if (!L.dist) {
-        launch_k(c->use_pdl, k_lat_restrict, dim3(nblk(N.g.n, 128)), dim3(128), 0, st, L.g, N.g, 0, N.g.n, 0, L.g.n, L.r.p, N.b.p, st_of(c), chk);
+        k_lat_restrict<<<nblk(N.g.n, 128), 128, 0, st>>>(L.g, N.g, 0, N.g.n, 0, L.g.n, L.r.p, N.b.p, st_of(c), chk);
         return FS_OK;
     }
     // parents with at least one child among this rank's slabs; the sum is partial where the children are split
     const int P0 = (L.s0 / 3) * N.slab_len, P1 = ((L.s1 + 2) / 3) * N.slab_len;
     if (!N.dist) FS_CUDA(c, cudaMemsetAsync(N.b.p, 0, sizeof(double) * 6 * (size_t)N.g.n, st));
-    launch_k(c->use_pdl, k_lat_restrict, dim3(nblk(P1 - P0, 128)), dim3(128), 0, st, L.g, N.g, P0, P1, L.c0, L.c1, L.r.p, N.b.p, st_of(c), chk);
+    k_lat_restrict<<<nblk(P1 - P0, 128), 128, 0, st>>>(L.g, N.g, P0, P1, L.c0, L.c1, L.r.p, N.b.p, st_of(c), chk);
     if (N.dist) {  // the parent slab split with the rank below belongs to that rank
         const std::vector<int> &S = m.bounds[l];
         const int R = c->rank, W = c->world;
@@ -915,7 +903,7 @@ static int lat_prolong_chain(fs_context *c, int l, double *e, double *x, bool ac
     }
     // t = P_t e on this rank's cells and one slab beyond on either side, so that the stencil below needs no exchange
     const int t0 = L.dist ? std::max(L.c0 - L.slab_len, 0) : 0, t1 = L.dist ? std::min(L.c1 + L.slab_len, L.g.n) : L.g.n;
-    launch_k(c->use_pdl, k_lat_prolong_t, dim3(nblk(t1 - t0, 256)), dim3(256), 0, st, L.g, N.g, t0, t1, e, L.t.p, st_of(c), chk);
+    k_lat_prolong_t<<<nblk(t1 - t0, 256), 256, 0, st>>>(L.g, N.g, t0, t1, e, L.t.p, st_of(c), chk);
     LAT_STENCIL_LAUNCH(LAT_PADD, L.g, nblk(n6, 192), st, L.g, L.c0, L.c1, L.A.p, L.dinv.p, L.t.p, nullptr, x, nullptr, L.omega, accumulate ? 1 : 0, st_of(c), chk);
     return FS_OK;
 }
@@ -938,12 +926,14 @@ static int lat_cycle(fs_context *c, int l, int chk, double **out)
     *out = L.xb.p;
     if (L.dense) {
         const int64_t n6 = 6 * (int64_t)L.g.n;
-        launch_k(c->use_pdl, k_dense_matvec, dim3(nblk(32 * n6, 256)), dim3(256), 0, st, (int)n6, L.minv.p, L.b.p, L.xb.p, st_of(c), chk);
+        k_dense_matvec<<<nblk(32 * n6, 256), 256, 0, st>>>((int)n6, L.minv.p, L.b.p, L.xb.p, st_of(c), chk);
         return FS_OK;
     }
     const int64_t t0 = 6 * (int64_t)L.c0, t1 = 6 * (int64_t)L.c1;
-    launch_k(c->use_pdl, k_lat_smooth0, dim3(nblk(t1 - t0, 256)), dim3(256), 0, st, t0, t1, L.b.p, L.dinv.p, L.omega, L.x.p, st_of(c), chk);
-    const int n_visits = ml_visits(c->ml_gamma, l);
+    k_lat_smooth0<<<nblk(t1 - t0, 256), 256, 0, st>>>(t0, t1, L.b.p, L.dinv.p, L.omega, L.x.p, st_of(c), chk);
+    // a dense level is an exact solve of the Galerkin system: after one visit the restricted residual is zero, a second
+    // visit would compute a zero correction (same iteration counts, measured: profiles/r02m_ml_cycle_sweep.json)
+    const int n_visits = m.lat[l + 1].dense ? 1 : ml_visits(c->ml_gamma, l);
     for (int gmm = 0; gmm < n_visits; gmm++) {
         int rc = lat_restrict_chain(c, l, L.b.p, L.x.p, chk);
         if (rc) return rc;
@@ -1003,7 +993,7 @@ static int fine_lambda(fs_context *c, double *lam)
         rc = spmv_once(c, v, c->d_q.p, false);
         if (rc) return rc;
         // t = -D^-1 A v ; r1 = -A v
-        launch_k(c->use_pdl, k_f_resid, dim3(nblk(n6, 192)), dim3(192), 0, st, n6, nullptr, c->d_q.p + o6, c->d_minv.p, m.d_r1.p + o6, m.d_t.p + o6, st_of(c), 0);
+        k_f_resid<<<nblk(n6, 192), 192, 0, st>>>(n6, nullptr, c->d_q.p + o6, c->d_minv.p, m.d_r1.p + o6, m.d_t.p + o6, st_of(c), 0);
         k_norm2<256><<<grid, 256, 0, st>>>(n6, v + o6, c->d_partials.p, c->d_counter.p, m.d_scalar.p);
         k_norm2<256><<<grid, 256, 0, st>>>(n6, m.d_t.p + o6, c->d_partials.p, c->d_counter.p, m.d_scalar.p + 1);
         double h[2];
@@ -1158,7 +1148,7 @@ int ml_enqueue_apply(fs_context *c, bool init, double *red, int fin, int vec_gri
     cudaStream_t st = c->stream;
     const int64_t o6 = 6 * c->own_lo, n6 = 6 * c->n_own;
     const int chk = (init || !red) ? 0 : 1;
-    launch_k(c->use_pdl, k_f_smooth0, dim3(nblk(n6, 256)), dim3(256), 0, st, n6, c->d_r.p + o6, c->d_minv.p, m.omega0, c->d_z.p + o6, st_of(c), chk);
+    k_f_smooth0<<<nblk(n6, 256), 256, 0, st>>>(n6, c->d_r.p + o6, c->d_minv.p, m.omega0, c->d_z.p + o6, st_of(c), chk);
     auto mark = [&](int k) { if (c->prof.on) cudaEventRecord(c->prof.ev[k], st); };
     int rc = fine_restrict_chain(c, c->d_r.p, c->d_z.p, chk);
     if (rc) return rc;
@@ -1175,13 +1165,13 @@ int ml_enqueue_apply(fs_context *c, bool init, double *red, int fin, int vec_gri
     constexpr int PB = 192;
     const int grid = std::max(1, vec_grid);
     if (!red)
-        launch_k(c->use_pdl, k_f_post_finish<false, false, PB>, dim3(grid), dim3(PB), 0, st, n6, c->d_r.p + o6, c->d_q.p + o6, c->d_minv.p, m.omega0, c->d_z.p + o6, nullptr,
+        k_f_post_finish<false, false, PB><<<grid, PB, 0, st>>>(n6, c->d_r.p + o6, c->d_q.p + o6, c->d_minv.p, m.omega0, c->d_z.p + o6, nullptr,
                                                                  c->d_partials.p, c->d_counter.p, c->d_state.p, nullptr, fin, 0);
     else if (init)
-        launch_k(c->use_pdl, k_f_post_finish<true, true, PB>, dim3(grid), dim3(PB), 0, st, n6, c->d_r.p + o6, c->d_q.p + o6, c->d_minv.p, m.omega0, c->d_z.p + o6, c->d_p.p + o6,
+        k_f_post_finish<true, true, PB><<<grid, PB, 0, st>>>(n6, c->d_r.p + o6, c->d_q.p + o6, c->d_minv.p, m.omega0, c->d_z.p + o6, c->d_p.p + o6,
                                                                c->d_partials.p, c->d_counter.p, c->d_state.p, red, fin, 0);
     else
-        launch_k(c->use_pdl, k_f_post_finish<false, true, PB>, dim3(grid), dim3(PB), 0, st, n6, c->d_r.p + o6, c->d_q.p + o6, c->d_minv.p, m.omega0, c->d_z.p + o6, c->d_p.p + o6,
+        k_f_post_finish<false, true, PB><<<grid, PB, 0, st>>>(n6, c->d_r.p + o6, c->d_q.p + o6, c->d_minv.p, m.omega0, c->d_z.p + o6, c->d_p.p + o6,
                                                                 c->d_partials.p, c->d_counter.p, c->d_state.p, red, fin, 1);
     return FS_OK;
 }

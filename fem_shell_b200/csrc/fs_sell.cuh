@@ -156,7 +156,6 @@ k_spmv_sell(int n_own, int own_lo, int n_slices, const int32_t *__restrict__ spt
             const double *x_own, double *partials, unsigned int *counter, CgState *state,
             double *red, int fin_mode, PeerWin *pw, const int32_t *__restrict__ hflag, const __grid_constant__ PlaneQ q)
 {
-    pdl_enter();
     if (WITH_DOT ? state->done : (state && state->done)) return;  // without the dot product: checked only when a state is passed
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);

@@ -170,7 +170,6 @@ k_update(int64_t n_own, double *__restrict__ x, double *__restrict__ r, const do
          const double *__restrict__ q, double *__restrict__ z, const double *__restrict__ minv,
          double *partials, unsigned int *counter, CgState *state, double *red, int fin_mode, PeerWin *pw)
 {
-    pdl_enter();
     if (state->done) return;
     double alpha;
     if (pw) {  // p.Ap arrives as one partial per rank in the mailbox: finish the sum here (fs_peer.cuh)
@@ -288,7 +287,6 @@ k_direction(int64_t n_own, const double *__restrict__ z, double *__restrict__ p,
             unsigned int *counter, const __grid_constant__ PushArgs push)
 {
     // after convergence x is final; p is not needed any more
-    pdl_enter();
     if (state->done) return;
     double beta, t[2] = {0.0, 0.0};
     if (pw) {  // r.z and the norm arrive as per-rank partials: finish the sums, beta from the OLD r.z
@@ -543,9 +541,9 @@ static void launch_sell_k(fs_context *c, int grid, const double *x, double *y_ow
     PlaneQ q;
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) q.m[i][j] = c->plane_Q[3 * i + j];
-    launch_k(c->use_pdl && WITH_DOT, k_spmv_sell<MASK, WITH_DOT, SELL_BLOCK, SELL_MINB, PEER, ROT>, dim3(grid), dim3(SELL_BLOCK), 0, c->stream,
-             (int)c->n_own, (int)c->own_lo, (int)c->sell_slices, c->d_sell_sptr.p, c->d_sell_adj.p, c->d_sell_vals.p, x, y_own, x_own,
-             c->d_partials.p, c->d_counter.p, state, red, fin_mode, pw, PEER ? c->d_sell_hflag.p : nullptr, q);
+    k_spmv_sell<MASK, WITH_DOT, SELL_BLOCK, SELL_MINB, PEER, ROT><<<grid, SELL_BLOCK, 0, c->stream>>>(
+        (int)c->n_own, (int)c->own_lo, (int)c->sell_slices, c->d_sell_sptr.p, c->d_sell_adj.p, c->d_sell_vals.p, x, y_own, x_own,
+        c->d_partials.p, c->d_counter.p, state, red, fin_mode, pw, PEER ? c->d_sell_hflag.p : nullptr, q);
 }
 
 template <unsigned long long MASK, bool WITH_DOT>
@@ -743,14 +741,14 @@ static int enqueue_iteration(fs_context *c, double *red, int sg, int vg)
         mark(6);
         return FS_OK;
     }
-    launch_k(c->use_pdl, k_update<PC == 3 ? 1 : PC, NORM, 256>, dim3(vg), dim3(256), 0, c->stream, c->n_own, c->d_x.p + o6, c->d_r.p + o6,
-             c->d_p.p + o6, c->d_q.p + o6, c->d_z.p + o6, c->d_minv.p, c->d_partials.p, c->d_counter.p, c->d_state.p, red + 4, fin, pw);
+    k_update<PC == 3 ? 1 : PC, NORM, 256><<<vg, 256, 0, c->stream>>>(c->n_own, c->d_x.p + o6, c->d_r.p + o6, c->d_p.p + o6,
+                                                       c->d_q.p + o6, c->d_z.p + o6, c->d_minv.p, c->d_partials.p,
+                                                       c->d_counter.p, c->d_state.p, red + 4, fin, pw);
     if (fin == FIN_RED) {
         FS_NCCL(c, nccl().AllReduce(red + 4, red + 4, 2, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
         k_finalize<<<1, 1, 0, c->stream>>>(c->d_state.p, red + 4, 2);
     }
-    launch_k(c->use_pdl, k_direction<256>, dim3(vg + push.n_push_blocks), dim3(256), 0, c->stream, c->n_own, c->d_z.p + o6, c->d_p.p + o6, c->d_state.p, pw,
-             c->d_counter.p, push);
+    k_direction<256><<<vg + push.n_push_blocks, 256, 0, c->stream>>>(c->n_own, c->d_z.p + o6, c->d_p.p + o6, c->d_state.p, pw, c->d_counter.p, push);
     return FS_OK;
 }
 
@@ -827,8 +825,7 @@ static int run_pcg(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
         pf.on = false;
     } else {
     constexpr int GRAPH_ITERS = (PC == 3) ? 1 : 8;  // a multilevel iteration is ~100 launches already
-    if (const char *e = getenv("FS_PDL")) c->use_pdl = atoi(e) != 0;
-    const int key = PC * 2 + NORM + (c->sell_active ? 8 * (1 + c->sell_kind) : 0) + (peer ? 64 : 0) + (c->use_pdl ? 128 : 0);
+    const int key = PC * 2 + NORM + (c->sell_active ? 8 * (1 + c->sell_kind) : 0) + (peer ? 64 : 0);
     if (!c->cg_graph_exec || c->cg_graph_key != key || c->cg_graph_red != red) {
         PhaseTimer tmc("run_pcg");
         if (c->cg_graph_exec) cudaGraphExecDestroy(c->cg_graph_exec);

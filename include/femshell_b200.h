@@ -239,7 +239,9 @@ int fs_bench_launch_chain(fs_context *ctx, int links, int n, int reps, double ou
  * all-reduced once per iteration).  dense_points: a lattice with at most this many cells is inverted densely
  * (default 400, maximum 512).  gamma: cycle index on the lattice levels, 1 = V, 2 = W (default); several decimal
  * digits, most significant first: digit l = visits of lattice level l+1 per visit of level l, the last digit also
- * serves every deeper level (21 = W on top, V below; 2211 = W on the two finest lattices).  Same values on all ranks. */
+ * serves every deeper level (21 = W on top, V below; 2211 = W on the two finest lattices).  The dense coarsest level is
+ * always visited once per visit of the level above (it is an exact solve: a second visit computes a zero correction).
+ * Same values on all ranks. */
 int fs_set_ml_options(fs_context *ctx, int64_t max_points, int dense_points, int gamma);
 /* *levels = number of lattice levels (0 before the first use); cells[3*l..3*l+2] = cells per axis of lattice l
  * (room for 3*14); weights[0] = estimate of lambda_max(D^-1 A) on the mesh, weights[1+l] = on lattice l (room

@@ -134,6 +134,8 @@ class Mirror:
         x = om * (Dinv @ b)
         digits = [int(ch) for ch in str(self.gamma)]          # digit k = visits of lattice k+1 per visit of lattice k
         g = digits[min(l - 1, len(digits) - 1)] if l >= 1 else 1
+        if "dense" in self.levels[l + 1]:
+            g = 1                     # exact coarse solve: a second visit computes a zero correction (fs_mlpc.cu lat_cycle)
         for _ in range(g if l >= 1 else 1):
             x = x + P @ self.cycle(l + 1, P.T @ (b - A @ x))
         return x + om * (Dinv @ (b - A @ x))

@@ -239,22 +239,6 @@ def test_pcg_same_iterations_as_oracle(fso, fsb, pc, norm):
     assert np.linalg.norm(u - uo) <= 1e-6 * np.linalg.norm(uo)
 
 
-@pytest.mark.parametrize("pc", [1, 2])
-def test_programmatic_dependent_launch_changes_nothing(fsb, pc, monkeypatch):
-    """FS_PDL=1: the kernels of the captured CG iteration are chained by programmatic dependent launch (each may be
-    scheduled while its predecessor drains, fs_cg_device.cuh pdl_enter); iteration count and solution stay bit-identical"""
-    m = fsb.meshgen("q", 120, 90, 0, 0, 10, 7.5, (1, 1, 1, 1), 300.0, 2, 1)
-    s = gpu_system(fsb, m, 0.3, 1e7, 0.5, loads=m["forces"])
-    monkeypatch.setenv("FS_PDL", "0")
-    a = s.solve(rtol=1e-9, max_its=100000, pc=pc, warm_start=False)
-    ua = s.solution()
-    monkeypatch.setenv("FS_PDL", "1")
-    b = s.solve(rtol=1e-9, max_its=100000, pc=pc, warm_start=False)
-    ub = s.solution()
-    assert a.status == b.status == 0 and a.iterations == b.iterations
-    assert np.array_equal(ua, ub)
-
-
 def test_mixed_folded_cantilever_solution(fso, fsb):
     for skew in (0.0, 0.35):
         m = meshes.folded_cantilever(skew=skew)

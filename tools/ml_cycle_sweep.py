@@ -27,7 +27,7 @@ s.set_nodal_loads(m["forces"])
 s.assemble()
 s.build_rhs(1.0)
 rows = []
-for gamma in (2, 21, 22, 31, 1, 32):
+for gamma in [int(g) for g in os.environ.get("FS_SWEEP_GAMMAS", "2,21,22,31,1,32").split(",")]:
     s.set_ml_options(gamma=gamma)
     s.solve(rtol=1e-8, max_its=5000, pc=fsb.PC_MLRBM, warm_start=False, allow_not_converged=True)   # set-up + capture
     torch.cuda.synchronize()
