@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = [
     "fs_set_nodal_loads", "fs_set_interface_loads", "fs_build_rhs", "fs_assemble", "fs_get_assembly_path", "fs_solve",
     "fs_get_solution", "fs_get_solution_owned", "fs_recover_resultants", "fs_solve_host", "fs_interface_nodes", "fs_step", "fs_commit_step", "fs_get_sizes",
     "fs_export_dof_order", "fs_export_csr", "fs_export_rhs", "fs_debug_element_matrices", "fs_spmv_host",
-    "fs_bench_spmv", "fs_bench_fp64_peak", "fs_bench_contraction", "fs_bench_launch_chain", "fs_set_ml_options", "fs_get_ml_info", "fs_get_ml_dist_levels", "fs_get_ml_profile", "fs_debug_ml_level", "fs_apply_mlrbm_host", "fs_partition_plan", "fs_gather_plan", "fs_meshgen", "fs_read_xda", "fs_read_mesh", "fs_write_xdr", "fs_read_forces", "fs_write_xda",
+    "fs_bench_spmv", "fs_bench_fp64_peak", "fs_bench_contraction", "fs_bench_launch_chain", "fs_set_ml_options", "fs_get_ml_info", "fs_get_ml_dist_levels", "fs_get_ml_compact_levels", "fs_get_ml_profile", "fs_debug_ml_level", "fs_apply_mlrbm_host", "fs_partition_plan", "fs_gather_plan", "fs_meshgen", "fs_read_xda", "fs_read_mesh", "fs_write_xdr", "fs_read_forces", "fs_write_xda",
 ]
 
 
@@ -422,7 +422,9 @@ class FemShell:
         n = int(lv.value)
         nd = C.c_int64(0)
         self._ck(self.lib.fs_get_ml_dist_levels(self.ctx, C.byref(nd)))
-        return {"levels": n, "distributed_levels": int(nd.value), "cells": [tuple(int(cells[3 * l + d]) for d in range(3)) for l in range(n)],
+        nc = C.c_int64(0)
+        self._ck(self.lib.fs_get_ml_compact_levels(self.ctx, C.byref(nc)))
+        return {"levels": n, "distributed_levels": int(nd.value), "compact_levels": int(nc.value), "cells": [tuple(int(cells[3 * l + d]) for d in range(3)) for l in range(n)],
                 "lambda": [float(w[i]) for i in range(n + 1)], "setup_ms": float(ms.value)}
 
     def bench_launch_chain(self, links=200, n=65536, reps=20):

@@ -947,6 +947,16 @@ int fs_get_ml_dist_levels(fs_context *c, int64_t *n_dist)
     return FS_OK;
 }
 
+int fs_get_ml_compact_levels(fs_context *c, int64_t *n_compact)
+{
+    FS_CHECK_CTX(c);
+    if (!n_compact) return fail(c, FS_ERR_ARG, "null output");
+    *n_compact = 0;
+    if (c->ml_values_ready)
+        for (int l = 0; l < c->ml.n_lat; l++) *n_compact += c->ml.lat[l].compact_kind >= 0 ? 1 : 0;
+    return FS_OK;
+}
+
 int fs_get_ml_profile(fs_context *c, double ms[8], int64_t *iterations, int reset)
 {
     FS_CHECK_CTX(c);

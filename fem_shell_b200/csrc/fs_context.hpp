@@ -81,6 +81,11 @@ struct MlLevelBuf {
     DevBuf<double> A;            // ns * 36 * n stencil values (structure of arrays, fs_mlpc.cu)
     DevBuf<double> dinv;         // 36 * n pseudo-inverses of the diagonal blocks
     DevBuf<double> minv;         // (6n)^2, dense level only
+    // shells in a coordinate plane: in-plane and out-of-plane modes never couple, on any level.  Ac / Dc hold the 18
+    // structurally non-zero entries of every 6x6 block, one plane of n values per (slot, item): thread = cell streams
+    // them with unit stride (k_lat_stencil_c); A / dinv stay as the probing wrote them (fs_debug_ml_level)
+    DevBuf<double> Ac, Dc;       // ns * 18 * n, 18 * n
+    int compact_kind = -1;       // -1: not compacted; else the mask kind (0 xy, 1 xz, 2 yz)
     DevBuf<double> x, xb, b, r, t;  // 6n each
     double omega = 0.0, lambda = 0.0;
     // distribution over the ranks (fs_mlpc.cu "distributed lattice levels"): cells are dealt out in slabs (all cells

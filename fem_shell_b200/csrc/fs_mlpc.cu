@@ -30,6 +30,7 @@
 #include "fs_context.hpp"
 #include "fs_mlpc.cuh"
 #include "fs_nccl.hpp"
+#include "fs_sell.cuh"
 
 namespace fs {
 
@@ -293,6 +294,135 @@ k_lat_stencil(const __grid_constant__ LatGeom g, int c0, int c1, const double *_
     } else {
         out1[t] = in[t] + omega * dw;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// lattice blocks of a shell lying in a coordinate plane: the rigid-body modes split into the in-plane class (two
+// translations + the rotation about the normal) and the out-of-plane class (deflection + two tilts), which never
+// couple -- 18 of 36 entries.  (The mesh blocks have 14: there the drilling rotation couples to nothing, but on a
+// lattice the rotation about the normal moves the in-plane translations of the aggregate.)
+constexpr unsigned long long LAT_MASK_XY = sell_group(0, 1, 5) | sell_group(2, 3, 4);
+constexpr unsigned long long LAT_MASK_XZ = sell_group(0, 2, 4) | sell_group(1, 3, 5);
+constexpr unsigned long long LAT_MASK_YZ = sell_group(1, 2, 3) | sell_group(0, 4, 5);
+constexpr int LAT_NZ = 18;
+static_assert(sell_popcount(LAT_MASK_XY) == LAT_NZ && sell_popcount(LAT_MASK_XZ) == LAT_NZ && sell_popcount(LAT_MASK_YZ) == LAT_NZ, "lattice masks");
+
+// the same four operations on the compacted stencil of a shell lying in a coordinate plane: thread = cell (all six
+// rows), 18 value planes per slot instead of 36, every load of a warp one contiguous line.  Skipped entries are exact
+// zeros (never written by the paired probing, kept by ginv6), and the sums run in the order of k_lat_stencil /
+// dinv_row with those zeros spelled out, so the results are bit-identical to the full-block kernels.
+// ---------------------------------------------------------------------------------------------
+template <unsigned long long MASK>
+__device__ __forceinline__ void dinv_apply_c(const double *__restrict__ Dc, int64_t n, int64_t p, const double w[6], double dw[6])
+{
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
+        double s = 0.0;
+#pragma unroll
+        for (int h = 0; h < 3; h++) {   // dinv_row's pairs; a structural zero is the literal 0.0
+            const double dx = (MASK & sell_bit(a, 2 * h)) ? Dc[(size_t)sell_item(MASK, a, 2 * h) * n + p] : 0.0;
+            const double dy = (MASK & sell_bit(a, 2 * h + 1)) ? Dc[(size_t)sell_item(MASK, a, 2 * h + 1) * n + p] : 0.0;
+            if ((MASK & sell_bit(a, 2 * h)) || (MASK & sell_bit(a, 2 * h + 1))) s += dx * w[2 * h] + dy * w[2 * h + 1];
+        }
+        dw[a] = s;
+    }
+}
+
+template <int MODE, int NS, unsigned long long MASK>
+__global__ void __launch_bounds__(128)
+k_lat_stencil_c(const __grid_constant__ LatGeom g, int c0, int c1, const double *__restrict__ Ac, const double *__restrict__ Dc,
+                const double *__restrict__ in, const double *aux, double *out1, double *__restrict__ out2, double omega,
+                int flag, const CgState *state, int chk)
+{
+    ML_RETURN_IF_DONE(state, chk);
+    constexpr int NZ = sell_popcount(MASK);
+    const int p = c0 + blockIdx.x * 128 + threadIdx.x;   // cells [c0, c1): this rank's slabs
+    if (p >= c1) return;
+    const int64_t n = g.n;
+    int k[3];
+    lat_unindex(g, p, k);
+    double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        int o[3];
+        lat_stencil_off(g, s, o);
+        const int kk[3] = {k[0] + o[0], k[1] + o[1], k[2] + o[2]};
+        const bool inside = kk[0] >= 0 && kk[0] < g.np[0] && kk[1] >= 0 && kk[1] < g.np[1] && kk[2] >= 0 && kk[2] < g.np[2];
+        double xv[6];
+        load6(in + 6 * (size_t)(inside ? lat_index(g, kk) : p), xv);
+        const double *as = Ac + (size_t)(NZ * s) * n + p;
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int b = 0; b < 6; b++)
+                if (MASK & sell_bit(a, b)) v[a] += as[(size_t)sell_item(MASK, a, b) * n] * xv[b];
+    }
+    const size_t at = 6 * (size_t)p;
+    if (MODE == LAT_RSMOOTH) {
+        double av[6], o6[6];
+        load6(aux + at, av);
+#pragma unroll
+        for (int a = 0; a < 6; a++) o6[a] = av[a] - omega * v[a];
+        store6(out1 + at, o6);
+        return;
+    }
+    double w[6], dw[6];
+    if (MODE == LAT_RESID || MODE == LAT_POST) {
+        double av[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (aux) load6(aux + at, av);
+#pragma unroll
+        for (int a = 0; a < 6; a++) w[a] = av[a] - v[a];
+    } else {
+#pragma unroll
+        for (int a = 0; a < 6; a++) w[a] = v[a];
+    }
+    dinv_apply_c<MASK>(Dc, n, p, w, dw);
+    if (MODE == LAT_RESID) {
+        store6(out1 + at, w);
+        store6(out2 + at, dw);
+        return;
+    }
+    double iv[6], o6[6];
+    load6(in + at, iv);
+    if (MODE == LAT_PADD) {
+        double prev[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (flag) load6(out1 + at, prev);
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            const double add = iv[a] - omega * dw[a];
+            o6[a] = flag ? prev[a] + add : add;
+        }
+    } else {
+#pragma unroll
+        for (int a = 0; a < 6; a++) o6[a] = iv[a] + omega * dw[a];
+    }
+    store6(out1 + at, o6);
+}
+
+// A / dinv (as probed) -> Ac / Dc for the cells [c0, c1); *bad is set when an entry outside the mask is not an exact zero
+template <unsigned long long MASK>
+__global__ void k_lat_compact(const __grid_constant__ LatGeom g, int c0, int c1, const double *__restrict__ A, const double *__restrict__ dinv,
+                              double *__restrict__ Ac, double *__restrict__ Dc, int *bad)
+{
+    constexpr int NZ = sell_popcount(MASK);
+    const int p = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= c1) return;
+    const int64_t n = g.n, n6 = 6 * n;
+    bool off = false;
+    for (int s = 0; s < g.ns; s++)
+        for (int a = 0; a < 6; a++)
+            for (int b = 0; b < 6; b++) {
+                const double val = A[(size_t)(6 * s + b) * n6 + 6 * (size_t)p + a];
+                if (MASK & sell_bit(a, b)) Ac[(size_t)(NZ * s + sell_item(MASK, a, b)) * n + p] = val;
+                else off |= val != 0.0;
+            }
+    for (int a = 0; a < 6; a++)
+        for (int b = 0; b < 6; b++) {
+            const double val = dinv[36 * (size_t)p + 6 * a + b];
+            if (MASK & sell_bit(a, b)) Dc[(size_t)sell_item(MASK, a, b) * n + p] = val;
+            else off |= val != 0.0;
+        }
+    if (off) *bad = 1;
 }
 
 __global__ void __launch_bounds__(256)
@@ -813,6 +943,29 @@ static int lat_reverse_add(fs_context *c, int l, double *vec, bool up, bool send
     return FS_OK;
 }
 
+// one stencil operation on this rank's cells of level L, on whichever copy of the stencil the level iterates on
+template <int MODE, unsigned long long MASK>
+static void lat_stencil_launch_c(MlLevelBuf &L, cudaStream_t st, const double *in, const double *aux, double *out1, double *out2, double omega,
+                                 int flag, const CgState *state, int chk)
+{
+    const unsigned grid = nblk((int64_t)(L.c1 - L.c0), 128);
+    if (L.g.ns == 9) k_lat_stencil_c<MODE, 9, MASK><<<grid, 128, 0, st>>>(L.g, L.c0, L.c1, L.Ac.p, L.Dc.p, in, aux, out1, out2, omega, flag, state, chk);
+    else k_lat_stencil_c<MODE, 3, MASK><<<grid, 128, 0, st>>>(L.g, L.c0, L.c1, L.Ac.p, L.Dc.p, in, aux, out1, out2, omega, flag, state, chk);
+}
+
+template <int MODE>
+static void lat_stencil_launch(fs_context *c, MlLevelBuf &L, const double *in, const double *aux, double *out1, double *out2, double omega, int flag,
+                               int chk)
+{
+    cudaStream_t st = c->stream;
+    const CgState *state = c->d_state.p;
+    if (L.compact_kind == 0) return lat_stencil_launch_c<MODE, LAT_MASK_XY>(L, st, in, aux, out1, out2, omega, flag, state, chk);
+    if (L.compact_kind == 1) return lat_stencil_launch_c<MODE, LAT_MASK_XZ>(L, st, in, aux, out1, out2, omega, flag, state, chk);
+    if (L.compact_kind == 2) return lat_stencil_launch_c<MODE, LAT_MASK_YZ>(L, st, in, aux, out1, out2, omega, flag, state, chk);
+    const int64_t n6 = 6 * (int64_t)(L.c1 - L.c0);
+    LAT_STENCIL_LAUNCH(MODE, L.g, nblk(n6, 192), st, L.g, L.c0, L.c1, L.A.p, L.dinv.p, in, aux, out1, out2, omega, flag, state, chk);
+}
+
 // ---------------------------------------------------------------------------------------------
 // the building blocks of the cycle (enqueue only)
 // ---------------------------------------------------------------------------------------------
@@ -869,10 +1022,10 @@ static int lat_restrict_chain(fs_context *c, int l, const double *b, double *x, 
     const int64_t n6 = 6 * (int64_t)(L.c1 - L.c0);
     int rc = lat_halo(c, l, x);
     if (rc) return rc;
-    LAT_STENCIL_LAUNCH(LAT_RESID, L.g, nblk(n6, 192), st, L.g, L.c0, L.c1, L.A.p, L.dinv.p, x, b, L.r.p, L.t.p, L.omega, 0, st_of(c), chk);
+    lat_stencil_launch<LAT_RESID>(c, L, x, b, L.r.p, L.t.p, L.omega, 0, chk);
     rc = lat_halo(c, l, L.t.p);
     if (rc) return rc;
-    LAT_STENCIL_LAUNCH(LAT_RSMOOTH, L.g, nblk(n6, 192), st, L.g, L.c0, L.c1, L.A.p, L.dinv.p, L.t.p, L.r.p, L.r.p, nullptr, L.omega, 0, st_of(c), chk);
+    lat_stencil_launch<LAT_RSMOOTH>(c, L, L.t.p, L.r.p, L.r.p, nullptr, L.omega, 0, chk);
     if (!L.dist) {
         k_lat_restrict<<<nblk(N.g.n, 128), 128, 0, st>>>(L.g, N.g, 0, N.g.n, 0, L.g.n, L.r.p, N.b.p, st_of(c), chk);
         return FS_OK;
@@ -904,7 +1057,7 @@ static int lat_prolong_chain(fs_context *c, int l, double *e, double *x, bool ac
     // t = P_t e on this rank's cells and one slab beyond on either side, so that the stencil below needs no exchange
     const int t0 = L.dist ? std::max(L.c0 - L.slab_len, 0) : 0, t1 = L.dist ? std::min(L.c1 + L.slab_len, L.g.n) : L.g.n;
     k_lat_prolong_t<<<nblk(t1 - t0, 256), 256, 0, st>>>(L.g, N.g, t0, t1, e, L.t.p, st_of(c), chk);
-    LAT_STENCIL_LAUNCH(LAT_PADD, L.g, nblk(n6, 192), st, L.g, L.c0, L.c1, L.A.p, L.dinv.p, L.t.p, nullptr, x, nullptr, L.omega, accumulate ? 1 : 0, st_of(c), chk);
+    lat_stencil_launch<LAT_PADD>(c, L, L.t.p, nullptr, x, nullptr, L.omega, accumulate ? 1 : 0, chk);
     return FS_OK;
 }
 
@@ -947,7 +1100,7 @@ static int lat_cycle(fs_context *c, int l, int chk, double **out)
     }
     int rc = lat_halo(c, l, L.x.p);
     if (rc) return rc;
-    LAT_STENCIL_LAUNCH(LAT_POST, L.g, nblk(t1 - t0, 192), st, L.g, L.c0, L.c1, L.A.p, L.dinv.p, L.x.p, L.b.p, L.xb.p, nullptr, L.omega, 0, st_of(c), chk);
+    lat_stencil_launch<LAT_POST>(c, L, L.x.p, L.b.p, L.xb.p, nullptr, L.omega, 0, chk);
     return FS_OK;
 }
 
@@ -1023,7 +1176,7 @@ static int lat_lambda(fs_context *c, int l, double *lam)
         rc = lat_halo(c, l, L.x.p);
         if (rc) return rc;
         // r = -A x ; t = -D^+ A x
-        LAT_STENCIL_LAUNCH(LAT_RESID, L.g, nblk(n6, 192), st, L.g, L.c0, L.c1, L.A.p, L.dinv.p, L.x.p, nullptr, L.r.p, L.t.p, 0.0, 0, st_of(c), 0);
+        lat_stencil_launch<LAT_RESID>(c, L, L.x.p, nullptr, L.r.p, L.t.p, 0.0, 0, 0);
         k_norm2<256><<<grid, 256, 0, st>>>(n6, L.x.p + t0, c->d_partials.p, c->d_counter.p, m.d_scalar.p);
         k_norm2<256><<<grid, 256, 0, st>>>(n6, L.t.p + t0, c->d_partials.p, c->d_counter.p, m.d_scalar.p + 1);
         double h[2];
@@ -1058,6 +1211,34 @@ static void ml_probe_pairs(const fs_context *c, int *n, int a[6], int b[6], unsi
     }
 }
 
+// Shell in a coordinate plane (the condition of the paired probes): the level iterates on the 18-of-36 copy of its stencil.
+// FS_ML_COMPACT=0 keeps the full blocks (lab / tests).
+static int lat_compact(fs_context *c, int l, bool planar_pairs)
+{
+    MlLevelBuf &L = c->ml.lat[l];
+    L.compact_kind = -1;
+    const char *e = getenv("FS_ML_COMPACT");
+    if (!planar_pairs || (e && e[0] == '0') || (L.g.ns != 9 && L.g.ns != 3)) return FS_OK;
+    // thread = cell pays where the stencil streams from HBM; a small level is a latency chain and runs faster with six
+    // threads per cell (c2: the 111^2 and 37^2 lattices lost 0.05 ms per visit in compact form, profiles/r02n)
+    int64_t min_cells = 32768;
+    if (const char *m = getenv("FS_ML_COMPACT_MIN_CELLS")) min_cells = std::max<int64_t>(1, atoll(m));
+    if ((int64_t)(L.c1 - L.c0) < min_cells) return FS_OK;
+    const size_t n = (size_t)L.g.n;
+    if (L.Ac.n < (size_t)L.g.ns * LAT_NZ * n) FS_CUDA(c, L.Ac.alloc((size_t)L.g.ns * LAT_NZ * n));
+    if (L.Dc.n < LAT_NZ * n) FS_CUDA(c, L.Dc.alloc(LAT_NZ * n));
+    FS_CUDA(c, cudaMemsetAsync(c->d_flag.p, 0, sizeof(int), c->stream));
+    const unsigned grid = nblk((int64_t)(L.c1 - L.c0), 128);
+    if (c->sell_kind == 0) k_lat_compact<LAT_MASK_XY><<<grid, 128, 0, c->stream>>>(L.g, L.c0, L.c1, L.A.p, L.dinv.p, L.Ac.p, L.Dc.p, c->d_flag.p);
+    else if (c->sell_kind == 1) k_lat_compact<LAT_MASK_XZ><<<grid, 128, 0, c->stream>>>(L.g, L.c0, L.c1, L.A.p, L.dinv.p, L.Ac.p, L.Dc.p, c->d_flag.p);
+    else k_lat_compact<LAT_MASK_YZ><<<grid, 128, 0, c->stream>>>(L.g, L.c0, L.c1, L.A.p, L.dinv.p, L.Ac.p, L.Dc.p, c->d_flag.p);
+    int bad = 0;
+    FS_CUDA(c, cudaMemcpyAsync(&bad, c->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    FS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!bad) L.compact_kind = c->sell_kind;   // an entry outside the pattern (never seen): stay on the full blocks, on this rank only -- same values
+    return FS_OK;
+}
+
 int ml_prepare(fs_context *c)
 {
     PhaseTimer tmg("ml_prepare");
@@ -1088,6 +1269,7 @@ int ml_prepare(fs_context *c)
         const int64_t n6 = 6 * (int64_t)g.n;
         // stencil of this level by probing the level below through the cycle's own transfer operators
         FS_CUDA(c, cudaMemsetAsync(L.A.p, 0, sizeof(double) * (size_t)g.ns * 6 * n6, st));
+        L.compact_kind = -1;
         const int nc0 = g.active[0] ? 3 : 1, nc1 = g.active[1] ? 3 : 1, nc2 = g.active[2] ? 3 : 1;
         int n_probe = 6, probe_a[6] = {0, 1, 2, 3, 4, 5}, probe_b[6] = {-1, -1, -1, -1, -1, -1};
         unsigned class_a = 0;
@@ -1125,6 +1307,8 @@ int ml_prepare(fs_context *c)
             L.lambda = 0.0;
         } else {
             k_lat_extract_dinv<<<nblk(L.c1 - L.c0, 64), 64, 0, st>>>(g, L.c0, L.c1, L.A.p, L.dinv.p);
+            rc = lat_compact(c, l, n_probe == 3);
+            if (rc) return rc;
             rc = lat_lambda(c, l, &lam);
             if (rc) return rc;
             L.lambda = lam;

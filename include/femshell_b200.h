@@ -251,6 +251,9 @@ int fs_get_ml_info(fs_context *ctx, int64_t *levels, int64_t *cells, double *wei
  * exchanged before each stencil application); the levels below are replicated.  0 with one rank, for lattices below
  * FS_ML_DIST_MIN_CELLS cells (environment, default 32768), or when the node blocks do not follow the slab direction. */
 int fs_get_ml_dist_levels(fs_context *ctx, int64_t *n_dist);
+/* number of lattice levels that iterate on the compacted copy of their stencil (18 of 36 entries per block: shells in a
+ * coordinate plane; environment FS_ML_COMPACT=0 keeps the full blocks).  Results are bit-identical either way. */
+int fs_get_ml_compact_levels(fs_context *ctx, int64_t *n_compact);
 /* lab (environment FS_ML_PROFILE=1): FS_PC_MLRBM solves run their iterations eagerly with CUDA events between the
  * stages; ms[0..5] = accumulated time of {halo + SpMV + update, pre-smoothing + restriction to the first lattice,
  * lattice cycle, prolongation, post-smoothing SpMV + r.z, all-reduce + new direction}, ms[6..7] = the two visits of

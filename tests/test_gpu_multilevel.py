@@ -114,6 +114,26 @@ def test_stage_profile_of_the_multilevel_iteration(fsb, monkeypatch):
     assert p["lattice_level2_visit1"] + p["lattice_level2_visit2"] <= p["lattice_cycle"]
 
 
+@pytest.mark.parametrize("case", ["quad40", "tri_xz", "folded"])
+def test_compacted_lattice_stencils_change_no_bit(fsb, case, monkeypatch):
+    """shells in a coordinate plane iterate on 18 of the 36 entries of every lattice block (k_lat_stencil_c); the skipped
+    entries are exact zeros and the sums keep their order, so z = M^-1 r is bit-identical to the full-block kernels.  The
+    folded shell is not planar: no level is compacted"""
+    m, nu, E, t = CASES[case](fsb)
+    monkeypatch.setenv("FS_ML_COMPACT_MIN_CELLS", "1")     # by default only lattices that stream from HBM are compacted
+    s = gpu_system(fsb, m, nu, E, t, loads=m["forces"])
+    s.set_ml_options(dense_points=24)
+    r = np.random.default_rng(11).standard_normal(6 * s.sizes()["n_dofnodes"])
+    z1 = s.apply_mlrbm(r)
+    info = s.ml_info()
+    assert info["compact_levels"] == (0 if case == "folded" else info["levels"] - 1), info
+    monkeypatch.setenv("FS_ML_COMPACT", "0")
+    s.assemble()                                        # new values -> the set-up runs again, now without compaction
+    z0 = s.apply_mlrbm(r)
+    assert s.ml_info()["compact_levels"] == 0
+    assert np.array_equal(z0, z1)
+
+
 def test_multilevel_rejects_preconditioned_norm(fsb):
     m = fsb.meshgen("q", 8, 8, 0, 0, 10, 10, (1, 1, 1, 1), 300.0, 2, 1)
     s = gpu_system(fsb, m, 0.3, 1e7, 0.5, loads=m["forces"])
