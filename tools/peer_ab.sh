@@ -1,5 +1,5 @@
 #!/bin/bash
-# N-GPU A/B of the CG exchange paths: peer windows (interior-first / natural slice order) vs NCCL, with the library's phase timings
+# N-GPU A/B of the CG exchange paths: peer windows vs NCCL, with the library's phase timings
 #   gpurun --gpus N -- 'bash tools/peer_ab.sh TAG N'
 TAG=$1; N=${2:-2}; O=gpurun_out/$TAG; mkdir -p gpurun_out
 run() {  # name, env..., -- extra bench flags
@@ -16,5 +16,4 @@ PY
 }
 run peer FS_TIMING=1 --
 grep -E "peer_window|peer window" ${O}_peer.err | head -40
-run natural FS_PEER_SPMV_ORDER=natural --
 run nccl FS_X=1 -- --comm nccl
