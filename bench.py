@@ -687,7 +687,9 @@ def run_ours(args):
                      "how": "halo: average per waiting warp of k_spmv_sell; partials: clock64 around the spin loops, block 0 (fs_peer.cuh)"},
                     # link-side evidence: NVML's NVLink data counters of rank 0's GPU around the timed region, against the bytes the
                     # algorithm must send per iteration (48 B per send-list node + the 8-byte words of the two mailbox reductions)
-                    "nvlink_rank0": None if not (nvl0 and nvl1) else
+                    "nvlink_rank0": ({"available": False, "note": "NVML and nvidia-smi report N/A for the NVLink byte counters on these boxes, and ncu's link "
+                                      "metrics need kernel replay, which a kernel that waits for its peer does not survive (tried: profiles/r02p_nvlink_attempt.txt); "
+                                      "the device-side wait counters above are the evidence there is"} if world > 1 else None) if not (nvl0 and nvl1) else
                     {"tx_bytes_per_iteration": 1024.0 * (nvl1[0] - nvl0[0]) / max(1, its_timed), "rx_bytes_per_iteration": 1024.0 * (nvl1[1] - nvl0[1]) / max(1, its_timed),
                      "algorithmic_tx_bytes_per_iteration": 48.0 * nx + 16.0 * 3 * (world - 1),   # rank 0: one neighbour, one node row of the strip
                      "source": "NVML NVLINK_THROUGHPUT_DATA_TX/RX, all links of rank 0's GPU, KiB granularity"}},
