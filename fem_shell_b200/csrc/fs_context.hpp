@@ -103,6 +103,11 @@ struct MlHier {
     DevBuf<int32_t> d_agg;       // n_local: cell of the first lattice holding each local node
     DevBuf<int32_t> d_sup_ptr, d_sup_node;  // cell -> owned nodes (owned-relative ids)
     DevBuf<double> d_r1, d_t;    // 6 * n_local work vectors of the mesh level
+    // shells in a coordinate plane: the inverses of the 6x6 diagonal blocks (d_minv, 36 per node) have the 14-entry pattern
+    // of the mesh blocks; the four mesh-level kernels of the cycle that apply them read this copy (14 per node, row-major
+    // over the set bits of the mask), bit-identical sums.  dinv_mask = 0: not compacted
+    DevBuf<double> d_dinv_c;
+    unsigned long long dinv_mask = 0;
     DevBuf<double> d_scalar;
     double omega0 = 0.0, lambda0 = 0.0;
     float setup_ms = 0.f;

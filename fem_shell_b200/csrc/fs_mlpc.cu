@@ -85,8 +85,54 @@ __device__ __forceinline__ double dinv_row(const double *__restrict__ dinv, int6
     return s;
 }
 
+// the diagonal-block inverses of the mesh level, either as extracted (36 per node, mask = 0) or compacted to the set bits of
+// `mask` (popcount(mask) per node, row-major).  The compacted sum spells out dinv_row's pairs with literal zeros for the
+// skipped entries: same products, same order, same rounding.
+struct DinvRef {
+    const double *p;
+    unsigned long long mask;
+};
+__device__ __forceinline__ double dinv_row(const DinvRef d, int64_t t, const double *__restrict__ v6)
+{
+    if (d.mask == 0) return dinv_row(d.p, t, v6);
+    const int64_t node = t / 6;
+    const int a = (int)(t - 6 * node);
+    const unsigned row = (unsigned)(d.mask >> (6 * a)) & 63u;
+    const double *e = d.p + (size_t)__popcll(d.mask) * node + __popcll(d.mask & ((1ull << (6 * a)) - 1ull));
+    double s = 0.0;
+    int k = 0;
+#pragma unroll
+    for (int h = 0; h < 3; h++) {
+        const bool bx = (row >> (2 * h)) & 1u, by = (row >> (2 * h + 1)) & 1u;
+        if (bx || by) {
+            const double dx = bx ? e[k] : 0.0;
+            k += bx ? 1 : 0;
+            const double dy = by ? e[k] : 0.0;
+            k += by ? 1 : 0;
+            s += dx * v6[2 * h] + dy * v6[2 * h + 1];
+        }
+    }
+    return s;
+}
+
+// d_minv (36 per node) -> the entries of `mask`, row-major; *bad is set when an entry outside the mask is not an exact zero
+__global__ void k_f_dinv_compact(int64_t n_own, unsigned long long mask, const double *__restrict__ dinv, double *__restrict__ out, int *bad)
+{
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= n_own) return;
+    const int nz = __popcll(mask);
+    int k = 0;
+    bool off = false;
+    for (int i = 0; i < 36; i++) {
+        const double v = dinv[36 * (size_t)p + i];
+        if ((mask >> i) & 1ull) out[(size_t)nz * p + k++] = v;
+        else off |= v != 0.0;
+    }
+    if (off) *bad = 1;
+}
+
 __global__ void __launch_bounds__(256)
-k_f_smooth0(int64_t n6, const double *__restrict__ b, const double *__restrict__ dinv, double omega, double *__restrict__ x,
+k_f_smooth0(int64_t n6, const double *__restrict__ b, const DinvRef dinv, double omega, double *__restrict__ x,
             const CgState *state, int chk)
 {
     ML_RETURN_IF_DONE(state, chk);
@@ -97,7 +143,7 @@ k_f_smooth0(int64_t n6, const double *__restrict__ b, const double *__restrict__
 
 // r1 = b - q (b may be null: zero) ; t = D^-1 r1
 __global__ void __launch_bounds__(192)
-k_f_resid(int64_t n6, const double *__restrict__ b, const double *__restrict__ q, const double *__restrict__ dinv,
+k_f_resid(int64_t n6, const double *__restrict__ b, const double *__restrict__ q, const DinvRef dinv,
           double *__restrict__ r1, double *__restrict__ tv, const CgState *state, int chk)
 {
     ML_RETURN_IF_DONE(state, chk);
@@ -176,7 +222,7 @@ k_f_prolong_t(const __grid_constant__ LatGeom g, int64_t n_local, const int32_t 
 
 // x (+)= t - w D^-1 q
 __global__ void __launch_bounds__(256)
-k_f_prolong_add(int64_t n6, const double *__restrict__ tv, const double *__restrict__ q, const double *__restrict__ dinv,
+k_f_prolong_add(int64_t n6, const double *__restrict__ tv, const double *__restrict__ q, const DinvRef dinv,
                 double omega, double *__restrict__ x, int accumulate, const CgState *state, int chk)
 {
     ML_RETURN_IF_DONE(state, chk);
@@ -191,7 +237,7 @@ k_f_prolong_add(int64_t n6, const double *__restrict__ tv, const double *__restr
 // WITH_DOT = false: plain post-smoothing step (tests, set-up).
 template <bool INIT, bool WITH_DOT, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
-k_f_post_finish(int64_t n6, const double *__restrict__ b, const double *__restrict__ q, const double *__restrict__ dinv,
+k_f_post_finish(int64_t n6, const double *__restrict__ b, const double *__restrict__ q, const DinvRef dinv,
                 double omega, double *__restrict__ z, double *__restrict__ p, double *partials, unsigned int *counter,
                 CgState *state, double *red, int fin_mode, int chk)
 {
@@ -970,6 +1016,10 @@ static void lat_stencil_launch(fs_context *c, MlLevelBuf &L, const double *in, c
 // the building blocks of the cycle (enqueue only)
 // ---------------------------------------------------------------------------------------------
 static const CgState *st_of(fs_context *c) { return c->d_state.p; }
+static DinvRef ml_dinv(const fs_context *c)
+{
+    return c->ml.dinv_mask ? DinvRef{c->ml.d_dinv_c.p, c->ml.dinv_mask} : DinvRef{c->d_minv.p, 0ull};
+}
 
 // mesh level: b_1 = P^T (b - A x).  b and x are LOCAL-layout vectors (b may be null: zero); x's halo is refreshed.
 static int fine_restrict_chain(fs_context *c, const double *b, double *x, int chk)
@@ -979,7 +1029,7 @@ static int fine_restrict_chain(fs_context *c, const double *b, double *x, int ch
     const int64_t o6 = 6 * c->own_lo, n6 = 6 * c->n_own;
     int rc = spmv_once(c, x, c->d_q.p, chk != 0);
     if (rc) return rc;
-    k_f_resid<<<nblk(n6, 192), 192, 0, st>>>(n6, b ? b + o6 : nullptr, c->d_q.p + o6, c->d_minv.p, m.d_r1.p + o6, m.d_t.p + o6, st_of(c), chk);
+    k_f_resid<<<nblk(n6, 192), 192, 0, st>>>(n6, b ? b + o6 : nullptr, c->d_q.p + o6, ml_dinv(c), m.d_r1.p + o6, m.d_t.p + o6, st_of(c), chk);
     rc = spmv_once(c, m.d_t.p, c->d_q.p, chk != 0);
     if (rc) return rc;
     MlLevelBuf &L1 = m.lat[0];
@@ -1009,7 +1059,7 @@ static int fine_prolong_chain(fs_context *c, double *e, double *x, bool accumula
     k_f_prolong_t<<<nblk(c->n_local, 256), 256, 0, st>>>(m.lat[0].g, c->n_local, m.d_agg.p, c->d_xyz.p, c->d_mask.p, e, m.d_t.p, st_of(c), chk);
     int rc = spmv_local(c, m.d_t.p, c->d_q.p, chk != 0);  // t is complete on owned and halo nodes: no exchange
     if (rc) return rc;
-    k_f_prolong_add<<<nblk(n6, 256), 256, 0, st>>>(n6, m.d_t.p + o6, c->d_q.p + o6, c->d_minv.p, m.omega0, x + o6, accumulate ? 1 : 0, st_of(c), chk);
+    k_f_prolong_add<<<nblk(n6, 256), 256, 0, st>>>(n6, m.d_t.p + o6, c->d_q.p + o6, ml_dinv(c), m.omega0, x + o6, accumulate ? 1 : 0, st_of(c), chk);
     return FS_OK;
 }
 
@@ -1146,7 +1196,7 @@ static int fine_lambda(fs_context *c, double *lam)
         rc = spmv_once(c, v, c->d_q.p, false);
         if (rc) return rc;
         // t = -D^-1 A v ; r1 = -A v
-        k_f_resid<<<nblk(n6, 192), 192, 0, st>>>(n6, nullptr, c->d_q.p + o6, c->d_minv.p, m.d_r1.p + o6, m.d_t.p + o6, st_of(c), 0);
+        k_f_resid<<<nblk(n6, 192), 192, 0, st>>>(n6, nullptr, c->d_q.p + o6, ml_dinv(c), m.d_r1.p + o6, m.d_t.p + o6, st_of(c), 0);
         k_norm2<256><<<grid, 256, 0, st>>>(n6, v + o6, c->d_partials.p, c->d_counter.p, m.d_scalar.p);
         k_norm2<256><<<grid, 256, 0, st>>>(n6, m.d_t.p + o6, c->d_partials.p, c->d_counter.p, m.d_scalar.p + 1);
         double h[2];
@@ -1239,6 +1289,30 @@ static int lat_compact(fs_context *c, int l, bool planar_pairs)
     return FS_OK;
 }
 
+// shells in a coordinate plane (same condition as the paired probes): the cycle's mesh-level kernels read a 14-per-node copy
+// of the diagonal-block inverses.  FS_ML_COMPACT=0 keeps the full blocks.
+static int mesh_dinv_compact(fs_context *c)
+{
+    MlHier &m = c->ml;
+    m.dinv_mask = 0;
+    int n_probe = 6, pa[6], pb[6];
+    unsigned cls = 0;
+    ml_probe_pairs(c, &n_probe, pa, pb, &cls);
+    const char *e = getenv("FS_ML_COMPACT");
+    if (n_probe != 3 || c->plane_rot || (e && e[0] == '0')) return FS_OK;
+    static const unsigned long long masks[3] = {SELL_MASK_XY, SELL_MASK_XZ, SELL_MASK_YZ};
+    const unsigned long long mask = masks[c->sell_kind];
+    const size_t need = (size_t)sell_popcount(mask) * c->n_own;
+    if (m.d_dinv_c.n < need) FS_CUDA(c, m.d_dinv_c.alloc(need));
+    FS_CUDA(c, cudaMemsetAsync(c->d_flag.p, 0, sizeof(int), c->stream));
+    k_f_dinv_compact<<<nblk(c->n_own, 128), 128, 0, c->stream>>>(c->n_own, mask, c->d_minv.p, m.d_dinv_c.p, c->d_flag.p);
+    int bad = 0;
+    FS_CUDA(c, cudaMemcpyAsync(&bad, c->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    FS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!bad) m.dinv_mask = mask;
+    return FS_OK;
+}
+
 int ml_prepare(fs_context *c)
 {
     PhaseTimer tmg("ml_prepare");
@@ -1258,7 +1332,9 @@ int ml_prepare(fs_context *c)
     cudaEvent_t e0 = c->ev0, e1 = c->ev1;
     FS_CUDA(c, cudaEventRecord(e0, st));
     double lam = 1.0;
-    int rc = fine_lambda(c, &lam);
+    int rc = mesh_dinv_compact(c);
+    if (rc) return rc;
+    rc = fine_lambda(c, &lam);
     if (rc) return rc;
     m.lambda0 = lam;
     m.omega0 = (4.0 / 3.0) / lam;
@@ -1332,7 +1408,7 @@ int ml_enqueue_apply(fs_context *c, bool init, double *red, int fin, int vec_gri
     cudaStream_t st = c->stream;
     const int64_t o6 = 6 * c->own_lo, n6 = 6 * c->n_own;
     const int chk = (init || !red) ? 0 : 1;
-    k_f_smooth0<<<nblk(n6, 256), 256, 0, st>>>(n6, c->d_r.p + o6, c->d_minv.p, m.omega0, c->d_z.p + o6, st_of(c), chk);
+    k_f_smooth0<<<nblk(n6, 256), 256, 0, st>>>(n6, c->d_r.p + o6, ml_dinv(c), m.omega0, c->d_z.p + o6, st_of(c), chk);
     auto mark = [&](int k) { if (c->prof.on) cudaEventRecord(c->prof.ev[k], st); };
     int rc = fine_restrict_chain(c, c->d_r.p, c->d_z.p, chk);
     if (rc) return rc;
@@ -1349,13 +1425,13 @@ int ml_enqueue_apply(fs_context *c, bool init, double *red, int fin, int vec_gri
     constexpr int PB = 192;
     const int grid = std::max(1, vec_grid);
     if (!red)
-        k_f_post_finish<false, false, PB><<<grid, PB, 0, st>>>(n6, c->d_r.p + o6, c->d_q.p + o6, c->d_minv.p, m.omega0, c->d_z.p + o6, nullptr,
+        k_f_post_finish<false, false, PB><<<grid, PB, 0, st>>>(n6, c->d_r.p + o6, c->d_q.p + o6, ml_dinv(c), m.omega0, c->d_z.p + o6, nullptr,
                                                                  c->d_partials.p, c->d_counter.p, c->d_state.p, nullptr, fin, 0);
     else if (init)
-        k_f_post_finish<true, true, PB><<<grid, PB, 0, st>>>(n6, c->d_r.p + o6, c->d_q.p + o6, c->d_minv.p, m.omega0, c->d_z.p + o6, c->d_p.p + o6,
+        k_f_post_finish<true, true, PB><<<grid, PB, 0, st>>>(n6, c->d_r.p + o6, c->d_q.p + o6, ml_dinv(c), m.omega0, c->d_z.p + o6, c->d_p.p + o6,
                                                                c->d_partials.p, c->d_counter.p, c->d_state.p, red, fin, 0);
     else
-        k_f_post_finish<false, true, PB><<<grid, PB, 0, st>>>(n6, c->d_r.p + o6, c->d_q.p + o6, c->d_minv.p, m.omega0, c->d_z.p + o6, c->d_p.p + o6,
+        k_f_post_finish<false, true, PB><<<grid, PB, 0, st>>>(n6, c->d_r.p + o6, c->d_q.p + o6, ml_dinv(c), m.omega0, c->d_z.p + o6, c->d_p.p + o6,
                                                                 c->d_partials.p, c->d_counter.p, c->d_state.p, red, fin, 1);
     return FS_OK;
 }
