@@ -303,11 +303,12 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
     });
 
     tm.lap("dof order");
-    // bounding box of the nodes that carry DOFs and largest element extent per axis (lattice of the multilevel
-    // preconditioner, fs_mlpc.cuh: the cells of the first lattice are three element extents wide)
+    // bounding box of the nodes that carry DOFs (planarity test below; lattice of the multilevel preconditioner).  The
+    // largest element extent per axis, which sizes the cells of the first lattice, is measured on the device when the
+    // hierarchy is first built (fs_mlpc.cu ml_element_extents): here it was a pass of random reads over the whole mesh
     {
         const double inf = 1e300;
-        std::vector<double> lo(3 * ht, inf), hi(3 * ht, -inf), hmax(3 * ht, 0.0);
+        std::vector<double> lo(3 * ht, inf), hi(3 * ht, -inf);
         parallel_chunks(n_nodes, ht, [&](int t, int64_t i0, int64_t i1) {
             double l[3] = {inf, inf, inf}, h[3] = {-inf, -inf, -inf};   // thread-local: the shared arrays are written once
             for (int64_t i = i0; i < i1; i++) {
@@ -320,29 +321,11 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
             }
             for (int d = 0; d < 3; d++) { lo[3 * t + d] = l[d]; hi[3 * t + d] = h[d]; }
         });
-        parallel_chunks(n_elem, ht, [&](int t, int64_t e0, int64_t e1) {
-            double hm[3] = {0.0, 0.0, 0.0};
-            for (int64_t e = e0; e < e1; e++) {
-                const int32_t *en = enodes + eptr[e];
-                const int nen = (int)(eptr[e + 1] - eptr[e]);
-                for (int d = 0; d < 3; d++) {
-                    double l = xyz[3 * (int64_t)en[0] + d], h = l;
-                    for (int k = 1; k < nen; k++) {
-                        const double v = xyz[3 * (int64_t)en[k] + d];
-                        l = std::min(l, v);
-                        h = std::max(h, v);
-                    }
-                    hm[d] = std::max(hm[d], h - l);
-                }
-            }
-            for (int d = 0; d < 3; d++) hmax[3 * t + d] = hm[d];
-        });
         for (int d = 0; d < 3; d++) {
             c->bbox_lo[d] = inf; c->bbox_hi[d] = -inf; c->ml_h[d] = 0.0;
             for (int t = 0; t < ht; t++) {
                 c->bbox_lo[d] = std::min(c->bbox_lo[d], lo[3 * t + d]);
                 c->bbox_hi[d] = std::max(c->bbox_hi[d], hi[3 * t + d]);
-                c->ml_h[d] = std::max(c->ml_h[d], hmax[3 * t + d]);
             }
             if (c->bbox_lo[d] > c->bbox_hi[d]) c->bbox_lo[d] = c->bbox_hi[d] = 0.0;
         }
@@ -390,7 +373,7 @@ int fs_set_mesh(fs_context *c, int64_t n_nodes, const double *xyz, int64_t n_ele
             }
         }
     }
-    tm.lap("bbox + element extents");
+    tm.lap("bbox + planarity");
     // ---- Dirichlet bits (fs.cpp:90-120) and coupling interface (fsp.cpp:55-71) ----
     c->node_mask.assign(n_nodes, 0);
     std::vector<uint8_t> is_if(n_nodes, 0);

@@ -229,7 +229,7 @@ struct fs_context {
 
     // multilevel rigid-body-mode preconditioner (fs_mlpc.cuh / fs_mlpc.cu)
     double bbox_lo[3] = {0, 0, 0}, bbox_hi[3] = {0, 0, 0};  // of all mesh nodes (identical on every rank)
-    double ml_h[3] = {0, 0, 0};            // largest element extent per axis (identical on every rank)
+    double ml_h[3] = {0, 0, 0};            // largest element extent per axis (identical on every rank; measured by ml_build_geometry)
     int64_t ml_max_points = 1 << 22;       // cap on the cells of the first lattice
     int ml_dense_points = fs::ML_DENSE_DEFAULT_POINTS;  // a lattice with at most this many cells is solved densely
     int ml_gamma = 2;                      // cycle index on the lattice levels (1 = V, 2 = W; two digits: first lattice, deeper ones)

@@ -761,6 +761,51 @@ __global__ void k_scale_copy(int64_t n, const double *__restrict__ in, double f,
     if (t < n) out[t] = f * in[t];
 }
 
+// largest extent of an element along each axis: non-negative doubles order like their bit patterns, so the maximum is an
+// integer atomicMax
+__global__ void k_elem_extent(int64_t n_elem, int nen, const int32_t *__restrict__ conn, const double *__restrict__ xyz, unsigned long long *hmax)
+{
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double ext[3] = {0.0, 0.0, 0.0};
+    if (e < n_elem) {
+        const int32_t *en = conn + (size_t)nen * e;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            double lo = xyz[3 * (size_t)en[0] + d], hi = lo;
+            for (int k = 1; k < nen; k++) {
+                const double v = xyz[3 * (size_t)en[k] + d];
+                lo = fmin(lo, v);
+                hi = fmax(hi, v);
+            }
+            ext[d] = hi - lo;
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        unsigned long long b = (unsigned long long)__double_as_longlong(ext[d]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+        if ((threadIdx.x & 31) == 0 && b) atomicMax(hmax + d, b);
+    }
+}
+
+// c->ml_h = largest element extent per axis over the whole mesh: every element is local to at least one rank
+static int ml_element_extents(fs_context *c)
+{
+    DevBuf<unsigned long long> d_h;
+    FS_CUDA(c, d_h.alloc(3));
+    FS_CUDA(c, cudaMemsetAsync(d_h.p, 0, 3 * sizeof(unsigned long long), c->stream));
+    if (c->n_tri) k_elem_extent<<<nblk(c->n_tri, 256), 256, 0, c->stream>>>(c->n_tri, 3, c->d_tri.p, c->d_xyz.p, d_h.p);
+    if (c->n_quad) k_elem_extent<<<nblk(c->n_quad, 256), 256, 0, c->stream>>>(c->n_quad, 4, c->d_quad.p, c->d_xyz.p, d_h.p);
+    if (c->world > 1)   // bit patterns of non-negative doubles: the integer maximum is the floating-point maximum
+        FS_NCCL_ML(c, nccl().AllReduce(d_h.p, d_h.p, 3, ncclUint64, ncclMax, (ncclComm_t)c->comm, c->stream));
+    unsigned long long h[3];
+    FS_CUDA(c, cudaMemcpyAsync(h, d_h.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    FS_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int d = 0; d < 3; d++) memcpy(&c->ml_h[d], &h[d], sizeof(double));
+    return FS_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host: hierarchy
 // ---------------------------------------------------------------------------------------------
@@ -768,6 +813,10 @@ static int ml_build_geometry(fs_context *c)
 {
     MlHier &m = c->ml;
     m.n_lat = 0;
+    {
+        int rce = ml_element_extents(c);
+        if (rce) return rce;
+    }
     double ext[3], maxext = 0.0;
     for (int d = 0; d < 3; d++) {
         ext[d] = c->bbox_hi[d] - c->bbox_lo[d];
