@@ -109,16 +109,19 @@ void *fs_get_stream(fs_context *ctx);
 /* ---- multi-GPU: one process per GPU ------------------------------------ */
 /* Call BEFORE fs_set_mesh.  nccl_unique_id = the 128 bytes of an ncclUniqueId created on
  * rank 0 (fs_dist_unique_id) and broadcast by the host program.  Replaces the MPI
- * communicator libMesh/PETSc use (fs.cpp:28,35). */
+ * communicator libMesh/PETSc use (fs.cpp:28,35).  Collective: creates the NCCL communicator and runs one
+ * all-reduce, all-gather and neighbour send/recv so that NCCL's channel set-up (0.3 s on 2 GPUs, about a
+ * second on 8) is paid here and not by the first fs_set_mesh. */
 int fs_dist_unique_id(uint8_t id_out[128]);
 int fs_dist_init(fs_context *ctx, int rank, int world, const uint8_t nccl_unique_id[128]);
 int fs_set_comm_mode(fs_context *ctx, int mode);
 /* FS_COMM_NCCL or FS_COMM_PEER: what the iteration of the current mesh uses (single rank: FS_COMM_NCCL) */
 int fs_get_comm_mode(fs_context *ctx, int *mode);
 /* FS_COMM_PEER: what the CG kernels of this rank spent WAITING for the other GPUs since the last reset, measured
- * by block 0 with clock64: out = {microseconds waiting for the neighbours' halo stamps (k_spmv_sell, after its
- * interior slices), for the partial sums of p.Ap (k_update), of r.z and the norm (k_direction), and the number of
- * waits of each kind (3 more entries), and the wall-clock microseconds (globaltimer) from the entry of block 0 to the
+ * with clock64: out = {microseconds waiting for the neighbours' halo stamps (k_spmv_sell: summed over the warps that
+ * reach a slice reading halo blocks; divide by the number of waits), for the partial sums of p.Ap (k_update, block 0),
+ * of r.z and the norm (k_direction, block 0), and the number of waits of each kind (3 more entries), and the
+ * wall-clock microseconds (globaltimer) from the entry of block 0 to the
  * end of the last block summed over the launches of k_spmv_sell, k_update, k_direction (3 more entries)}.
  * reset != 0 zeroes the counters afterwards.  Zeros on the NCCL path. */
 int fs_get_comm_stats(fs_context *ctx, double out[9], int reset);
