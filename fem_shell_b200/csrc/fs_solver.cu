@@ -824,38 +824,38 @@ static int run_pcg(fs_context *c, const fs_solve_opts *o, fs_solve_info *info)
         }
         pf.on = false;
     } else {
-    constexpr int GRAPH_ITERS = (PC == 3) ? 1 : 8;  // a multilevel iteration is ~100 launches already
-    const int key = PC * 2 + NORM + (c->sell_active ? 8 * (1 + c->sell_kind) : 0) + (peer ? 64 : 0);
-    if (!c->cg_graph_exec || c->cg_graph_key != key || c->cg_graph_red != red) {
-        PhaseTimer tmc("run_pcg");
-        if (c->cg_graph_exec) cudaGraphExecDestroy(c->cg_graph_exec);
-        c->cg_graph_exec = nullptr;
-        cudaGraph_t graph = nullptr;
-        FS_CUDA(c, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        rc = FS_OK;
-        for (int k = 0; k < GRAPH_ITERS && rc == FS_OK; k++) rc = enqueue_iteration<PC, NORM>(c, red, sg, vg);
-        cudaError_t ce = cudaStreamEndCapture(st, &graph);
-        if (rc) {
-            if (graph) cudaGraphDestroy(graph);
-            return rc;
+        constexpr int GRAPH_ITERS = (PC == 3) ? 1 : 8;  // a multilevel iteration is ~100 launches already
+        const int key = PC * 2 + NORM + (c->sell_active ? 8 * (1 + c->sell_kind) : 0) + (peer ? 64 : 0);
+        if (!c->cg_graph_exec || c->cg_graph_key != key || c->cg_graph_red != red) {
+            PhaseTimer tmc("run_pcg");
+            if (c->cg_graph_exec) cudaGraphExecDestroy(c->cg_graph_exec);
+            c->cg_graph_exec = nullptr;
+            cudaGraph_t graph = nullptr;
+            FS_CUDA(c, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            rc = FS_OK;
+            for (int k = 0; k < GRAPH_ITERS && rc == FS_OK; k++) rc = enqueue_iteration<PC, NORM>(c, red, sg, vg);
+            cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc) {
+                if (graph) cudaGraphDestroy(graph);
+                return rc;
+            }
+            FS_CUDA(c, ce);
+            FS_CUDA(c, cudaGraphInstantiate(&c->cg_graph_exec, graph, 0));
+            FS_CUDA(c, cudaGraphDestroy(graph));
+            tmc.lap("graph capture + instantiate");
+            c->cg_graph_key = key;
+            c->cg_graph_red = red;
         }
-        FS_CUDA(c, ce);
-        FS_CUDA(c, cudaGraphInstantiate(&c->cg_graph_exec, graph, 0));
-        FS_CUDA(c, cudaGraphDestroy(graph));
-        tmc.lap("graph capture + instantiate");
-        c->cg_graph_key = key;
-        c->cg_graph_red = red;
-    }
-    const int batch = o->check_every > 0 ? o->check_every : (PC == 3 ? 4 : 64);
-    for (;;) {
-        FS_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state.p, sizeof(CgState), cudaMemcpyDeviceToHost, st));
-        FS_CUDA(c, cudaStreamSynchronize(st));
-        if (c->h_state->done) break;
-        int64_t left = c->h_state->max_its - c->h_state->iter;
-        int64_t n = std::min<int64_t>(batch, std::max<int64_t>(left, 1));
-        for (int64_t k = 0; k < n; k += GRAPH_ITERS) FS_CUDA(c, cudaGraphLaunch(c->cg_graph_exec, st));
-        FS_CUDA(c, cudaGetLastError());
-    }
+        const int batch = o->check_every > 0 ? o->check_every : (PC == 3 ? 4 : 64);
+        for (;;) {
+            FS_CUDA(c, cudaMemcpyAsync(c->h_state, c->d_state.p, sizeof(CgState), cudaMemcpyDeviceToHost, st));
+            FS_CUDA(c, cudaStreamSynchronize(st));
+            if (c->h_state->done) break;
+            int64_t left = c->h_state->max_its - c->h_state->iter;
+            int64_t n = std::min<int64_t>(batch, std::max<int64_t>(left, 1));
+            for (int64_t k = 0; k < n; k += GRAPH_ITERS) FS_CUDA(c, cudaGraphLaunch(c->cg_graph_exec, st));
+            FS_CUDA(c, cudaGetLastError());
+        }
     }
     FS_CUDA(c, cudaEventRecord(c->ev1, st));
     FS_CUDA(c, cudaStreamSynchronize(st));
