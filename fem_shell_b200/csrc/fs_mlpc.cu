@@ -374,16 +374,17 @@ __device__ __forceinline__ void dinv_apply_c(const double *__restrict__ Dc, int6
     }
 }
 
-template <int MODE, int NS, unsigned long long MASK>
-__global__ void __launch_bounds__(128)
-k_lat_stencil_c(const __grid_constant__ LatGeom g, int c0, int c1, const double *__restrict__ Ac, const double *__restrict__ Dc,
-                const double *__restrict__ in, const double *aux, double *out1, double *__restrict__ out2, double omega,
-                int flag, const CgState *state, int chk)
+// rows of mode class CLS: class 0 = the rows coupled to row 0, class 1 = the other three
+__host__ __device__ constexpr bool lat_in_class(unsigned long long mask, int cls, int a) { return ((mask & sell_bit(0, a)) != 0) == (cls == 0); }
+
+// thread = (cell, mode class): the two classes of a block never couple, so each is a 3x3 problem of its own with half
+// the loads -- twice the threads in flight for a kernel that waits on memory latency (profiles/r02w_ncu_ml.txt)
+template <int MODE, int NS, unsigned long long MASK, int CLS>
+__device__ __forceinline__ void lat_stencil_c_class(const LatGeom &g, int p, const double *__restrict__ Ac, const double *__restrict__ Dc,
+                                                    const double *__restrict__ in, const double *aux, double *out1, double *__restrict__ out2,
+                                                    double omega, int flag)
 {
-    ML_RETURN_IF_DONE(state, chk);
     constexpr int NZ = sell_popcount(MASK);
-    const int p = c0 + blockIdx.x * 128 + threadIdx.x;   // cells [c0, c1): this rank's slabs
-    if (p >= c1) return;
     const int64_t n = g.n;
     int k[3];
     lat_unindex(g, p, k);
@@ -394,55 +395,56 @@ k_lat_stencil_c(const __grid_constant__ LatGeom g, int c0, int c1, const double 
         lat_stencil_off(g, s, o);
         const int kk[3] = {k[0] + o[0], k[1] + o[1], k[2] + o[2]};
         const bool inside = kk[0] >= 0 && kk[0] < g.np[0] && kk[1] >= 0 && kk[1] < g.np[1] && kk[2] >= 0 && kk[2] < g.np[2];
-        double xv[6];
-        load6(in + 6 * (size_t)(inside ? lat_index(g, kk) : p), xv);
+        const double *xin = in + 6 * (size_t)(inside ? lat_index(g, kk) : p);
+        double xv[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int b = 0; b < 6; b++)
+            if (lat_in_class(MASK, CLS, b)) xv[b] = xin[b];
         const double *as = Ac + (size_t)(NZ * s) * n + p;
 #pragma unroll
         for (int a = 0; a < 6; a++)
 #pragma unroll
             for (int b = 0; b < 6; b++)
-                if (MASK & sell_bit(a, b)) v[a] += as[(size_t)sell_item(MASK, a, b) * n] * xv[b];
+                if (lat_in_class(MASK, CLS, a) && (MASK & sell_bit(a, b))) v[a] += as[(size_t)sell_item(MASK, a, b) * n] * xv[b];
     }
     const size_t at = 6 * (size_t)p;
     if (MODE == LAT_RSMOOTH) {
-        double av[6], o6[6];
-        load6(aux + at, av);
 #pragma unroll
-        for (int a = 0; a < 6; a++) o6[a] = av[a] - omega * v[a];
-        store6(out1 + at, o6);
+        for (int a = 0; a < 6; a++)
+            if (lat_in_class(MASK, CLS, a)) out1[at + a] = aux[at + a] - omega * v[a];
         return;
     }
-    double w[6], dw[6];
-    if (MODE == LAT_RESID || MODE == LAT_POST) {
-        double av[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        if (aux) load6(aux + at, av);
+    double w[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, dw[6];   // the other class stays zero: dinv_apply_c multiplies it by literal zeros
 #pragma unroll
-        for (int a = 0; a < 6; a++) w[a] = av[a] - v[a];
-    } else {
-#pragma unroll
-        for (int a = 0; a < 6; a++) w[a] = v[a];
-    }
+    for (int a = 0; a < 6; a++)
+        if (lat_in_class(MASK, CLS, a)) w[a] = (MODE == LAT_RESID || MODE == LAT_POST) ? (aux ? aux[at + a] : 0.0) - v[a] : v[a];
     dinv_apply_c<MASK>(Dc, n, p, w, dw);
-    if (MODE == LAT_RESID) {
-        store6(out1 + at, w);
-        store6(out2 + at, dw);
-        return;
-    }
-    double iv[6], o6[6];
-    load6(in + at, iv);
-    if (MODE == LAT_PADD) {
-        double prev[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        if (flag) load6(out1 + at, prev);
 #pragma unroll
-        for (int a = 0; a < 6; a++) {
-            const double add = iv[a] - omega * dw[a];
-            o6[a] = flag ? prev[a] + add : add;
+    for (int a = 0; a < 6; a++)
+        if (lat_in_class(MASK, CLS, a)) {
+            if (MODE == LAT_RESID) {
+                out1[at + a] = w[a];
+                out2[at + a] = dw[a];
+            } else if (MODE == LAT_PADD) {
+                const double add = in[at + a] - omega * dw[a];
+                out1[at + a] = flag ? out1[at + a] + add : add;
+            } else {
+                out1[at + a] = in[at + a] + omega * dw[a];
+            }
         }
-    } else {
-#pragma unroll
-        for (int a = 0; a < 6; a++) o6[a] = iv[a] + omega * dw[a];
-    }
-    store6(out1 + at, o6);
+}
+
+template <int MODE, int NS, unsigned long long MASK>
+__global__ void __launch_bounds__(128)
+k_lat_stencil_c(const __grid_constant__ LatGeom g, int c0, int c1, const double *__restrict__ Ac, const double *__restrict__ Dc,
+                const double *__restrict__ in, const double *aux, double *out1, double *__restrict__ out2, double omega,
+                int flag, const CgState *state, int chk)
+{
+    ML_RETURN_IF_DONE(state, chk);
+    const int p = c0 + blockIdx.x * 128 + threadIdx.x;   // cells [c0, c1): this rank's slabs; blockIdx.y = mode class
+    if (p >= c1) return;
+    if (blockIdx.y == 0) lat_stencil_c_class<MODE, NS, MASK, 0>(g, p, Ac, Dc, in, aux, out1, out2, omega, flag);
+    else lat_stencil_c_class<MODE, NS, MASK, 1>(g, p, Ac, Dc, in, aux, out1, out2, omega, flag);
 }
 
 // A / dinv (as probed) -> Ac / Dc for the cells [c0, c1); *bad is set when an entry outside the mask is not an exact zero
@@ -1043,7 +1045,7 @@ template <int MODE, unsigned long long MASK>
 static void lat_stencil_launch_c(MlLevelBuf &L, cudaStream_t st, const double *in, const double *aux, double *out1, double *out2, double omega,
                                  int flag, const CgState *state, int chk)
 {
-    const unsigned grid = nblk((int64_t)(L.c1 - L.c0), 128);
+    const dim3 grid(nblk((int64_t)(L.c1 - L.c0), 128), 2);   // y = mode class
     if (L.g.ns == 9) k_lat_stencil_c<MODE, 9, MASK><<<grid, 128, 0, st>>>(L.g, L.c0, L.c1, L.Ac.p, L.Dc.p, in, aux, out1, out2, omega, flag, state, chk);
     else k_lat_stencil_c<MODE, 3, MASK><<<grid, 128, 0, st>>>(L.g, L.c0, L.c1, L.Ac.p, L.Dc.p, in, aux, out1, out2, omega, flag, state, chk);
 }
