@@ -1320,9 +1320,9 @@ static int lat_compact(fs_context *c, int l, bool planar_pairs)
     L.compact_kind = -1;
     const char *e = getenv("FS_ML_COMPACT");
     if (!planar_pairs || (e && e[0] == '0') || (L.g.ns != 9 && L.g.ns != 3)) return FS_OK;
-    // thread = cell pays where the stencil streams from HBM; a small level is a latency chain and runs faster with six
-    // threads per cell (c2: the 111^2 and 37^2 lattices lost 0.05 ms per visit in compact form, profiles/r02n)
-    int64_t min_cells = 32768;
+    // measured (profiles/r02x_compact_threshold.json): with two threads per cell the compacted kernel also wins on lattices
+    // that sit in L2; below a couple of thousand cells a visit is a latency chain either way
+    int64_t min_cells = 2048;
     if (const char *m = getenv("FS_ML_COMPACT_MIN_CELLS")) min_cells = std::max<int64_t>(1, atoll(m));
     if ((int64_t)(L.c1 - L.c0) < min_cells) return FS_OK;
     const size_t n = (size_t)L.g.n;
